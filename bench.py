@@ -1,0 +1,387 @@
+#!/usr/bin/env python
+"""bench.py — VEM iterations/s of the MAGMAclust hot path on B200 (contract: one JSON line on rank 0).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload C2]
+
+A "step" is one iteration of training_VEM's loop body (MAGMAclust.R:44-93) from the study's start state
+(theta_k = theta_i = (1, 1, 0.2), prior means 0, tau_0 = one-hot k-means labels): E-step, ELBO, M-step with the
+built-in L-BFGS, ELBO at the new hp, acceptance rule. Workload = BASELINE.json configs[1] ("C2": M = 1000
+individuals, K = 5, n_i = 50, individual-specific hyper-parameters) PER GPU; with N GPUs the individuals are
+sharded (weak scaling: N*1000 individuals) and the grid accumulators are all-reduced with NCCL.
+
+  value : device-resident state, CUDA-event time on the library's stream, max over ranks
+  e2e   : the same step through the host-buffer API (upload dataset + state from pinned host memory, download
+          mean/cov/tau/hp every step)
+  --impl reference : the CPU path timed on this box's host cores. R is not installed (neither here nor on the
+          GPU box), so this is the numpy restatement in oracle/ ("port"), timed on a bounded sample and
+          extrapolated to the workload (per-individual cost is linear in M, grid cost unchanged).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "VEM iterations/sec at M individuals x K clusters"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="C2", choices=["C1", "C2", "C3"])
+    ap.add_argument("--no-flush", action="store_true", help="do not evict L2 between timed steps")
+    ap.add_argument("--cpu-sample", type=int, default=48, help="individuals in the CPU baseline sample")
+    ap.add_argument("--skip-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+class Clocks:
+    """nvidia-smi sampler running during the timed region"""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.p = None
+        self.idx = gpu_index
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={self.Q}",
+                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            out, _ = self.p.communicate(timeout=5)
+        except Exception:
+            self.p.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def workload_data(name, nranks):
+    from magmaclust_b200 import synth
+    c = dict(synth.CONFIGS[name])
+    ds = synth.make_dataset(c["M"] * nranks, c["K"], c["n"], c["n_grid"], c["common_hp_i"], c["seed"])
+    return ds, c
+
+
+def start_state(M, K):
+    theta_k = np.tile(np.array([1.0, 1.0, 0.2]), (K, 1))
+    theta_i = np.tile(np.array([1.0, 1.0, 0.2]), (M, 1))
+    return theta_k, theta_i, np.zeros(K)
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_baseline(ds, cfg, sample, steps=1, warmup=0):
+    """One VEM iteration of the oracle (numpy port of the reference R code) on `sample` individuals of the
+    workload; returns seconds per iteration on the sample, split into the per-individual and the grid part, and
+    the extrapolation to the full per-GPU workload."""
+    from magmaclust_b200 import synth
+    from oracle import magma_oracle as O
+    M_full = cfg["M"]
+    K = cfg["K"]
+    sub = synth.shard(ds, 0, max(1, ds["M"] // sample))
+    n = np.diff(sub["offsets"])
+    db = {"ID": np.repeat(sub["ids"], n), "Timestamp": sub["t"], "Output": sub["y"]}
+    names = [f"K{k + 1}" for k in range(K)]
+    ids = [int(i) for i in sub["ids"]]
+    tau = {k: {i: float(sub["tau0"][r, c]) for r, i in enumerate(ids)} for c, k in enumerate(names)}
+    m_k = {k: 0.0 for k in names}
+    common_i = cfg["common_hp_i"]
+
+    def one_iteration():
+        t = {}
+        hp = {"theta_k": {k: np.array([1.0, 1.0, 0.2]) for k in names},
+              "theta_i": {i: np.array([1.0, 1.0, 0.2]) for i in ids},
+              "pi_k": np.array([np.mean(list(tau[k].values())) for k in names])}
+        t0 = time.perf_counter()
+        param = O.e_step_VEM(db, m_k, O.kernel_mu, O.kernel, hp, tau)
+        t["e_step"] = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        O.elbo_VEM(hp, db, O.kernel, O.kernel_mu, param, m_k)
+        t["elbo"] = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        st = {}
+        new_hp = O.m_step_VEM(db, hp, param, O.kernel_mu, O.kernel, m_k, True, common_i, stats=st)
+        t["m_step"] = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        O.logL_monitoring_VEM(new_hp, db, O.kernel, O.kernel_mu, param, m_k)
+        O.logL_monitoring_VEM(hp, db, O.kernel, O.kernel_mu, param, m_k)
+        t["elbo"] += time.perf_counter() - t0
+        t["nfev"] = st
+        return t
+
+    for _ in range(warmup):
+        one_iteration()
+    runs = [one_iteration() for _ in range(max(1, steps))]
+    tot = float(np.mean([r["e_step"] + r["elbo"] + r["m_step"] for r in runs]))
+    t_k = float(np.mean([r["nfev"]["t_k"] for r in runs]))   # theta_k optimiser: N x N work, independent of M
+    Ms = len(ids)
+    return {"sample_seconds_per_iteration": tot, "sample_individuals": Ms, "grid_seconds": t_k,
+            "phases": {k: float(np.mean([r[k] for r in runs])) for k in ("e_step", "elbo", "m_step")},
+            "nfev": runs[-1]["nfev"], "M_full": M_full}
+
+
+def extrapolate(b, M):
+    """per-individual loops scale linearly in M; the theta_k optimiser (N x N grid work) does not"""
+    return (b["sample_seconds_per_iteration"] - b["grid_seconds"]) * (M / b["sample_individuals"]) + b["grid_seconds"]
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    ds, cfg = workload_data(args.workload, 1)
+    cores = os.cpu_count() or 1
+    base = cpu_baseline(ds, cfg, args.cpu_sample, steps=args.steps, warmup=args.warmup)
+    M = cfg["M"] * args.gpus
+    sec = extrapolate(base, M)
+    value = M / sec  # individual-VEM-iterations per second
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "individual-VEM-iterations/s",
+        "vem_iterations_per_s": 1.0 / sec, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": f"{args.workload}: M={cfg['M']} individuals/GPU x K={cfg['K']}, n_i={cfg['n']}, "
+                               f"grid N={cfg['n_grid']}, individual-specific hp={not cfg['common_hp_i']}",
+                   "M_total": M, "K": cfg["K"]},
+        "cpu_baseline": {"value": value, "unit": "individual-VEM-iterations/s", "cores": cores, "kind": "port",
+                         "sample": f"numpy port of the reference R code (R is not installed on this box): one VEM "
+                                   f"iteration on {base['sample_individuals']} of {M} individuals "
+                                   f"({base['sample_seconds_per_iteration']:.2f} s, of which "
+                                   f"{base['grid_seconds']:.2f} s theta_k grid work); per-individual part scaled "
+                                   f"linearly in M, grid part kept",
+                         "phases_s": base["phases"], "nfev": base["nfev"]},
+        "e2e": {"value": value, "unit": "individual-VEM-iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    dist = None
+    if world > 1:
+        import torch.distributed as dist  # control plane only (id broadcast, barriers, max over ranks)
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+
+    from magmaclust_b200 import synth
+    from magmaclust_b200.engine import Engine
+
+    ds, cfg = workload_data(args.workload, world)
+    sh = synth.shard(ds, rank, world)
+    M, K, N = sh["M"], sh["K"], sh["N"]
+    eng = Engine(local)
+    if world > 1:
+        import torch
+        idt = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            idt = torch.tensor(list(Engine.comm_unique_id()), dtype=torch.uint8)
+        dist.broadcast(idt, 0)
+        eng.comm_init(world, rank, bytes(idt.tolist()))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        import torch
+        t = torch.tensor([x], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
+
+    def sum_over_ranks(x):
+        if dist is None:
+            return x
+        import torch
+        t = torch.tensor([x], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t[0])
+
+    common_i = cfg["common_hp_i"]
+    theta_k, theta_i, m_k = start_state(M, K)
+    tau0 = np.ascontiguousarray(sh["tau0"])
+    pi0 = ds["tau0"].mean(axis=0)
+    host = {"offsets": sh["offsets"], "grid_idx": sh["grid_idx"], "y": sh["y"], "grid": np.ascontiguousarray(sh["grid"]),
+            "theta_k": theta_k, "theta_i": theta_i, "pi": np.ascontiguousarray(pi0), "m_k": m_k, "tau0": tau0}
+    pinned = [a for a in host.values() if eng.pin(a)]
+
+    eng.set_data(host["offsets"], host["grid_idx"], host["y"], host["grid"], M_total=sh["M_total"])
+    peaks = eng.measure_fp64_peaks()
+
+    def step_resident():
+        eng.set_state(host["theta_k"], host["theta_i"], host["pi"], host["m_k"], host["tau0"])
+        return eng.vem_iteration(True, common_i)
+
+    # ---- value: resident dataset, CUDA events on the library stream ---------------------------------
+    for _ in range(args.warmup):
+        step_resident()
+    phase_ms = {}
+    launches = 0
+    nfev_i_sum = 0
+    nfev_k = 0
+    barrier()
+    clocks = Clocks(local)
+    eng.timer_start()
+    for _ in range(args.steps):
+        if not args.no_flush:
+            eng.flush_l2()
+        step_resident()
+        # reading the phase events costs a host sync that the step itself already paid
+        ph, nl = eng.last_timings()
+        for k, v in ph.items():
+            phase_ms[k] = phase_ms.get(k, 0.0) + v
+        launches += nl
+        st = eng.last_mstep_stats()
+        nfev_i_sum += st["nfev_i_sum"]
+        nfev_k += st["nfev_k"]
+    ms = eng.timer_stop()
+    barrier()
+    clk = clocks.stop()
+    ms = max_over_ranks(ms)
+    M_total = sh["M_total"]
+    value = M_total * args.steps / (ms / 1e3)
+
+    # ---- e2e: host buffers in, host buffers out, every step -----------------------------------------
+    out_mean = np.empty((K, N))
+    out_cov = np.empty((K, N, N))
+    out_tau = np.empty((M, K))
+    pinned += [a for a in (out_mean, out_cov, out_tau) if eng.pin(a)]
+    from magmaclust_b200._lib import dptr
+
+    def step_e2e():
+        eng.set_data(host["offsets"], host["grid_idx"], host["y"], host["grid"], M_total=sh["M_total"])
+        eng.set_state(host["theta_k"], host["theta_i"], host["pi"], host["m_k"], host["tau0"])
+        r = eng.vem_iteration(True, common_i)
+        eng._ck(eng.lib.mcb_get_mean(eng.h, dptr(out_mean)))
+        for k in range(K):
+            eng._ck(eng.lib.mcb_get_cov(eng.h, k, dptr(out_cov[k])))
+        eng._ck(eng.lib.mcb_get_tau_new(eng.h, dptr(out_tau)))
+        hp = eng.get_new_hp()
+        return r, hp
+
+    for _ in range(min(2, args.warmup)):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    eng.timer_start()
+    for _ in range(args.steps):
+        step_e2e()
+    ms_e2e = eng.timer_stop()
+    wall_e2e = (time.perf_counter() - t0) * 1e3
+    ms_e2e = max_over_ranks(max(ms_e2e, wall_e2e))
+    h2d = sum(host[k].nbytes for k in ("offsets", "grid_idx", "y", "grid", "theta_k", "theta_i", "pi", "tau0")) + 8 * K
+    d2h = out_mean.nbytes + out_cov.nbytes + out_tau.nbytes + 8 * (3 * K + 3 * M + K)
+    e2e_value = M_total * args.steps / (ms_e2e / 1e3)
+
+    # ---- roofline of the dominant kernel --------------------------------------------------------------
+    n = cfg["n"]
+    flop_fit = 5.0 * n ** 3 + 10.0 * n ** 2           # objective + gradient of one individual
+    flop_mean_eval = 5.0 * float(N) ** 3               # K^-1 (N^3) + K^-1 Csum K^-1 (4 N^3), shared theta_k
+    kernels = {}
+    if phase_ms.get("mstep_indiv", 0) > 0:
+        t = phase_ms["mstep_indiv"] / 1e3
+        kernels["indiv_mstep_kernel"] = {"ms_per_step": phase_ms["mstep_indiv"] / args.steps,
+                                         "gp_fits_per_s": nfev_i_sum / t, "tflops": nfev_i_sum * flop_fit / t / 1e12}
+    if phase_ms.get("mstep_mean", 0) > 0:
+        t = phase_ms["mstep_mean"] / 1e3
+        kernels["mean_process_evaluations"] = {"ms_per_step": phase_ms["mstep_mean"] / args.steps,
+                                               "evals_per_s": nfev_k / t, "tflops": nfev_k * flop_mean_eval / t / 1e12}
+    dom = max(kernels, key=lambda k: kernels[k]["ms_per_step"]) if kernels else None
+    peak = peaks["dfma_tflops"]
+    roofline = None
+    if dom:
+        roofline = {"kernel": dom, "bound": "fp64", "achieved": kernels[dom]["tflops"], "peak": peak, "unit": "TFLOP/s",
+                    "frac": kernels[dom]["tflops"] / peak, "traffic": None,
+                    "peak_source": "live DFMA loop on this GPU (mcb_measure_fp64_peaks); MEASURED_PEAKS.json has no "
+                                   "FP64 entry; DMMA m8n8k4 measured %.1f TFLOP/s" % peaks["dmma_tflops"],
+                    "all": kernels, "phase_ms_per_step": {k: v / args.steps for k, v in phase_ms.items()}}
+
+    gp_fits = sum_over_ranks(nfev_i_sum)
+    line = None
+    if rank == 0:
+        base = None
+        if not args.skip_cpu_baseline:
+            b = cpu_baseline(ds, cfg, args.cpu_sample)
+            sec = extrapolate(b, cfg["M"])
+            base = {"value": cfg["M"] / sec, "unit": "individual-VEM-iterations/s", "cores": os.cpu_count() or 1,
+                    "kind": "port",
+                    "sample": f"numpy port of the reference R code (no R on this box): one VEM iteration on "
+                              f"{b['sample_individuals']} of {cfg['M']} individuals took "
+                              f"{b['sample_seconds_per_iteration']:.2f} s ({b['grid_seconds']:.2f} s of it theta_k grid "
+                              f"work); per-individual part scaled linearly in M, grid part kept",
+                    "phases_s": b["phases"], "nfev": b["nfev"]}
+        line = {
+            "metric": METRIC, "value": value, "unit": "individual-VEM-iterations/s",
+            "vem_iterations_per_s": args.steps / (ms / 1e3), "gp_fits_per_s": gp_fits / (ms / 1e3),
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: M={cfg['M']} individuals/GPU x K={cfg['K']}, n_i={cfg['n']}, "
+                                   f"grid N={N}, individual-specific hp={not common_i}, common theta_k",
+                       "M_total": int(M_total), "K": K,
+                       "step": "one training_VEM loop body from the start state (E-step, ELBO, M-step L-BFGS, ELBO)",
+                       "l2": "flushed between steps (256 MiB memset on the stream, inside the timed region)"
+                             if not args.no_flush else "not flushed",
+                       "state_reset": "start state re-uploaded each step (%d B H2D, inside the timed region)" %
+                                      (theta_i.nbytes + tau0.nbytes + theta_k.nbytes)},
+            "clocks": clk, "roofline": roofline, "cpu_baseline": base,
+            "e2e": {"value": e2e_value, "unit": "individual-VEM-iterations/s", "ms_per_step": ms_e2e / args.steps,
+                    "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "pinned_host_buffers": len(pinned)},
+            "gpu_launches": int(launches),
+            "mstep_evals_per_step": {"theta_i_total": nfev_i_sum / args.steps, "theta_k": nfev_k / args.steps},
+        }
+        print(json.dumps(line))
+    for a in pinned:
+        eng.unpin(a)
+    eng.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    a = parse()
+    sys.exit(run_reference(a) if a.impl == "reference" else run_ours(a))

@@ -1,0 +1,177 @@
+/* mcb.h — C ABI of libmagmaclust_b200.so: the B200 (sm_100a) implementation of MAGMAclust's
+ * variational-EM hot path. Plain C, plain pointers and sizes; no torch / R types cross this boundary.
+ *
+ * The reference (ArthurLeroy/MAGMAclust) has no native interface at all: its "operator API" is a set of R
+ * closures in a flat namespace. Each entry point below names the R function(s) it replaces
+ * (CF.R = Computing_functions.R, MC.R = MAGMAclust.R, line numbers into /root/reference). INTEGRATION.md
+ * shows the `.Call` shim and the ctypes binding over exactly these symbols.
+ *
+ * Conventions
+ *   - All reals are FP64. All matrices are dense, row-major, and symmetric where the maths says so (so
+ *     R's column-major view is identical).
+ *   - The training set is canonicalised ONCE into a CSR-like layout (replaces the tibble `db` with columns
+ *     ID, Timestamp, Output and the string-named matrices of CF.R:83,146):
+ *         grid[N]        sorted unique timestamps over all individuals  (all_t, CF.R:601)
+ *         offsets[M+1]   rows of individual i are [offsets[i], offsets[i+1])
+ *         grid_idx[P]    position of each row's timestamp in grid[]      (match(Timestamp, all_t) - 1)
+ *         y[P]           outputs
+ *     Rows of one individual must be sorted by timestamp and unique (the reference silently assumes it,
+ *     SURVEY.md §8.0 Q2).
+ *   - Individuals are positional (order of unique(db$ID)); clusters are positional (order of names(m_k)).
+ *   - theta_i is [M][3] = (log variance, log lengthscale^2, noise sd), theta_k is [K][3] with theta_k[.][2]
+ *     the jitter sd ("pen_diag", CF.R:662); tau is [M][K] (row i = individual).
+ *   - Return value: 0 ok; <0 invalid argument / state; >0 CUDA, NCCL or numerical failure. Nothing throws
+ *     or exits across the ABI; mcb_last_error() gives the text. Where the reference silently switches to
+ *     MASS::ginv on a singular matrix (CF.R:142,177,612), this library reports MCB_ENOTPD instead.
+ *   - There is no CPU fallback: every compute entry point needs a CUDA device.
+ */
+#ifndef MCB_H
+#define MCB_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mcb_handle mcb_handle;
+
+enum {
+  MCB_OK = 0,
+  MCB_EINVAL = -1,   /* bad argument */
+  MCB_ESTATE = -2,   /* call sequence error (e.g. E-step before data upload) */
+  MCB_ECUDA = 1,     /* CUDA runtime error */
+  MCB_ENOTPD = 2,    /* a covariance matrix was not positive definite (non-positive pivot) */
+  MCB_ENCCL = 3,     /* NCCL error / NCCL not loadable */
+  MCB_ENOMEM = 4
+};
+
+/* ---- lifetime ------------------------------------------------------------------------------------- */
+int mcb_version(void);
+int mcb_device_count(void);                       /* 0 when no CUDA device is usable */
+int mcb_create(mcb_handle** out, int device);     /* binds the handle to one GPU, creates its streams */
+void mcb_destroy(mcb_handle* h);
+const char* mcb_last_error(const mcb_handle* h);  /* NULL handle -> last creation error */
+
+/* ---- multi-GPU: individuals are sharded over ranks; grid accumulators are all-reduced (NCCL) -------- */
+/* One process per GPU. Rank 0 calls mcb_comm_unique_id and ships the 128 bytes to the other ranks by any
+ * out-of-band channel; every rank then calls mcb_comm_init. After that, every mcb_* call that contains a
+ * reduction (E-step accumulators, common-hp objectives, ELBO, pi_k) is collective over the ranks. */
+int mcb_comm_unique_id(unsigned char out_id[128]);
+int mcb_comm_init(mcb_handle* h, int nranks, int rank, const unsigned char id[128]);
+
+/* ---- data ----------------------------------------------------------------------------------------- */
+/* Upload the (local shard of the) training set. M_total = number of individuals over all ranks (== M when
+ * single-GPU); it is the denominator of pi_k = mean_i tau_ik (CF.R:682). */
+int mcb_set_data(mcb_handle* h, int M, int N, long long P, const int* offsets, const int* grid_idx,
+                 const double* y, const double* grid, long long M_total);
+
+/* ---- model state (device resident between calls) --------------------------------------------------- */
+/* m_k: prior means of the mean processes, m_k_len == K (scalar per cluster, CF.R:718) or K*N. */
+int mcb_set_state(mcb_handle* h, int K, const double* theta_k, const double* theta_i, const double* pi_k,
+                  const double* m_k, int m_k_len, const double* tau);
+int mcb_get_hp(mcb_handle* h, double* theta_k, double* theta_i, double* pi_k);
+int mcb_get_tau(mcb_handle* h, double* tau);             /* the tau the next E-step will use as "old" */
+
+/* ---- E-step: e_step_VEM (CF.R:589-629) = kern_to_inv (CF.R:123-191) + update_inv_VEM (CF.R:690-707)
+ *      + update_mean_VEM (CF.R:709-731) + solve (CF.R:612) + update_tau_i_k_VEM (CF.R:733-762) --------- */
+/* Runs on the resident state. Results stay on the device (hyper-posterior mean[K][N], cov[K][N][N], new
+ * tau[M][K], log-likelihood matrix mat_logL[M][K]) and are fetched with the getters below. */
+int mcb_e_step(mcb_handle* h);
+int mcb_get_mean(mcb_handle* h, double* mean /* [K][N] */);
+int mcb_get_cov(mcb_handle* h, int k, double* cov /* [N][N] */);
+int mcb_get_tau_new(mcb_handle* h, double* tau /* [M][K] */);
+int mcb_get_mat_logL(mcb_handle* h, double* logL /* [M][K] */);
+int mcb_get_logdet_cov(mcb_handle* h, double* logdet /* [K] : log det C_k (finite; see MC.R:53 / Q8) */);
+/* tau <- tau_new (MC.R:90) */
+int mcb_accept_tau(mcb_handle* h);
+
+/* Host-buffer convenience = one call per reference call; what the `.Call` shim binds for e_step_VEM.
+ * Any output pointer may be NULL. cov is [K][N][N]. */
+int mcb_e_step_VEM(mcb_handle* h, int K, const double* theta_k, const double* theta_i, const double* pi_k,
+                   const double* m_k, int m_k_len, const double* old_tau, double* out_mean, double* out_cov,
+                   double* out_tau, double* out_mat_logL);
+
+/* Install an explicit hyper-posterior — the `mu_k_param` / `list_mu_param` / `new_cov` arguments of the
+ * reference's callbacks (CF.R:218, 280, 327, 631) — instead of the one left by the last E-step:
+ * mean[K][N], cov[K][N][N], tau[M][K] (host). Evaluated against the resident hp. */
+int mcb_set_posterior(mcb_handle* h, const double* mean, const double* cov, const double* tau);
+
+/* ---- M-step objectives and gradients (the optimiser callbacks of CF.R:647-677) ----------------------- */
+/* All evaluate against the hyper-posterior (mean, cov, tau_new) left on the device by the last E-step.
+ * Individuals: F_i(theta) of logL_clust_multi_GP (CF.R:218-248) and its gradient gr_clust_multi_GP
+ * (CF.R:477-508). theta is [M][3] (one row per individual) -> f[M], g[M][3]; g may be NULL. */
+int mcb_eval_indiv(mcb_handle* h, const double* theta /* [M][3] */, double* f, double* g);
+/* Shared theta_i: logL_clust_multi_GP_common_hp_i (CF.R:280-325) / gr_..._common_hp_i (CF.R:539-586):
+ * sum over ALL individuals (all ranks) at one theta[3] -> f[1], g[3]. */
+int mcb_eval_indiv_common(mcb_handle* h, const double* theta /* [3] */, double* f, double* g);
+/* Mean processes: logL_GP_mod (CF.R:194-216) / gr_GP_mod (CF.R:448-475) for cluster k with nhp = 2
+ * (theta = (a, b), sigma = pen_diag) or nhp = 3 (theta = (a, b, sigma)); g has nhp entries. */
+int mcb_eval_mean(mcb_handle* h, int k, const double* theta, int nhp, double pen_diag, double* f, double* g);
+/* Shared theta_k: logL_GP_mod_common_hp_k (CF.R:250-278) / gr_GP_mod_common_hp_k (CF.R:510-537). */
+int mcb_eval_mean_common(mcb_handle* h, const double* theta, int nhp, double pen_diag, double* f, double* g);
+
+/* ---- ELBO monitor: logL_monitoring_VEM (CF.R:327-352) + 0.5*(K*N + sum_k log det C_k) (MC.R:51-53) ----- */
+/* Evaluated at the given hp against the resident hyper-posterior. out[0] = logL_monitoring_VEM value,
+ * out[1] = the MC.R:51-53 total (finite log-determinants). theta_* NULL -> use the resident hp. */
+int mcb_elbo(mcb_handle* h, const double* theta_k, const double* theta_i, double out[2]);
+
+/* ---- built-in M-step: m_step_VEM (CF.R:631-687) with the L-BFGS of csrc/lbfgs.h -------------------- */
+/* Optimises theta_i (one batched on-device L-BFGS per individual, or one shared), then theta_k, then
+ * pi_k = mean_i tau_ik. Writes the NEW hp to new_* (host, may be NULL) and keeps them as "candidate" on the
+ * device; mcb_accept_hp() makes them current (MC.R:85,89). stats[0..3] = #objective evaluations for
+ * theta_i (max over individuals), theta_k, and the two optimisers' iteration counts. */
+int mcb_m_step(mcb_handle* h, int common_hp_k, int common_hp_i, double* new_theta_k, double* new_theta_i,
+               double* new_pi_k, int* stats);
+int mcb_accept_hp(mcb_handle* h);
+/* the last M-step's candidate (training_VEM returns hp = new_hp even when it was not accepted, MC.R:95) */
+int mcb_get_new_hp(mcb_handle* h, double* theta_k, double* theta_i, double* pi_k);
+
+/* ---- one VEM iteration = the loop body of training_VEM (MC.R:44-93) ---------------------------------- */
+/* E-step, ELBO(hp), M-step, eps = (L(new_hp) - L(hp)) / |L(new_hp)|, acceptance rule of MC.R:83-90.
+ * out[0] = ELBO total appended to logL_iterations (MC.R:77), out[1] = eps, out[2] = 1 if converged. */
+int mcb_vem_iteration(mcb_handle* h, int common_hp_k, int common_hp_i, double out[3]);
+
+/* ---- prediction -------------------------------------------------------------------------------------- */
+/* posterior_mu_k (MC.R:196-233): hyper-posterior on a prediction grid `timestamps[T]` (sorted, must
+ * contain every training timestamp) with theta_k[.][2] := 0.1 (MC.R:206), the resident hp and a frozen
+ * tau[M][K] (NULL: param$tau_i_k of the last E-step, MC.R:208). The result stays resident as the
+ * "prediction posterior" (mean_p[K][T], cov_p[K][T][T]); out_mean / out_cov may be NULL. */
+int mcb_posterior_mu_k(mcb_handle* h, int T, const double* timestamps, const double* tau, double* out_mean,
+                       double* out_cov);
+/* Batched new individuals against the prediction posterior:
+ *   update_tau_star_k_EM (CF.R:764-786) -> out_tau[B][K]
+ *   pred_gp_clust (MC.R:235-274)        -> out_mean[B][K][Tp], out_var[B][K][Tp]
+ * new individuals in CSR (offsets[B+1], obs_idx = positions in the prediction grid, y), shared theta_new[3]
+ * (train_new_gp_EM fixed-hp branch, MC.R:187-191), targets pred_idx[Tp] = positions in the prediction grid.
+ * pi_k[K]: mixing proportions (NULL: mean_i tau_ik of the tau frozen in mcb_posterior_mu_k, MC.R:141).
+ * out_mean/out_var may both be NULL (tau only). At most 64 observations per new individual. */
+int mcb_predict(mcb_handle* h, int B, const int* offsets, const int* obs_idx, const double* y,
+                const double* theta_new, const double* pi_k, int Tp, const int* pred_idx, double* out_tau,
+                double* out_mean, double* out_var);
+
+/* ---- measurement helpers ----------------------------------------------------------------------------- */
+/* Device time (ms, CUDA events on the handle's stream) of the kernels launched by the last compute call,
+ * per phase: [0] per-individual E-step kernel, [1] dense hyper-posterior, [2] tau kernel, [3] M-step
+ * individuals, [4] M-step mean processes, [5] ELBO, [6] prediction, [7] collectives. Also the number of
+ * kernel launches of the last call. */
+int mcb_last_timings(mcb_handle* h, float ms[8], long long* launches);
+/* Counters of the last M-step: out[0] max #evaluations per individual optimiser, out[1] #evaluations of the
+ * theta_k optimiser(s), out[2], out[3] the iteration counts, out[4] total individual objective+gradient
+ * evaluations on this rank, out[5] number of local individuals. */
+int mcb_last_mstep_stats(mcb_handle* h, long long out[6]);
+/* Page-lock / release a host buffer (cudaHostRegister) so that the copies of the host-buffer entry points run
+ * from pinned memory. */
+int mcb_pin_host(void* ptr, size_t bytes);
+int mcb_unpin_host(void* ptr);
+/* CUDA-event stopwatch on the handle's stream (the stream every kernel of this library is launched on):
+ * start synchronises and records; stop records, synchronises and returns the elapsed device time. */
+int mcb_timer_start(mcb_handle* h);
+int mcb_timer_stop(mcb_handle* h, float* ms);
+/* Evict the working set from L2 between timed steps: writes a 256 MiB scratch buffer on the stream. */
+int mcb_flush_l2(mcb_handle* h);
+/* FP64 roofline denominators measured on this GPU: out[0] DFMA TFLOP/s, out[1] DMMA m8n8k4 TFLOP/s. */
+int mcb_measure_fp64_peaks(mcb_handle* h, double out[2]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MCB_H */

@@ -1,0 +1,944 @@
+// C ABI of libmagmaclust_b200.so (see include/mcb.h): handle lifetime, data/state upload, and the host
+// orchestration of the E-step (CF.R:589-629), the M-step objective/gradient evaluators (CF.R:194-325,
+// 448-586), the ELBO monitor (CF.R:327-352, MC.R:51-53), the built-in M-step (CF.R:631-687) and one
+// iteration of training_VEM's loop (MC.R:44-93).
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "handle.h"
+#include "lbfgs.h"
+
+using namespace mcb;
+
+static std::string g_create_err;
+
+#define H_CUDA(expr) MCB_CUDA(h, expr)
+static inline cudaError_t sync_copy(mcb_handle* h, void* dst, const void* src, size_t bytes, cudaMemcpyKind kind) {
+  cudaError_t e = cudaMemcpyAsync(dst, src, bytes, kind, h->st);
+  return e != cudaSuccess ? e : cudaStreamSynchronize(h->st);
+}
+static inline cudaError_t sync_copy2d(mcb_handle* h, void* dst, size_t dpitch, const void* src, size_t spitch,
+                                      size_t width, size_t height, cudaMemcpyKind kind) {
+  cudaError_t e = cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, height, kind, h->st);
+  return e != cudaSuccess ? e : cudaStreamSynchronize(h->st);
+}
+#define H_CHECK(cond, code, text) \
+  do {                            \
+    if (!(cond)) {                \
+      h->err = (text);            \
+      return (code);              \
+    }                             \
+  } while (0)
+
+// ---- timing spans ------------------------------------------------------------------------------------
+static void spans_reset(mcb_handle* h) {
+  h->spans.clear();
+  h->ev_next = 0;
+  h->launches = 0;
+}
+static int ev_get(mcb_handle* h) {
+  if (h->ev_next == (int)h->evpool.size()) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    h->evpool.push_back(e);
+  }
+  return h->ev_next++;
+}
+struct PhaseScope {
+  mcb_handle* h;
+  int phase, e0;
+  PhaseScope(mcb_handle* h_, int ph) : h(h_), phase(ph) {
+    e0 = ev_get(h);
+    cudaEventRecord(h->evpool[e0], h->st);
+  }
+  ~PhaseScope() {
+    int e1 = ev_get(h);
+    cudaEventRecord(h->evpool[e1], h->st);
+    h->spans.push_back({phase, e0, e1});
+  }
+};
+
+// ---- lifetime ----------------------------------------------------------------------------------------
+extern "C" int mcb_version(void) { return 100; }
+
+extern "C" int mcb_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+extern "C" int mcb_create(mcb_handle** out, int device) {
+  if (!out) return MCB_EINVAL;
+  *out = nullptr;
+  int n = mcb_device_count();
+  if (n <= 0) {
+    g_create_err = "no CUDA device available (this library has no CPU fallback)";
+    return MCB_ECUDA;
+  }
+  if (device < 0 || device >= n) {
+    g_create_err = "device index out of range";
+    return MCB_EINVAL;
+  }
+  cudaError_t e = cudaSetDevice(device);
+  if (e != cudaSuccess) {
+    g_create_err = cudaGetErrorString(e);
+    return MCB_ECUDA;
+  }
+  mcb_handle* h = new mcb_handle();
+  h->device = device;
+  if ((e = cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking)) != cudaSuccess ||
+      (e = cudaMallocHost(&h->hbuf, sizeof(double) * mcb_handle::kHbuf)) != cudaSuccess ||
+      (e = h->info.ensure(4)) != cudaSuccess || (e = h->scal.ensure(64)) != cudaSuccess) {
+    g_create_err = cudaGetErrorString(e);
+    delete h;
+    return MCB_ECUDA;
+  }
+  cudaMemset(h->info.p, 0, sizeof(int) * 4);
+  *out = h;
+  return MCB_OK;
+}
+
+extern "C" void mcb_destroy(mcb_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->st);
+  comm_destroy(h);
+  for (auto e : h->evpool) cudaEventDestroy(e);
+  mcb::DevBuf<double>* dbl[] = {&h->t, &h->y, &h->grid, &h->theta_i, &h->theta_k, &h->pi, &h->mk, &h->tau,
+                                &h->theta_i_new, &h->theta_k_new, &h->pi_new, &h->tau_new, &h->logL, &h->Winv,
+                                &h->pvec, &h->yWy, &h->logdet_i, &h->c1, &h->c2, &h->Fi, &h->fi_tmp, &h->gi_tmp,
+                                &h->theta_g, &h->Kinv, &h->cov, &h->wk, &h->mean, &h->rvec, &h->pz, &h->logdetK,
+                                &h->logdetA, &h->eK, &h->eD1, &h->eD2, &h->eCsum, &h->eX, &h->etheta, &h->ered,
+                                &h->elogdet, &h->ws.Pbuf, &h->ws.Cold, &h->ws.red, &h->scal, &h->pgrid, &h->pKinv,
+                                &h->pcov, &h->pwk, &h->pmean, &h->plogdet};
+  for (auto* b : dbl) b->release();
+  mcb::DevBuf<int>* ints[] = {&h->off, &h->gidx, &h->nfev_i, &h->niter_i, &h->status_i, &h->gmap_d, &h->egmap,
+                              &h->info, &h->pmapidx};
+  for (auto* b : ints) b->release();
+  h->woff.release();
+  h->flush.release();
+  if (h->tm0) { cudaEventDestroy(h->tm0); cudaEventDestroy(h->tm1); }
+  if (h->hbuf) cudaFreeHost(h->hbuf);
+  if (h->st) cudaStreamDestroy(h->st);
+  delete h;
+}
+
+extern "C" const char* mcb_last_error(const mcb_handle* h) { return h ? h->err.c_str() : g_create_err.c_str(); }
+
+// ---- data --------------------------------------------------------------------------------------------
+extern "C" int mcb_set_data(mcb_handle* h, int M, int N, long long P, const int* offsets, const int* grid_idx,
+                            const double* y, const double* grid, long long M_total) {
+  if (!h) return MCB_EINVAL;
+  H_CHECK(M > 0 && N > 0 && P > 0 && offsets && grid_idx && y && grid, MCB_EINVAL, "mcb_set_data: bad argument");
+  H_CHECK(offsets[0] == 0 && offsets[M] == P, MCB_EINVAL, "mcb_set_data: offsets must span [0, P]");
+  H_CHECK(M_total >= M, MCB_EINVAL, "mcb_set_data: M_total < M");
+  for (int j = 1; j < N; ++j) H_CHECK(grid[j] > grid[j - 1], MCB_EINVAL, "mcb_set_data: grid must be sorted and unique");
+  std::vector<long long> woff(M + 1, 0);
+  std::vector<double> t((size_t)P);
+  int nmax = 0;
+  for (int i = 0; i < M; ++i) {
+    const int n = offsets[i + 1] - offsets[i];
+    H_CHECK(n >= 1, MCB_EINVAL, "mcb_set_data: empty individual");
+    nmax = std::max(nmax, n);
+    woff[i + 1] = woff[i] + (long long)n * n;
+    for (int a = offsets[i]; a < offsets[i + 1]; ++a) {
+      H_CHECK(grid_idx[a] >= 0 && grid_idx[a] < N, MCB_EINVAL, "mcb_set_data: grid_idx out of range");
+      H_CHECK(a == offsets[i] || grid_idx[a] > grid_idx[a - 1], MCB_EINVAL,
+              "mcb_set_data: rows of an individual must be sorted by timestamp and unique");
+      t[a] = grid[grid_idx[a]];
+    }
+  }
+  H_CHECK(eval_smem_bytes(nmax) <= 227 * 1024, MCB_EINVAL,
+          "mcb_set_data: an individual has too many observations for the shared-memory path (n_i <= ~115)");
+  H_CUDA(cudaSetDevice(h->device));
+  h->K = 0;  // forces the state buffers to be re-sized for the new N
+  h->M = M; h->N = N; h->ld = (N + 3) & ~3; h->P = P; h->nmax = nmax; h->M_total = M_total; h->W2 = woff[M];
+  H_CUDA(h->off.ensure(M + 1)); H_CUDA(h->gidx.ensure(P)); H_CUDA(h->woff.ensure(M + 1));
+  H_CUDA(h->t.ensure(P)); H_CUDA(h->y.ensure(P)); H_CUDA(h->grid.ensure(N));
+  H_CUDA(cudaMemcpyAsync(h->off.p, offsets, sizeof(int) * (M + 1), cudaMemcpyHostToDevice, h->st));
+  H_CUDA(cudaMemcpyAsync(h->gidx.p, grid_idx, sizeof(int) * P, cudaMemcpyHostToDevice, h->st));
+  H_CUDA(cudaMemcpyAsync(h->woff.p, woff.data(), sizeof(long long) * (M + 1), cudaMemcpyHostToDevice, h->st));
+  H_CUDA(cudaMemcpyAsync(h->t.p, t.data(), sizeof(double) * P, cudaMemcpyHostToDevice, h->st));
+  H_CUDA(cudaMemcpyAsync(h->y.p, y, sizeof(double) * P, cudaMemcpyHostToDevice, h->st));
+  H_CUDA(cudaMemcpyAsync(h->grid.p, grid, sizeof(double) * N, cudaMemcpyHostToDevice, h->st));
+  H_CUDA(h->Winv.ensure(h->W2)); H_CUDA(h->c2.ensure(h->W2));
+  H_CUDA(h->pvec.ensure(P)); H_CUDA(h->c1.ensure(P));
+  H_CUDA(h->yWy.ensure(M)); H_CUDA(h->logdet_i.ensure(M)); H_CUDA(h->Fi.ensure(M));
+  H_CUDA(h->fi_tmp.ensure(M)); H_CUDA(h->gi_tmp.ensure(3 * (size_t)M));
+  H_CUDA(h->nfev_i.ensure(M)); H_CUDA(h->niter_i.ensure(M)); H_CUDA(h->status_i.ensure(M));
+  H_CUDA(h->theta_i.ensure(3 * (size_t)M)); H_CUDA(h->theta_i_new.ensure(3 * (size_t)M));
+  H_CUDA(cudaStreamSynchronize(h->st));  // host vectors go out of scope
+  h->has_data = true; h->has_state = false; h->has_post = false; h->has_cand = false; h->has_pred = false;
+  return MCB_OK;
+}
+
+// ---- state -------------------------------------------------------------------------------------------
+static int alloc_state(mcb_handle* h, int K) {
+  const size_t KN = (size_t)K * h->ld, KNN = (size_t)K * h->N * h->ld;
+  H_CUDA(h->theta_k.ensure(3 * K)); H_CUDA(h->theta_k_new.ensure(3 * K));
+  H_CUDA(h->pi.ensure(K)); H_CUDA(h->pi_new.ensure(K));
+  H_CUDA(h->mk.ensure(KN)); H_CUDA(h->wk.ensure(KN)); H_CUDA(h->mean.ensure(KN));
+  H_CUDA(h->rvec.ensure(KN)); H_CUDA(h->pz.ensure(KN));
+  H_CUDA(h->tau.ensure((size_t)h->M * K)); H_CUDA(h->tau_new.ensure((size_t)h->M * K));
+  H_CUDA(h->logL.ensure((size_t)h->M * K));
+  H_CUDA(h->Kinv.ensure(KNN)); H_CUDA(h->cov.ensure(KNN));
+  H_CUDA(h->logdetK.ensure(K)); H_CUDA(h->logdetA.ensure(K));
+  H_CUDA(h->gmap_d.ensure(K)); H_CUDA(h->theta_g.ensure(3 * K));
+  H_CUDA(h->eK.ensure(KNN)); H_CUDA(h->eD1.ensure(KNN)); H_CUDA(h->eD2.ensure(KNN));
+  H_CUDA(h->eCsum.ensure(KNN)); H_CUDA(h->eX.ensure(KNN));
+  H_CUDA(h->etheta.ensure(3 * K)); H_CUDA(h->ered.ensure(16 * (size_t)K)); H_CUDA(h->elogdet.ensure(K));
+  H_CUDA(h->egmap.ensure(K));
+  return MCB_OK;
+}
+
+extern "C" int mcb_set_state(mcb_handle* h, int K, const double* theta_k, const double* theta_i,
+                             const double* pi_k, const double* m_k, int m_k_len, const double* tau) {
+  if (!h) return MCB_EINVAL;
+  H_CHECK(h->has_data, MCB_ESTATE, "mcb_set_state: call mcb_set_data first");
+  H_CHECK(K >= 1 && theta_k && theta_i && pi_k && m_k && tau, MCB_EINVAL, "mcb_set_state: bad argument");
+  H_CHECK(m_k_len == K || m_k_len == K * h->N, MCB_EINVAL, "mcb_set_state: m_k_len must be K or K*N");
+  H_CUDA(cudaSetDevice(h->device));
+  if (K != h->K) {
+    MCB_TRY(alloc_state(h, K));
+    h->K = K;
+  }
+  const int N = h->N, ld = h->ld, M = h->M;
+  std::vector<double> mk((size_t)K * ld, 0.0);
+  for (int k = 0; k < K; ++k)
+    for (int j = 0; j < N; ++j) mk[(size_t)k * ld + j] = (m_k_len == K) ? m_k[k] : m_k[(size_t)k * N + j];
+  H_CUDA(cudaMemcpyAsync(h->theta_k.p, theta_k, sizeof(double) * 3 * K, cudaMemcpyHostToDevice, h->st));
+  H_CUDA(cudaMemcpyAsync(h->theta_i.p, theta_i, sizeof(double) * 3 * M, cudaMemcpyHostToDevice, h->st));
+  H_CUDA(cudaMemcpyAsync(h->pi.p, pi_k, sizeof(double) * K, cudaMemcpyHostToDevice, h->st));
+  H_CUDA(cudaMemcpyAsync(h->mk.p, mk.data(), sizeof(double) * K * ld, cudaMemcpyHostToDevice, h->st));
+  H_CUDA(cudaMemcpyAsync(h->tau.p, tau, sizeof(double) * (size_t)M * K, cudaMemcpyHostToDevice, h->st));
+  H_CUDA(cudaStreamSynchronize(h->st));
+  h->h_theta_k.assign(theta_k, theta_k + 3 * K);
+  h->h_pi.assign(pi_k, pi_k + K);
+  h->has_state = true; h->has_post = false; h->has_cand = false;
+  return MCB_OK;
+}
+
+extern "C" int mcb_get_hp(mcb_handle* h, double* theta_k, double* theta_i, double* pi_k) {
+  if (!h) return MCB_EINVAL;
+  H_CHECK(h->has_state, MCB_ESTATE, "mcb_get_hp: no state");
+  H_CUDA(cudaSetDevice(h->device));
+  if (theta_k) H_CUDA(cudaMemcpyAsync(theta_k, h->theta_k.p, sizeof(double) * 3 * h->K, cudaMemcpyDeviceToHost, h->st));
+  if (theta_i) H_CUDA(cudaMemcpyAsync(theta_i, h->theta_i.p, sizeof(double) * 3 * h->M, cudaMemcpyDeviceToHost, h->st));
+  if (pi_k) H_CUDA(cudaMemcpyAsync(pi_k, h->pi.p, sizeof(double) * h->K, cudaMemcpyDeviceToHost, h->st));
+  H_CUDA(cudaStreamSynchronize(h->st));
+  return MCB_OK;
+}
+
+extern "C" int mcb_get_new_hp(mcb_handle* h, double* theta_k, double* theta_i, double* pi_k) {
+  if (!h) return MCB_EINVAL;
+  H_CHECK(h->has_cand, MCB_ESTATE, "mcb_get_new_hp: no M-step candidate");
+  H_CUDA(cudaSetDevice(h->device));
+  if (theta_k) memcpy(theta_k, h->h_theta_k_new.data(), sizeof(double) * 3 * h->K);
+  if (pi_k) memcpy(pi_k, h->h_pi_new.data(), sizeof(double) * h->K);
+  if (theta_i) {
+    H_CUDA(cudaMemcpyAsync(theta_i, h->theta_i_new.p, sizeof(double) * 3 * h->M, cudaMemcpyDeviceToHost, h->st));
+    H_CUDA(cudaStreamSynchronize(h->st));
+  }
+  return MCB_OK;
+}
+
+extern "C" int mcb_get_tau(mcb_handle* h, double* tau) {
+  if (!h || !tau) return MCB_EINVAL;
+  H_CHECK(h->has_state, MCB_ESTATE, "mcb_get_tau: no state");
+  H_CUDA(cudaSetDevice(h->device));
+  H_CUDA(cudaMemcpyAsync(tau, h->tau.p, sizeof(double) * (size_t)h->M * h->K, cudaMemcpyDeviceToHost, h->st));
+  H_CUDA(cudaStreamSynchronize(h->st));
+  return MCB_OK;
+}
+
+// ---- helpers -----------------------------------------------------------------------------------------
+// distinct rows of theta[K][3] -> gmap, returns G and fills groups[G][3]
+static int group_theta(const double* theta, int K, std::vector<int>& gmap, std::vector<double>& groups) {
+  gmap.assign(K, -1);
+  groups.clear();
+  int G = 0;
+  for (int k = 0; k < K; ++k) {
+    for (int g = 0; g < G; ++g)
+      if (groups[3 * g] == theta[3 * k] && groups[3 * g + 1] == theta[3 * k + 1] && groups[3 * g + 2] == theta[3 * k + 2]) {
+        gmap[k] = g;
+        break;
+      }
+    if (gmap[k] < 0) {
+      gmap[k] = G++;
+      groups.insert(groups.end(), theta + 3 * k, theta + 3 * k + 3);
+    }
+  }
+  return G;
+}
+
+static int check_info(mcb_handle* h, const char* where) {
+  int flag = 0;
+  H_CUDA(cudaMemcpyAsync(&flag, h->info.p, sizeof(int), cudaMemcpyDeviceToHost, h->st));
+  H_CUDA(cudaStreamSynchronize(h->st));
+  if (flag) {
+    cudaMemsetAsync(h->info.p, 0, sizeof(int), h->st);
+    h->err = std::string(where) + ": a covariance matrix is not positive definite (non-positive pivot); "
+             "the reference would silently fall back to MASS::ginv here";
+    return MCB_ENOTPD;
+  }
+  return MCB_OK;
+}
+
+// MCB_DEBUG=1: check the not-positive-definite flag after every stage (adds host syncs)
+static int dbg_stage(mcb_handle* h, const char* stage) {
+  static const bool on = getenv("MCB_DEBUG") != nullptr;
+  return on ? check_info(h, stage) : MCB_OK;
+}
+
+// ---- E-step ------------------------------------------------------------------------------------------
+static int e_step_impl(mcb_handle* h) {
+  const int M = h->M, N = h->N, ld = h->ld, K = h->K;
+  const long long sN = (long long)N * ld;
+  std::vector<double> groups;
+  h->G = group_theta(h->h_theta_k.data(), K, h->gmap, groups);
+  const int G = h->G;
+  H_CUDA(cudaMemcpyAsync(h->gmap_d.p, h->gmap.data(), sizeof(int) * K, cudaMemcpyHostToDevice, h->st));
+  H_CUDA(cudaMemcpyAsync(h->theta_g.p, groups.data(), sizeof(double) * 3 * G, cudaMemcpyHostToDevice, h->st));
+  {
+    PhaseScope ps(h, PH_DENSE);
+    // K_k^-1 for each distinct theta_k (CF.R:604)
+    se_build(h->st, h->Kinv.p, nullptr, nullptr, N, ld, sN, h->grid.p, h->theta_g.p, 3, G, &h->launches);
+    H_CUDA(spd_inverse(h->st, h->Kinv.p, N, ld, sN, G, h->logdetK.p, h->info.p, h->ws, &h->launches));
+    MCB_TRY(dbg_stage(h, "e_step: solve(K_k)"));
+    // A_k starts as K_k^-1 (rank 0 only when sharded: the all-reduce adds it exactly once), w_k as K_k^-1 m_k
+    copy_mapped(h->st, N, ld, sN, h->Kinv.p, h->gmap_d.p, h->cov.p, K, h->rank == 0 ? 1.0 : 0.0, &h->launches);
+    if (h->rank == 0) symv_mapped(h->st, N, ld, sN, h->Kinv.p, h->gmap_d.p, h->mk.p, h->wk.p, K, &h->launches);
+    else H_CUDA(cudaMemsetAsync(h->wk.p, 0, sizeof(double) * K * ld, h->st));
+  }
+  {
+    PhaseScope ps(h, PH_INDIV);
+    H_CUDA(launch_factor_scatter(h->st, h->idata(), M, h->nmax, h->theta_i.p, h->tau.p, K, h->cov.p, ld, sN,
+                                 h->wk.p, h->iwork(), h->info.p));
+    ++h->launches;
+    MCB_TRY(dbg_stage(h, "e_step: solve(Psi_i)"));
+  }
+  if (h->nranks > 1) {
+    PhaseScope ps(h, PH_COMM);
+    MCB_TRY(comm_allreduce_sum(h, h->cov.p, (size_t)K * sN));
+    MCB_TRY(comm_allreduce_sum(h, h->wk.p, (size_t)K * ld));
+  }
+  {
+    PhaseScope ps(h, PH_DENSE);
+    // C_k = A_k^-1 (CF.R:612), m_k = C_k w_k (CF.R:620)
+    H_CUDA(spd_inverse(h->st, h->cov.p, N, ld, sN, K, h->logdetA.p, h->info.p, h->ws, &h->launches));
+    symv(h->st, N, h->cov.p, ld, sN, h->wk.p, ld, h->mean.p, ld, K, &h->launches);
+    vec_sub(h->st, K * ld, h->mean.p, h->mk.p, h->rvec.p, &h->launches);
+  }
+  {
+    PhaseScope ps(h, PH_TAU);
+    H_CUDA(launch_tau(h->st, h->idata(), M, h->nmax, K, h->mean.p, h->cov.p, ld, sN, h->pi.p, h->iwork(),
+                      h->tau_new.p, h->logL.p, 0));
+    ++h->launches;
+  }
+  H_CUDA(cudaMemcpyAsync(h->hbuf, h->logdetK.p, sizeof(double) * G, cudaMemcpyDeviceToHost, h->st));
+  H_CUDA(cudaMemcpyAsync(h->hbuf + K, h->logdetA.p, sizeof(double) * K, cudaMemcpyDeviceToHost, h->st));
+  MCB_TRY(check_info(h, "e_step_VEM"));
+  h->h_logdetK.assign(h->hbuf, h->hbuf + G);
+  h->h_logdetA.assign(h->hbuf + K, h->hbuf + 2 * K);
+  h->has_post = true;
+  h->csum_valid = false;
+  return MCB_OK;
+}
+
+extern "C" int mcb_e_step(mcb_handle* h) {
+  if (!h) return MCB_EINVAL;
+  H_CHECK(h->has_state, MCB_ESTATE, "mcb_e_step: call mcb_set_data and mcb_set_state first");
+  H_CUDA(cudaSetDevice(h->device));
+  spans_reset(h);
+  return e_step_impl(h);
+}
+
+static int copy_rows(mcb_handle* h, double* dst, const double* src, int rows, int N, int ld) {
+  H_CUDA(cudaMemcpy2DAsync(dst, sizeof(double) * N, src, sizeof(double) * ld, sizeof(double) * N, rows,
+                           cudaMemcpyDeviceToHost, h->st));
+  return MCB_OK;
+}
+
+extern "C" int mcb_get_mean(mcb_handle* h, double* mean) {
+  if (!h || !mean) return MCB_EINVAL;
+  H_CHECK(h->has_post, MCB_ESTATE, "mcb_get_mean: no E-step result");
+  H_CUDA(cudaSetDevice(h->device));
+  MCB_TRY(copy_rows(h, mean, h->mean.p, h->K, h->N, h->ld));
+  H_CUDA(cudaStreamSynchronize(h->st));
+  return MCB_OK;
+}
+
+extern "C" int mcb_get_cov(mcb_handle* h, int k, double* cov) {
+  if (!h || !cov) return MCB_EINVAL;
+  H_CHECK(h->has_post, MCB_ESTATE, "mcb_get_cov: no E-step result");
+  H_CHECK(k >= 0 && k < h->K, MCB_EINVAL, "mcb_get_cov: k out of range");
+  H_CUDA(cudaSetDevice(h->device));
+  MCB_TRY(copy_rows(h, cov, h->cov.p + (size_t)k * h->N * h->ld, h->N, h->N, h->ld));
+  H_CUDA(cudaStreamSynchronize(h->st));
+  return MCB_OK;
+}
+
+extern "C" int mcb_get_tau_new(mcb_handle* h, double* tau) {
+  if (!h || !tau) return MCB_EINVAL;
+  H_CHECK(h->has_post, MCB_ESTATE, "mcb_get_tau_new: no E-step result");
+  H_CUDA(cudaSetDevice(h->device));
+  H_CUDA(cudaMemcpyAsync(tau, h->tau_new.p, sizeof(double) * (size_t)h->M * h->K, cudaMemcpyDeviceToHost, h->st));
+  H_CUDA(cudaStreamSynchronize(h->st));
+  return MCB_OK;
+}
+
+extern "C" int mcb_get_mat_logL(mcb_handle* h, double* logL) {
+  if (!h || !logL) return MCB_EINVAL;
+  H_CHECK(h->has_post, MCB_ESTATE, "mcb_get_mat_logL: no E-step result");
+  H_CUDA(cudaSetDevice(h->device));
+  H_CUDA(cudaMemcpyAsync(logL, h->logL.p, sizeof(double) * (size_t)h->M * h->K, cudaMemcpyDeviceToHost, h->st));
+  H_CUDA(cudaStreamSynchronize(h->st));
+  return MCB_OK;
+}
+
+extern "C" int mcb_get_logdet_cov(mcb_handle* h, double* logdet) {
+  if (!h || !logdet) return MCB_EINVAL;
+  H_CHECK(h->has_post, MCB_ESTATE, "mcb_get_logdet_cov: no E-step result");
+  for (int k = 0; k < h->K; ++k) logdet[k] = -h->h_logdetA[k];
+  return MCB_OK;
+}
+
+extern "C" int mcb_accept_tau(mcb_handle* h) {
+  if (!h) return MCB_EINVAL;
+  H_CHECK(h->has_post, MCB_ESTATE, "mcb_accept_tau: no E-step result");
+  H_CUDA(cudaSetDevice(h->device));
+  H_CUDA(cudaMemcpyAsync(h->tau.p, h->tau_new.p, sizeof(double) * (size_t)h->M * h->K, cudaMemcpyDeviceToDevice, h->st));
+  return MCB_OK;
+}
+
+extern "C" int mcb_e_step_VEM(mcb_handle* h, int K, const double* theta_k, const double* theta_i,
+                              const double* pi_k, const double* m_k, int m_k_len, const double* old_tau,
+                              double* out_mean, double* out_cov, double* out_tau, double* out_mat_logL) {
+  MCB_TRY(mcb_set_state(h, K, theta_k, theta_i, pi_k, m_k, m_k_len, old_tau));
+  MCB_TRY(mcb_e_step(h));
+  const int N = h->N, ld = h->ld, M = h->M;
+  if (out_mean) MCB_TRY(copy_rows(h, out_mean, h->mean.p, K, N, ld));
+  if (out_cov)
+    for (int k = 0; k < K; ++k)
+      MCB_TRY(copy_rows(h, out_cov + (size_t)k * N * N, h->cov.p + (size_t)k * N * ld, N, N, ld));
+  if (out_tau) H_CUDA(cudaMemcpyAsync(out_tau, h->tau_new.p, sizeof(double) * (size_t)M * K, cudaMemcpyDeviceToHost, h->st));
+  if (out_mat_logL) H_CUDA(cudaMemcpyAsync(out_mat_logL, h->logL.p, sizeof(double) * (size_t)M * K, cudaMemcpyDeviceToHost, h->st));
+  H_CUDA(cudaStreamSynchronize(h->st));
+  return MCB_OK;
+}
+
+// Install an explicit hyper-posterior (the `mu_k_param` / `list_mu_param` argument of the reference's
+// callbacks) instead of the one left by mcb_e_step: mean[K][N], cov[K][N][N], tau[M][K] from host memory.
+extern "C" int mcb_set_posterior(mcb_handle* h, const double* mean, const double* cov, const double* tau) {
+  if (!h || !mean || !cov || !tau) return MCB_EINVAL;
+  H_CHECK(h->has_state, MCB_ESTATE, "mcb_set_posterior: call mcb_set_data and mcb_set_state first");
+  H_CUDA(cudaSetDevice(h->device));
+  spans_reset(h);
+  const int M = h->M, N = h->N, ld = h->ld, K = h->K;
+  const long long sN = (long long)N * ld;
+  H_CUDA(cudaMemcpy2DAsync(h->mean.p, sizeof(double) * ld, mean, sizeof(double) * N, sizeof(double) * N, K,
+                           cudaMemcpyHostToDevice, h->st));
+  for (int k = 0; k < K; ++k)
+    H_CUDA(cudaMemcpy2DAsync(h->cov.p + k * sN, sizeof(double) * ld, cov + (size_t)k * N * N, sizeof(double) * N,
+                             sizeof(double) * N, N, cudaMemcpyHostToDevice, h->st));
+  H_CUDA(cudaMemcpyAsync(h->tau_new.p, tau, sizeof(double) * (size_t)M * K, cudaMemcpyHostToDevice, h->st));
+  // Psi_i^-1 at the resident theta_i (no scatter: K = 0), then corr1/corr2/F_i with the supplied tau
+  H_CUDA(launch_factor_scatter(h->st, h->idata(), M, h->nmax, h->theta_i.p, h->tau.p, 0, h->cov.p, ld, sN, h->wk.p,
+                               h->iwork(), h->info.p));
+  vec_sub(h->st, K * ld, h->mean.p, h->mk.p, h->rvec.p, &h->launches);
+  H_CUDA(launch_tau(h->st, h->idata(), M, h->nmax, K, h->mean.p, h->cov.p, ld, sN, h->pi.p, h->iwork(),
+                    h->tau_new.p, h->logL.p, 1));
+  h->launches += 2;
+  // K_k^-1 and log|K_k| at the resident theta_k, log|C_k| of the supplied covariances (for the ELBO)
+  std::vector<double> groups;
+  h->G = group_theta(h->h_theta_k.data(), K, h->gmap, groups);
+  H_CUDA(cudaMemcpyAsync(h->gmap_d.p, h->gmap.data(), sizeof(int) * K, cudaMemcpyHostToDevice, h->st));
+  H_CUDA(cudaMemcpyAsync(h->theta_g.p, groups.data(), sizeof(double) * 3 * h->G, cudaMemcpyHostToDevice, h->st));
+  se_build(h->st, h->Kinv.p, nullptr, nullptr, N, ld, sN, h->grid.p, h->theta_g.p, 3, h->G, &h->launches);
+  H_CUDA(spd_inverse(h->st, h->Kinv.p, N, ld, sN, h->G, h->logdetK.p, h->info.p, h->ws, &h->launches));
+  H_CUDA(cudaMemcpyAsync(h->eX.p, h->cov.p, sizeof(double) * K * sN, cudaMemcpyDeviceToDevice, h->st));
+  H_CUDA(spd_inverse(h->st, h->eX.p, N, ld, sN, K, h->logdetA.p, h->info.p, h->ws, &h->launches));
+  H_CUDA(cudaMemcpyAsync(h->hbuf, h->logdetK.p, sizeof(double) * h->G, cudaMemcpyDeviceToHost, h->st));
+  H_CUDA(cudaMemcpyAsync(h->hbuf + K, h->logdetA.p, sizeof(double) * K, cudaMemcpyDeviceToHost, h->st));
+  MCB_TRY(check_info(h, "mcb_set_posterior"));
+  h->h_logdetK.assign(h->hbuf, h->hbuf + h->G);
+  h->h_logdetA.resize(K);
+  for (int k = 0; k < K; ++k) h->h_logdetA[k] = -h->hbuf[K + k];  // stored as log|A_k| = -log|C_k|
+  h->has_post = true;
+  h->csum_valid = false;
+  return MCB_OK;
+}
+
+// ---- mean-process objective / gradient -------------------------------------------------------------
+// Evaluates G groups of clusters, group g with hyper-parameters theta_h[g] = (a, b, sigma) shared by the
+// clusters z with gmap_h[z] == g (gmap -1: cluster not evaluated). f_out[g] and g_out[g][3] (d/da, d/db,
+// d/dsigma) follow logL_GP_mod(_common_hp_k) / gr_GP_mod(_common_hp_k) (CF.R:194-216, 250-278, 448-475,
+// 510-537). use_resident: take K^-1 and log|K| from the last E-step instead of building them.
+static int eval_mean_groups(mcb_handle* h, int G, const double* theta_h, const int* gmap_h, bool want_grad,
+                            bool use_resident, double* f_out, double* g_out) {
+  const int N = h->N, ld = h->ld, K = h->K;
+  const long long sN = (long long)N * ld;
+  double* stage = h->hbuf + 1024;
+  int* stage_i = (int*)(h->hbuf + 2048);
+  memcpy(stage, theta_h, sizeof(double) * 3 * G);
+  memcpy(stage_i, gmap_h, sizeof(int) * K);
+  H_CUDA(cudaMemcpyAsync(h->etheta.p, stage, sizeof(double) * 3 * G, cudaMemcpyHostToDevice, h->st));
+  H_CUDA(cudaMemcpyAsync(h->egmap.p, stage_i, sizeof(int) * K, cudaMemcpyHostToDevice, h->st));
+  const double* Kinv;
+  const double* logdetK;
+  if (use_resident) {
+    Kinv = h->Kinv.p;
+    logdetK = h->logdetK.p;
+  } else {
+    se_build(h->st, h->eK.p, want_grad ? h->eD1.p : nullptr, want_grad ? h->eD2.p : nullptr, N, ld, sN, h->grid.p,
+             h->etheta.p, 3, G, &h->launches);
+    H_CUDA(spd_inverse(h->st, h->eK.p, N, ld, sN, G, h->elogdet.p, h->info.p, h->ws, &h->launches));
+    Kinv = h->eK.p;
+    logdetK = h->elogdet.p;
+  }
+  // sum of the hyper-posterior covariances of each group (theta independent: cached per E-step + grouping)
+  std::vector<int> gm(gmap_h, gmap_h + K);
+  if (!h->csum_valid || gm != h->csum_gmap) {
+    sum_groups(h->st, N, ld, sN, h->cov.p, h->egmap.p, K, h->eCsum.p, G, &h->launches);
+    h->csum_gmap = gm;
+    h->csum_valid = true;
+  }
+  symv_mapped(h->st, N, ld, sN, Kinv, h->egmap.p, h->rvec.p, h->pz.p, K, &h->launches);
+  double* redg = h->ered.p;          // [G][4]
+  double* redz = redg + 4 * K;       // [K][4]
+  double* redt = redz + 4 * K;       // [G][4] (3 used)
+  H_CUDA(cudaMemsetAsync(h->ered.p, 0, sizeof(double) * 12 * K, h->st));
+  group_reduce(h->st, N, ld, sN, Kinv, h->eCsum.p, sN, want_grad ? h->eD1.p : nullptr,
+               want_grad ? h->eD2.p : nullptr, redg, G, &h->launches);
+  cluster_reduce(h->st, N, ld, sN, h->rvec.p, h->pz.p, want_grad ? h->eD1.p : nullptr,
+                 want_grad ? h->eD2.p : nullptr, h->egmap.p, redz, K, &h->launches);
+  if (want_grad) {
+    // X = K^-1 Csum ; G = X K^-1 only through its traces against dK/da, dK/db and I
+    gemm_nt(h->st, N, N, N, Kinv, ld, sN, h->eCsum.p, ld, sN, h->eX.p, ld, sN, 1.0, 0.0, G, &h->launches);
+    gemm_nt_trace(h->st, N, h->eX.p, ld, sN, Kinv, ld, sN, h->eD1.p, h->eD2.p, ld, sN, redt, 4, G, &h->launches);
+  }
+  double* hr = h->hbuf + 4096;
+  H_CUDA(cudaMemcpyAsync(hr, h->ered.p, sizeof(double) * 12 * K, cudaMemcpyDeviceToHost, h->st));
+  H_CUDA(cudaMemcpyAsync(hr + 12 * K, logdetK, sizeof(double) * G, cudaMemcpyDeviceToHost, h->st));
+  MCB_TRY(check_info(h, "mean-process objective"));
+  const double* hg = hr;
+  const double* hz = hr + 4 * K;
+  const double* ht = hr + 8 * K;
+  const double* hl = hr + 12 * K;
+  for (int g = 0; g < G; ++g) {
+    int ng = 0;
+    double q = 0, pp = 0, d1 = 0, d2 = 0;
+    for (int z = 0; z < K; ++z)
+      if (gmap_h[z] == g) {
+        ++ng;
+        q += hz[4 * z]; pp += hz[4 * z + 1]; d1 += hz[4 * z + 2]; d2 += hz[4 * z + 3];
+      }
+    f_out[g] = 0.5 * ng * ((double)N * kLog2Pi + hl[g]) + 0.5 * q + 0.5 * hg[4 * g];
+    if (want_grad && g_out) {
+      const double sg = theta_h[3 * g + 2];
+      g_out[3 * g + 0] = -0.5 * (d1 + ht[4 * g + 0] - ng * hg[4 * g + 1]);
+      g_out[3 * g + 1] = -0.5 * (d2 + ht[4 * g + 1] - ng * hg[4 * g + 2]);
+      g_out[3 * g + 2] = -sg * (pp + ht[4 * g + 2] - ng * hg[4 * g + 3]);
+    }
+  }
+  return MCB_OK;
+}
+
+extern "C" int mcb_eval_mean(mcb_handle* h, int k, const double* theta, int nhp, double pen_diag, double* f,
+                             double* g) {
+  if (!h || !theta || !f) return MCB_EINVAL;
+  H_CHECK(h->has_post, MCB_ESTATE, "mcb_eval_mean: run the E-step first");
+  H_CHECK(k >= 0 && k < h->K && (nhp == 2 || nhp == 3), MCB_EINVAL, "mcb_eval_mean: bad argument");
+  H_CUDA(cudaSetDevice(h->device));
+  spans_reset(h);
+  PhaseScope ps(h, PH_MSTEP_K);
+  double th[3] = {theta[0], theta[1], nhp == 3 ? theta[2] : pen_diag};
+  std::vector<int> gm(h->K, -1);
+  gm[k] = 0;
+  double fo[1], go[3];
+  MCB_TRY(eval_mean_groups(h, 1, th, gm.data(), g != nullptr, false, fo, go));
+  *f = fo[0];
+  if (g) for (int j = 0; j < nhp; ++j) g[j] = go[j];
+  return MCB_OK;
+}
+
+extern "C" int mcb_eval_mean_common(mcb_handle* h, const double* theta, int nhp, double pen_diag, double* f,
+                                    double* g) {
+  if (!h || !theta || !f) return MCB_EINVAL;
+  H_CHECK(h->has_post, MCB_ESTATE, "mcb_eval_mean_common: run the E-step first");
+  H_CHECK(nhp == 2 || nhp == 3, MCB_EINVAL, "mcb_eval_mean_common: nhp must be 2 or 3");
+  H_CUDA(cudaSetDevice(h->device));
+  spans_reset(h);
+  PhaseScope ps(h, PH_MSTEP_K);
+  double th[3] = {theta[0], theta[1], nhp == 3 ? theta[2] : pen_diag};
+  std::vector<int> gm(h->K, 0);
+  double fo[1], go[3];
+  MCB_TRY(eval_mean_groups(h, 1, th, gm.data(), g != nullptr, false, fo, go));
+  *f = fo[0];
+  if (g) for (int j = 0; j < nhp; ++j) g[j] = go[j];
+  return MCB_OK;
+}
+
+// ---- individual objective / gradient ---------------------------------------------------------------
+extern "C" int mcb_eval_indiv(mcb_handle* h, const double* theta, double* f, double* g) {
+  if (!h || !theta || !f) return MCB_EINVAL;
+  H_CHECK(h->has_post, MCB_ESTATE, "mcb_eval_indiv: run the E-step first");
+  H_CUDA(cudaSetDevice(h->device));
+  spans_reset(h);
+  const int M = h->M;
+  H_CUDA(cudaMemcpyAsync(h->theta_i_new.p, theta, sizeof(double) * 3 * M, cudaMemcpyHostToDevice, h->st));
+  {
+    PhaseScope ps(h, PH_MSTEP_I);
+    H_CUDA(launch_indiv_eval(h->st, h->idata(), M, h->nmax, h->iwork(), h->theta_i_new.p, 3, g != nullptr,
+                             h->fi_tmp.p, h->gi_tmp.p, nullptr, h->info.p));
+    ++h->launches;
+  }
+  H_CUDA(cudaMemcpyAsync(f, h->fi_tmp.p, sizeof(double) * M, cudaMemcpyDeviceToHost, h->st));
+  if (g) H_CUDA(cudaMemcpyAsync(g, h->gi_tmp.p, sizeof(double) * 3 * M, cudaMemcpyDeviceToHost, h->st));
+  h->has_cand = false;
+  return check_info(h, "logL_clust_multi_GP");
+}
+
+// sum over all individuals (all ranks) of (F_i, dF_i) at one shared theta; result in out4 (host)
+static int eval_indiv_common(mcb_handle* h, const double* theta3, bool want_grad, double* out4) {
+  double* stage = h->hbuf + 512;
+  memcpy(stage, theta3, sizeof(double) * 3);
+  double* dth = h->scal.p + 8;
+  double* dsum = h->scal.p + 16;
+  H_CUDA(cudaMemcpyAsync(dth, stage, sizeof(double) * 3, cudaMemcpyHostToDevice, h->st));
+  H_CUDA(cudaMemsetAsync(dsum, 0, sizeof(double) * 4, h->st));
+  H_CUDA(launch_indiv_eval(h->st, h->idata(), h->M, h->nmax, h->iwork(), dth, 0, want_grad, nullptr, nullptr, dsum,
+                           h->info.p));
+  ++h->launches;
+  MCB_TRY(comm_allreduce_sum(h, dsum, 4));
+  H_CUDA(cudaMemcpyAsync(h->hbuf + 520, dsum, sizeof(double) * 4, cudaMemcpyDeviceToHost, h->st));
+  MCB_TRY(check_info(h, "logL_clust_multi_GP_common_hp_i"));
+  memcpy(out4, h->hbuf + 520, sizeof(double) * 4);
+  return MCB_OK;
+}
+
+extern "C" int mcb_eval_indiv_common(mcb_handle* h, const double* theta, double* f, double* g) {
+  if (!h || !theta || !f) return MCB_EINVAL;
+  H_CHECK(h->has_post, MCB_ESTATE, "mcb_eval_indiv_common: run the E-step first");
+  H_CUDA(cudaSetDevice(h->device));
+  spans_reset(h);
+  PhaseScope ps(h, PH_MSTEP_I);
+  double out[4];
+  MCB_TRY(eval_indiv_common(h, theta, g != nullptr, out));
+  *f = out[0];
+  if (g) { g[0] = out[1]; g[1] = out[2]; g[2] = out[3]; }
+  return MCB_OK;
+}
+
+// ---- ELBO --------------------------------------------------------------------------------------------
+// logL_monitoring_VEM at (theta_k, theta_i) host arrays, or at the resident hp when both are NULL.
+static int elbo_impl(mcb_handle* h, const double* theta_k, const double* theta_i_dev, double out[2]) {
+  PhaseScope ps(h, PH_ELBO);
+  const int K = h->K, N = h->N;
+  double sum_k = 0.0;
+  {
+    std::vector<int> gmap;
+    std::vector<double> groups;
+    const bool resident = (theta_k == nullptr);
+    const int G = group_theta(resident ? h->h_theta_k.data() : theta_k, K, gmap, groups);
+    std::vector<double> f(G);
+    MCB_TRY(eval_mean_groups(h, G, groups.data(), gmap.data(), false, resident, f.data(), nullptr));
+    for (int g = 0; g < G; ++g) sum_k += f[g];
+  }
+  double* dsum = h->scal.p + 24;
+  H_CUDA(cudaMemsetAsync(dsum, 0, sizeof(double), h->st));
+  if (theta_i_dev == nullptr) {
+    vec_sum(h->st, h->M, h->Fi.p, dsum, &h->launches);
+  } else {
+    H_CUDA(launch_indiv_eval(h->st, h->idata(), h->M, h->nmax, h->iwork(), theta_i_dev, 3, 0, nullptr, nullptr, dsum,
+                             h->info.p));
+    ++h->launches;
+  }
+  MCB_TRY(comm_allreduce_sum(h, dsum, 1));
+  H_CUDA(cudaMemcpyAsync(h->hbuf + 600, dsum, sizeof(double), cudaMemcpyDeviceToHost, h->st));
+  MCB_TRY(check_info(h, "logL_monitoring_VEM"));
+  const double sum_i = h->hbuf[600];
+  out[0] = -sum_k - sum_i;
+  double ld = 0.0;
+  for (int k = 0; k < K; ++k) ld += -h->h_logdetA[k];
+  out[1] = out[0] + 0.5 * ((double)K * N + ld);
+  return MCB_OK;
+}
+
+extern "C" int mcb_elbo(mcb_handle* h, const double* theta_k, const double* theta_i, double out[2]) {
+  if (!h || !out) return MCB_EINVAL;
+  H_CHECK(h->has_post, MCB_ESTATE, "mcb_elbo: run the E-step first");
+  H_CHECK((theta_k == nullptr) == (theta_i == nullptr), MCB_EINVAL, "mcb_elbo: pass both theta_k and theta_i or neither");
+  H_CUDA(cudaSetDevice(h->device));
+  spans_reset(h);
+  const double* ti = nullptr;
+  if (theta_i) {
+    H_CUDA(cudaMemcpyAsync(h->gi_tmp.p, theta_i, sizeof(double) * 3 * h->M, cudaMemcpyHostToDevice, h->st));
+    ti = h->gi_tmp.p;
+  }
+  return elbo_impl(h, theta_k, ti, out);
+}
+
+// ---- M-step ------------------------------------------------------------------------------------------
+static int m_step_impl(mcb_handle* h, int common_hp_k, int common_hp_i, int* stats) {
+  const int M = h->M, K = h->K;
+  int nfev_i = 0, nit_i = 0, nfev_k = 0, nit_k = 0;
+  // --- individuals (CF.R:645-660)
+  {
+    PhaseScope ps(h, PH_MSTEP_I);
+    if (common_hp_i) {
+      // one optimiser on sum_i F_i, starting from theta_i[[1]] (CF.R:647)
+      double x0[3];
+      H_CUDA(cudaMemcpyAsync(h->hbuf, h->theta_i.p, sizeof(double) * 3, cudaMemcpyDeviceToHost, h->st));
+      H_CUDA(cudaStreamSynchronize(h->st));
+      if (h->nranks > 1) {
+        // every rank must start from rank 0's first individual
+        double* d = h->scal.p + 32;
+        if (h->rank == 0) H_CUDA(cudaMemcpyAsync(d, h->theta_i.p, sizeof(double) * 3, cudaMemcpyDeviceToDevice, h->st));
+        else H_CUDA(cudaMemsetAsync(d, 0, sizeof(double) * 3, h->st));
+        MCB_TRY(comm_allreduce_sum(h, d, 3));
+        H_CUDA(cudaMemcpyAsync(h->hbuf, d, sizeof(double) * 3, cudaMemcpyDeviceToHost, h->st));
+        H_CUDA(cudaStreamSynchronize(h->st));
+      }
+      memcpy(x0, h->hbuf, sizeof x0);
+      Lbfgs opt;
+      lb_init(opt, 3, x0);
+      int st = LB_EVAL;
+      double out[4];
+      while (st == LB_EVAL) {
+        MCB_TRY(eval_indiv_common(h, opt.x, true, out));
+        st = lb_advance(opt, out[0], out + 1);
+      }
+      nfev_i = opt.nfev; nit_i = opt.iter;
+      std::vector<double> rep(3 * (size_t)M);
+      for (int i = 0; i < M; ++i) { rep[3 * i] = opt.x[0]; rep[3 * i + 1] = opt.x[1]; rep[3 * i + 2] = opt.x[2]; }
+      H_CUDA(cudaMemcpyAsync(h->theta_i_new.p, rep.data(), sizeof(double) * 3 * M, cudaMemcpyHostToDevice, h->st));
+      H_CUDA(cudaStreamSynchronize(h->st));
+    } else {
+      H_CUDA(launch_indiv_mstep(h->st, h->idata(), M, h->nmax, h->iwork(), h->theta_i.p, h->theta_i_new.p, 100,
+                                h->nfev_i.p, h->niter_i.p, h->status_i.p, h->info.p));
+      ++h->launches;
+    }
+  }
+  // pen_diag = mean_i theta_i[3] (CF.R:662)
+  double pen_diag;
+  {
+    double* d = h->scal.p + 40;
+    theta3_sum(h->st, M, h->theta_i_new.p, d, &h->launches);
+    MCB_TRY(comm_allreduce_sum(h, d, 1));
+    H_CUDA(cudaMemcpyAsync(h->hbuf + 700, d, sizeof(double), cudaMemcpyDeviceToHost, h->st));
+    H_CUDA(cudaStreamSynchronize(h->st));
+    pen_diag = h->hbuf[700] / (double)h->M_total;
+  }
+  // --- mean processes (CF.R:664-680)
+  h->h_theta_k_new.assign(3 * K, 0.0);
+  {
+    PhaseScope ps(h, PH_MSTEP_K);
+    if (common_hp_k) {
+      // NB reference behaviour: the start vector theta_k[[1]] has 3 entries, so sigma is optimised too and
+      // then discarded: opm(...)[1, 1:2] keeps (a, b) and pen_diag becomes the third entry (CF.R:666-668)
+      Lbfgs opt;
+      lb_init(opt, 3, h->h_theta_k.data());
+      std::vector<int> gm(K, 0);
+      int st = LB_EVAL;
+      double f, g[3];
+      while (st == LB_EVAL) {
+        MCB_TRY(eval_mean_groups(h, 1, opt.x, gm.data(), true, false, &f, g));
+        st = lb_advance(opt, f, g);
+      }
+      nfev_k = opt.nfev; nit_k = opt.iter;
+      for (int k = 0; k < K; ++k) {
+        h->h_theta_k_new[3 * k] = opt.x[0];
+        h->h_theta_k_new[3 * k + 1] = opt.x[1];
+        h->h_theta_k_new[3 * k + 2] = pen_diag;
+      }
+    } else {
+      // K optimisers over (a, b) with sigma = pen_diag, advanced in lock step: one batched launch sequence
+      // evaluates every unfinished cluster (CF.R:673-679)
+      std::vector<Lbfgs> opt(K);
+      std::vector<int> st(K, LB_EVAL), gm(K), active;
+      for (int k = 0; k < K; ++k) lb_init(opt[k], 2, h->h_theta_k.data() + 3 * k);
+      std::vector<double> th(3 * K), f(K), g(3 * K);
+      for (;;) {
+        active.clear();
+        std::fill(gm.begin(), gm.end(), -1);
+        for (int k = 0; k < K; ++k)
+          if (st[k] == LB_EVAL) {
+            gm[k] = (int)active.size();
+            th[3 * active.size()] = opt[k].x[0];
+            th[3 * active.size() + 1] = opt[k].x[1];
+            th[3 * active.size() + 2] = pen_diag;
+            active.push_back(k);
+          }
+        if (active.empty()) break;
+        MCB_TRY(eval_mean_groups(h, (int)active.size(), th.data(), gm.data(), true, false, f.data(), g.data()));
+        for (size_t a = 0; a < active.size(); ++a) {
+          const int k = active[a];
+          st[k] = lb_advance(opt[k], f[a], g.data() + 3 * a);
+        }
+      }
+      for (int k = 0; k < K; ++k) {
+        h->h_theta_k_new[3 * k] = opt[k].x[0];
+        h->h_theta_k_new[3 * k + 1] = opt[k].x[1];
+        h->h_theta_k_new[3 * k + 2] = pen_diag;
+        nfev_k = std::max(nfev_k, opt[k].nfev);
+        nit_k = std::max(nit_k, opt[k].iter);
+      }
+    }
+  }
+  memcpy(h->hbuf + 800, h->h_theta_k_new.data(), sizeof(double) * 3 * K);
+  H_CUDA(cudaMemcpyAsync(h->theta_k_new.p, h->hbuf + 800, sizeof(double) * 3 * K, cudaMemcpyHostToDevice, h->st));
+  // pi_k = mean_i tau_ik (CF.R:682)
+  tau_colsum(h->st, M, K, h->tau_new.p, h->pi_new.p, &h->launches);
+  MCB_TRY(comm_allreduce_sum(h, h->pi_new.p, K));
+  H_CUDA(cudaMemcpyAsync(h->hbuf + 900, h->pi_new.p, sizeof(double) * K, cudaMemcpyDeviceToHost, h->st));
+  H_CUDA(cudaStreamSynchronize(h->st));
+  h->h_pi_new.resize(K);
+  for (int k = 0; k < K; ++k) h->h_pi_new[k] = h->hbuf[900 + k] / (double)h->M_total;
+  memcpy(h->hbuf + 900, h->h_pi_new.data(), sizeof(double) * K);
+  H_CUDA(cudaMemcpyAsync(h->pi_new.p, h->hbuf + 900, sizeof(double) * K, cudaMemcpyHostToDevice, h->st));
+  H_CUDA(cudaStreamSynchronize(h->st));
+  if (!common_hp_i && stats) {
+    // max evaluations / iterations over individuals
+    std::vector<int> tmp(2 * (size_t)M);
+    H_CUDA(sync_copy(h, tmp.data(), h->nfev_i.p, sizeof(int) * M, cudaMemcpyDeviceToHost));
+    H_CUDA(sync_copy(h, tmp.data() + M, h->niter_i.p, sizeof(int) * M, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < M; ++i) { nfev_i = std::max(nfev_i, tmp[i]); nit_i = std::max(nit_i, tmp[M + i]); }
+  }
+  if (stats) { stats[0] = nfev_i; stats[1] = nfev_k; stats[2] = nit_i; stats[3] = nit_k; }
+  h->ms_stats[0] = nfev_i; h->ms_stats[1] = nfev_k; h->ms_stats[2] = nit_i; h->ms_stats[3] = nit_k;
+  h->ms_stats[4] = common_hp_i ? (long long)nfev_i * h->M : -1;  // -1: per-individual counts live on the device
+  h->has_cand = true;
+  return MCB_OK;
+}
+
+extern "C" int mcb_m_step(mcb_handle* h, int common_hp_k, int common_hp_i, double* new_theta_k,
+                          double* new_theta_i, double* new_pi_k, int* stats) {
+  if (!h) return MCB_EINVAL;
+  H_CHECK(h->has_post, MCB_ESTATE, "mcb_m_step: run the E-step first");
+  H_CUDA(cudaSetDevice(h->device));
+  spans_reset(h);
+  MCB_TRY(m_step_impl(h, common_hp_k, common_hp_i, stats));
+  if (new_theta_k) memcpy(new_theta_k, h->h_theta_k_new.data(), sizeof(double) * 3 * h->K);
+  if (new_pi_k) memcpy(new_pi_k, h->h_pi_new.data(), sizeof(double) * h->K);
+  if (new_theta_i) {
+    H_CUDA(cudaMemcpyAsync(new_theta_i, h->theta_i_new.p, sizeof(double) * 3 * h->M, cudaMemcpyDeviceToHost, h->st));
+    H_CUDA(cudaStreamSynchronize(h->st));
+  }
+  return MCB_OK;
+}
+
+static int accept_hp_impl(mcb_handle* h) {
+  H_CUDA(cudaMemcpyAsync(h->theta_i.p, h->theta_i_new.p, sizeof(double) * 3 * h->M, cudaMemcpyDeviceToDevice, h->st));
+  H_CUDA(cudaMemcpyAsync(h->theta_k.p, h->theta_k_new.p, sizeof(double) * 3 * h->K, cudaMemcpyDeviceToDevice, h->st));
+  H_CUDA(cudaMemcpyAsync(h->pi.p, h->pi_new.p, sizeof(double) * h->K, cudaMemcpyDeviceToDevice, h->st));
+  h->h_theta_k = h->h_theta_k_new;
+  h->h_pi = h->h_pi_new;
+  return MCB_OK;
+}
+
+extern "C" int mcb_accept_hp(mcb_handle* h) {
+  if (!h) return MCB_EINVAL;
+  H_CHECK(h->has_cand, MCB_ESTATE, "mcb_accept_hp: no M-step candidate");
+  H_CUDA(cudaSetDevice(h->device));
+  return accept_hp_impl(h);
+}
+
+// ---- one iteration of training_VEM's loop (MC.R:44-93) --------------------------------------------
+extern "C" int mcb_vem_iteration(mcb_handle* h, int common_hp_k, int common_hp_i, double out[3]) {
+  if (!h || !out) return MCB_EINVAL;
+  H_CHECK(h->has_state, MCB_ESTATE, "mcb_vem_iteration: call mcb_set_data and mcb_set_state first");
+  H_CUDA(cudaSetDevice(h->device));
+  spans_reset(h);
+  MCB_TRY(e_step_impl(h));
+  double e_old[2], e_new[2];
+  MCB_TRY(elbo_impl(h, nullptr, nullptr, e_old));           // MC.R:51-53; also the second term of MC.R:71
+  MCB_TRY(m_step_impl(h, common_hp_k, common_hp_i, nullptr));
+  MCB_TRY(elbo_impl(h, h->h_theta_k_new.data(), h->theta_i_new.p, e_new));  // MC.R:70
+  const double eps = (e_new[0] - e_old[0]) / fabs(e_new[0]);
+  out[0] = e_old[1];
+  out[1] = eps;
+  if (eps < 1e-2) {
+    if (eps > 0) MCB_TRY(accept_hp_impl(h));
+    out[2] = 1.0;
+  } else {
+    MCB_TRY(accept_hp_impl(h));
+    H_CUDA(cudaMemcpyAsync(h->tau.p, h->tau_new.p, sizeof(double) * (size_t)h->M * h->K, cudaMemcpyDeviceToDevice, h->st));
+    out[2] = 0.0;
+  }
+  H_CUDA(cudaStreamSynchronize(h->st));
+  return MCB_OK;
+}
+
+// ---- measurement -------------------------------------------------------------------------------------
+// out[0..3] as mcb_m_step's stats; out[4] = total number of individual objective+gradient evaluations of the
+// last M-step on this rank (sum over individuals), out[5] = number of individuals
+extern "C" int mcb_last_mstep_stats(mcb_handle* h, long long out[6]) {
+  if (!h || !out) return MCB_EINVAL;
+  H_CHECK(h->has_cand, MCB_ESTATE, "mcb_last_mstep_stats: no M-step has run");
+  H_CUDA(cudaSetDevice(h->device));
+  for (int j = 0; j < 4; ++j) out[j] = h->ms_stats[j];
+  if (h->ms_stats[4] < 0) {
+    std::vector<int> tmp(h->M);
+    H_CUDA(sync_copy(h, tmp.data(), h->nfev_i.p, sizeof(int) * h->M, cudaMemcpyDeviceToHost));
+    long long sum = 0, mx = 0;
+    for (int v : tmp) { sum += v; mx = std::max<long long>(mx, v); }
+    h->ms_stats[4] = sum;
+    h->ms_stats[0] = mx;
+    out[0] = mx;
+  }
+  out[4] = h->ms_stats[4];
+  out[5] = h->M;
+  return MCB_OK;
+}
+
+extern "C" int mcb_pin_host(void* ptr, size_t bytes) {
+  return cudaHostRegister(ptr, bytes, cudaHostRegisterDefault) == cudaSuccess ? MCB_OK : MCB_ECUDA;
+}
+
+extern "C" int mcb_unpin_host(void* ptr) { return cudaHostUnregister(ptr) == cudaSuccess ? MCB_OK : MCB_ECUDA; }
+
+extern "C" int mcb_timer_start(mcb_handle* h) {
+  if (!h) return MCB_EINVAL;
+  H_CUDA(cudaSetDevice(h->device));
+  if (!h->tm0) { H_CUDA(cudaEventCreate(&h->tm0)); H_CUDA(cudaEventCreate(&h->tm1)); }
+  H_CUDA(cudaStreamSynchronize(h->st));
+  H_CUDA(cudaEventRecord(h->tm0, h->st));
+  return MCB_OK;
+}
+
+extern "C" int mcb_timer_stop(mcb_handle* h, float* ms) {
+  if (!h || !ms) return MCB_EINVAL;
+  H_CHECK(h->tm0 != nullptr, MCB_ESTATE, "mcb_timer_stop: timer not started");
+  H_CUDA(cudaSetDevice(h->device));
+  H_CUDA(cudaEventRecord(h->tm1, h->st));
+  H_CUDA(cudaEventSynchronize(h->tm1));
+  H_CUDA(cudaEventElapsedTime(ms, h->tm0, h->tm1));
+  return MCB_OK;
+}
+
+extern "C" int mcb_flush_l2(mcb_handle* h) {
+  if (!h) return MCB_EINVAL;
+  H_CUDA(cudaSetDevice(h->device));
+  const size_t n = (size_t)256 << 20;  // 256 MiB > 126 MB of L2
+  H_CUDA(h->flush.ensure(n));
+  H_CUDA(cudaMemsetAsync(h->flush.p, h->flush_byte++ & 0xff, n, h->st));
+  return MCB_OK;
+}
+
+extern "C" int mcb_last_timings(mcb_handle* h, float ms[8], long long* launches) {
+  if (!h || !ms) return MCB_EINVAL;
+  H_CUDA(cudaSetDevice(h->device));
+  H_CUDA(cudaStreamSynchronize(h->st));
+  for (int i = 0; i < 8; ++i) ms[i] = 0.f;
+  for (auto& sp : h->spans) {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, h->evpool[sp.e0], h->evpool[sp.e1]) == cudaSuccess) ms[sp.phase] += t;
+  }
+  if (launches) *launches = h->launches;
+  return MCB_OK;
+}

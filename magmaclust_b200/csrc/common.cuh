@@ -1,0 +1,121 @@
+// Internal declarations shared by the translation units of libmagmaclust_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdlib>
+#include <string>
+#include <vector>
+
+#include "../../include/mcb.h"
+
+namespace mcb {
+
+constexpr double kLog2Pi = 1.8378770664093454835606594728112;
+
+// ---- error plumbing: nothing throws across the C ABI -----------------------------------------------
+struct Status {
+  int code = MCB_OK;
+  std::string msg;
+};
+
+#define MCB_CUDA(h, expr)                                                                  \
+  do {                                                                                     \
+    cudaError_t e_ = (expr);                                                               \
+    if (e_ != cudaSuccess) {                                                               \
+      char b_[512];                                                                        \
+      snprintf(b_, sizeof b_, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+      (h)->err = b_;                                                                       \
+      return MCB_ECUDA;                                                                    \
+    }                                                                                      \
+  } while (0)
+
+#define MCB_TRY(expr)              \
+  do {                             \
+    int rc_ = (expr);              \
+    if (rc_ != MCB_OK) return rc_; \
+  } while (0)
+
+// ---- growable device buffer ----------------------------------------------------------------------
+template <class T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t cap = 0;  // elements
+  cudaError_t ensure(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    cudaError_t e = cudaMalloc(&p, n * sizeof(T));
+    if (e == cudaSuccess) cap = n;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+// ---- dense N x N toolkit (dense.cu) ----------------------------------------------------------------
+// All matrices row-major with leading dimension ld; batches are addressed as base + z * stride.
+constexpr int kNB = 32;  // pivot block of the blocked symmetric sweep
+
+struct DenseWs {
+  DevBuf<double> Pbuf, Cold;  // [Z][Npad][kNB] panels of the blocked sweep
+  DevBuf<double> red;         // scratch for reductions
+};
+
+// K[z] = SE covariance on `grid` with theta[z] = (a, b, sigma): exp(a - exp(-b)/2 d^2) off-diagonal,
+// exp(a) + sigma^2 on the diagonal (kern_to_cov, CF.R:61-86). Optionally also D2[z] = dK/db (deriv_hp2,
+// CF.R:441-446; zero diagonal). theta is a DEVICE pointer, theta_stride doubles between problems.
+// D1[z] = dK/da (deriv_hp1, CF.R:436-439: the kernel itself, diagonal exp(a) without the noise term).
+void se_build(cudaStream_t s, double* Kmat, double* D1, double* D2, int N, int ld, long long stride,
+              const double* grid, const double* theta, int theta_stride, int Z, long long* launches);
+
+// In-place inverse of Z symmetric positive definite matrices by a blocked symmetric sweep (block
+// Gauss-Jordan). logdet[z] (device) receives log det of the ORIGINAL matrix; *info (device int) is set
+// non-zero if a non-positive pivot is met. Both triangles are read and written.
+cudaError_t spd_inverse(cudaStream_t s, double* A, int N, int ld, long long stride, int Z, double* logdet,
+                        int* info, DenseWs& ws, long long* launches);
+
+// C[z] = alpha * A[z] * B[z]^T + beta * C[z]  (M x N x K, row-major, DMMA m8n8k4)
+void gemm_nt(cudaStream_t s, int M, int N, int K, const double* A, int lda, long long sA, const double* B,
+             int ldb, long long sB, double* C, int ldc, long long sC, double alpha, double beta, int Z,
+             long long* launches);
+
+// out[z][0..2] += (sum_ij G_ij D1_ij, sum_ij G_ij D2_ij, trace G) with G = A[z] * B[z]^T never stored.
+void gemm_nt_trace(cudaStream_t s, int N, const double* A, int lda, long long sA, const double* B, int ldb,
+                   long long sB, const double* D1, const double* D2, int ldd, long long sD, double* out,
+                   int out_stride, int Z, long long* launches);
+
+// y[z] = A[z] x[z]; optional dot[z] += x[z] . y[z]
+void symv(cudaStream_t s, int N, const double* A, int lda, long long sA, const double* x, long long sx,
+          double* y, long long sy, int Z, long long* launches);
+
+// ---- mean-process reductions (meanproc.cu) ---------------------------------------------------------
+// redg[g][0..3] += (sum Kinv_g o Csum_g, sum Kinv_g o D1_g, sum Kinv_g o D2_g, trace Kinv_g); D1/D2 may be NULL
+void group_reduce(cudaStream_t s, int N, int ld, long long stride, const double* Kinv, const double* Csum,
+                  long long strideCs, const double* D1, const double* D2, double* redg, int G, long long* launches);
+// redz[z][0..3] += (r_z.p_z, p_z.p_z, p_z'D1_g p_z, p_z'D2_g p_z) with g = gmap[z]; D1/D2 may be NULL
+void cluster_reduce(cudaStream_t s, int N, int ld, long long stride, const double* r, const double* p,
+                    const double* D1, const double* D2, const int* gmap, double* redz, int K, long long* launches);
+// p[z] = Kinv[gmap[z]] r[z]
+void symv_mapped(cudaStream_t s, int N, int ld, long long stride, const double* Kinv, const int* gmap,
+                 const double* r, double* p, int K, long long* launches);
+// dst[g] = sum over z with gmap[z] == g of src[z]   (N x ld matrices)
+void sum_groups(cudaStream_t s, int N, int ld, long long stride, const double* src, const int* gmap, int K,
+                double* dst, int G, long long* launches);
+// dst[k] = src[gmap[k]] scaled by `scale` (0 -> zero fill): initialises A_k with K_k^-1
+void copy_mapped(cudaStream_t s, int N, int ld, long long stride, const double* src, const int* gmap,
+                 double* dst, int K, double scale, long long* launches);
+// r[k][j] = mean[k][j] - mk[k][j]
+void vec_sub(cudaStream_t s, int n, const double* a, const double* b, double* out, long long* launches);
+// out[k] = (sum_i tau[i][k])   (caller divides by M_total after any all-reduce)
+void tau_colsum(cudaStream_t s, int M, int K, const double* tau, double* out, long long* launches);
+// out[0] = sum_i theta[i][2]
+void theta3_sum(cudaStream_t s, int M, const double* theta, double* out, long long* launches);
+// out[0] += sum_i v[i]
+void vec_sum(cudaStream_t s, int M, const double* v, double* out, long long* launches);
+// symmetrise/mirror helpers are not needed: every producer writes both triangles.
+
+}  // namespace mcb

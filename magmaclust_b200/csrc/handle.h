@@ -1,0 +1,86 @@
+// The opaque handle behind the C ABI: one GPU, its stream, the resident training set, model state and
+// workspaces.
+#pragma once
+#include "common.cuh"
+#include "indiv.cuh"
+
+struct mcb_handle {
+  int device = 0;
+  cudaStream_t st = nullptr;
+  std::string err;
+
+  // ---- communicator (NCCL, loaded lazily; nranks == 1 means single GPU) ----
+  int nranks = 1, rank = 0;
+  void* comm = nullptr;
+
+  // ---- training set (local shard) ----
+  bool has_data = false;
+  int M = 0, N = 0, ld = 0, nmax = 0;
+  long long P = 0, M_total = 0, W2 = 0;
+  mcb::DevBuf<int> off, gidx;
+  mcb::DevBuf<long long> woff;
+  mcb::DevBuf<double> t, y, grid;
+
+  // ---- model state ----
+  bool has_state = false, has_post = false, has_cand = false;
+  int K = 0;
+  mcb::DevBuf<double> theta_i, theta_k, pi, mk, tau;               // current hp / prior means / "old" tau
+  mcb::DevBuf<double> theta_i_new, theta_k_new, pi_new;            // M-step candidate
+  mcb::DevBuf<double> tau_new, logL;                               // E-step outputs
+  std::vector<double> h_theta_k, h_theta_k_new, h_pi, h_pi_new;    // host mirrors (tiny)
+
+  // ---- per-individual work ----
+  mcb::DevBuf<double> Winv, pvec, yWy, logdet_i, c1, c2, Fi, fi_tmp, gi_tmp;
+  mcb::DevBuf<int> nfev_i, niter_i, status_i;
+
+  // ---- dense side ----
+  int G = 0;                       // distinct theta_k at the last E-step
+  std::vector<int> gmap;           // cluster -> group
+  mcb::DevBuf<int> gmap_d;
+  mcb::DevBuf<double> theta_g;     // [G][3] device
+  mcb::DevBuf<double> Kinv, cov, wk, mean, rvec, pz, logdetK, logdetA;
+  std::vector<double> h_logdetK, h_logdetA;
+  // evaluator workspace (trial theta_k)
+  mcb::DevBuf<double> eK, eD1, eD2, eCsum, eX, etheta, ered, elogdet;
+  mcb::DevBuf<int> egmap;
+  bool csum_valid = false;
+  std::vector<int> csum_gmap;
+  mcb::DenseWs ws;
+  mcb::DevBuf<int> info;
+  mcb::DevBuf<double> scal;        // small device scalars
+
+  // ---- prediction posterior ----
+  bool has_pred = false;
+  int T = 0, ldT = 0;
+  mcb::DevBuf<double> pgrid, pKinv, pcov, pwk, pmean, plogdet;
+  std::vector<double> h_pi_pred;   // pi_k = mean_i tau_ik of the frozen tau (MC.R:141)
+  mcb::DevBuf<int> pmapidx;        // training row -> index in the prediction grid
+
+  // ---- pinned staging + timing ----
+  double* hbuf = nullptr;          // pinned, kHbuf doubles
+  static constexpr size_t kHbuf = 1 << 16;
+  std::vector<cudaEvent_t> evpool;
+  struct Span { int phase; int e0, e1; };
+  std::vector<Span> spans;
+  int ev_next = 0;
+  long long launches = 0;
+  long long ms_stats[6] = {0, 0, 0, 0, 0, 0};
+  cudaEvent_t tm0 = nullptr, tm1 = nullptr;   // mcb_timer_start / mcb_timer_stop
+  mcb::DevBuf<unsigned char> flush;            // mcb_flush_l2
+  int flush_byte = 0;
+
+  mcb::IndivData idata() const {
+    return mcb::IndivData{off.p, woff.p, gidx.p, t.p, y.p};
+  }
+  mcb::IndivWork iwork() const {
+    return mcb::IndivWork{Winv.p, pvec.p, yWy.p, logdet_i.p, c1.p, c2.p, Fi.p};
+  }
+};
+
+namespace mcb {
+enum Phase { PH_INDIV = 0, PH_DENSE = 1, PH_TAU = 2, PH_MSTEP_I = 3, PH_MSTEP_K = 4, PH_ELBO = 5, PH_PRED = 6, PH_COMM = 7 };
+
+// NCCL shim (comm.cu): no-ops when the handle is single-rank
+int comm_allreduce_sum(mcb_handle* h, double* buf, size_t count);
+void comm_destroy(mcb_handle* h);
+}  // namespace mcb

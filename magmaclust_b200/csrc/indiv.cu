@@ -1,0 +1,471 @@
+// Per-individual FP64 kernels of the VEM path (sm_100a): one CTA per individual, the n_i x n_i problem
+// resident in shared memory.
+//
+//   indiv_factor_scatter  kern_to_inv (CF.R:153-190) + update_inv_VEM (CF.R:690-707) + update_mean_VEM
+//                         (CF.R:709-731): Psi_i^-1, Psi_i^-1 y_i, log|Psi_i|, scattered tau-weighted onto A_k, w_k
+//   indiv_tau             update_tau_i_k_VEM (CF.R:733-762) via logL_GP_mod (CF.R:194-216) / dmvnorm
+//                         (CF.R:10-35); also emits the theta-independent M-step inputs corr1/corr2
+//                         (CF.R:236-245) and F_i at the current hp (logL_clust_multi_GP, CF.R:218-248)
+//   indiv_eval            logL_clust_multi_GP + gr_clust_multi_GP (CF.R:218-248, 477-508) at a trial theta
+//   indiv_mstep           the per-individual optimiser loop of m_step_VEM (CF.R:653-659), L-BFGS in-kernel
+//
+// The inverse is a symmetric sweep of the bordered matrix [[Psi, y, c1], [., 0]]: after sweeping the n
+// pivots the block holds -Psi^-1, the borders hold Psi^-1 y and Psi^-1 c1, the corner -y'Psi^-1 y, and
+// log|Psi| is the sum of the log pivots. Same flop count as Cholesky + inverse (n^3), but one uniform
+// rank-1 update per step and no separate triangular phases.
+#include "common.cuh"
+#include "indiv.cuh"
+#include "lbfgs.h"
+
+namespace mcb {
+
+constexpr int kT = 128;  // threads per CTA
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// sum `NV` values over the CTA; result valid in all threads. red: smem [NV][kT/32]
+template <int NV>
+__device__ __forceinline__ void cta_sum(double (&v)[NV], double* red) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int q = 0; q < NV; ++q) v[q] = warp_sum(v[q]);
+  __syncthreads();
+  if (lane == 0) {
+#pragma unroll
+    for (int q = 0; q < NV; ++q) red[q * (kT / 32) + warp] = v[q];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int q = 0; q < NV; ++q) {
+    double s = 0;
+#pragma unroll
+    for (int w = 0; w < kT / 32; ++w) s += red[q * (kT / 32) + w];
+    v[q] = s;
+  }
+}
+
+// Build the bordered SE covariance in shared memory (kern_to_cov semantics, CF.R:61-86):
+// A[a][b] = exp(th1 - exp(-th2)/2 (ta-tb)^2) off-diagonal, exp(th1) + sigma^2 on the diagonal.
+__device__ __forceinline__ void build_bordered(double* A, int ld, int n, int nbord, const double* t,
+                                               const double* const* bord, double th1, double th2, double sg) {
+  const double hl = exp(-th2) / 2.0;
+  const double dg = exp(th1) + sg * sg;
+  const int ntot = n + nbord;
+  for (int e = threadIdx.x; e < ntot * ntot; e += kT) {
+    const int a = e / ntot, b = e - a * ntot;
+    double v;
+    if (a < n && b < n) {
+      const double d = t[a] - t[b];
+      v = (a == b) ? dg : exp(th1 - hl * (d * d));
+    } else if (a < n) {
+      v = bord[b - n][a];
+    } else if (b < n) {
+      v = bord[a - n][b];
+    } else {
+      v = 0.0;
+    }
+    A[a * ld + b] = v;
+  }
+}
+
+// Sweep pivots 0..n-1 of the symmetric ntot x ntot matrix in shared memory. Returns sum of log pivots
+// (identical in every thread); *bad is set if a pivot is not positive.
+__device__ double cta_sweep(double* A, int n, int ntot, int ld, int* bad) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double logdet = 0.0;
+  __syncthreads();
+  for (int k = 0; k < n; ++k) {
+    const double d = A[k * ld + k];
+    const double inv_d = 1.0 / d;
+    logdet += log(d);
+    if (!(d > 0.0) && threadIdx.x == 0) *bad = 1;
+    const double* rk = A + k * ld;
+    for (int a = warp; a < ntot; a += kT / 32) {
+      if (a == k) continue;
+      double* ra = A + a * ld;
+      const double ca = ra[k] * inv_d;
+      for (int b = lane; b < ntot; b += 32)
+        if (b != k) ra[b] -= ca * rk[b];
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < ntot; b += kT) {
+      if (b == k) continue;
+      const double v = A[k * ld + b] * inv_d;
+      A[k * ld + b] = v;
+      A[b * ld + k] = v;
+    }
+    if (threadIdx.x == 0) A[k * ld + k] = -inv_d;
+    __syncthreads();
+  }
+  return logdet;
+}
+
+// -------------------------------------------------------------------------------------------------
+// E-step, part 1
+// -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kT) indiv_factor_scatter_kernel(IndivData dd, const double* __restrict__ theta_i,
+                                                                  const double* __restrict__ tau, int K,
+                                                                  double* __restrict__ acc, int ldN,
+                                                                  long long strideA, double* __restrict__ wk,
+                                                                  IndivWork w, int* __restrict__ info) {
+  extern __shared__ double sm[];
+  const int i = blockIdx.x;
+  const int o0 = dd.off[i], n = dd.off[i + 1] - o0;
+  const int ntot = n + 1, ld = ntot | 1;
+  double* A = sm;
+  double* t = A + (size_t)ntot * ld;
+  double* y = t + n;
+  int* idx = (int*)(y + n);
+  for (int a = threadIdx.x; a < n; a += kT) {
+    t[a] = dd.t[o0 + a];
+    y[a] = dd.y[o0 + a];
+    idx[a] = dd.gidx[o0 + a];
+  }
+  __syncthreads();
+  const double th1 = theta_i[3 * i], th2 = theta_i[3 * i + 1], sg = theta_i[3 * i + 2];
+  const double* bord[1] = {y};
+  build_bordered(A, ld, n, 1, t, bord, th1, th2, sg);
+  const double logdet = cta_sweep(A, n, ntot, ld, info);
+  double* Wg = w.Winv + dd.woff[i];
+  for (int e = threadIdx.x; e < n * n; e += kT) {
+    const int a = e / n, b = e - a * n;
+    Wg[e] = -A[a * ld + b];
+  }
+  for (int a = threadIdx.x; a < n; a += kT) w.pvec[o0 + a] = A[a * ld + n];
+  if (threadIdx.x == 0) {
+    w.yWy[i] = -A[n * ld + n];
+    w.logdet[i] = logdet;
+  }
+  // scatter tau-weighted Psi^-1 and Psi^-1 y onto the union grid
+  for (int k = 0; k < K; ++k) {
+    const double tk = tau[(size_t)i * K + k];
+    if (tk == 0.0) continue;  // exact zeros (one-hot initial tau) contribute nothing
+    double* Ak = acc + k * strideA;
+    for (int e = threadIdx.x; e < n * n; e += kT) {
+      const int a = e / n, b = e - a * n;
+      atomicAdd(Ak + (size_t)idx[a] * ldN + idx[b], -tk * A[a * ld + b]);
+    }
+    for (int a = threadIdx.x; a < n; a += kT) atomicAdd(wk + (size_t)k * ldN + idx[a], tk * A[a * ld + n]);
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// E-step, part 2: responsibilities
+// -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kT) indiv_tau_kernel(IndivData dd, int K, const double* __restrict__ mean,
+                                                       const double* __restrict__ cov, int ldN, long long strideC,
+                                                       const double* __restrict__ pi, IndivWork w,
+                                                       double* __restrict__ tau_new, double* __restrict__ logL,
+                                                       int fixed_tau) {
+  extern __shared__ double sm[];
+  __shared__ double red[3 * (kT / 32)];
+  const int i = blockIdx.x;
+  const int o0 = dd.off[i], n = dd.off[i + 1] - o0;
+  double* W = sm;                 // n*n
+  double* mu = W + (size_t)n * n;  // n
+  double* p = mu + n;             // n
+  double* lk = p + n;             // K : l_ik then tau_ik
+  double* ak = lk + K;            // K : mu' W mu + sum W o C
+  double* ek = ak + K;            // K : p' mu
+  int* idx = (int*)(ek + K);
+  const double* Wg = w.Winv + dd.woff[i];
+  for (int e = threadIdx.x; e < n * n; e += kT) W[e] = Wg[e];
+  for (int a = threadIdx.x; a < n; a += kT) {
+    p[a] = w.pvec[o0 + a];
+    idx[a] = dd.gidx[o0 + a];
+  }
+  __syncthreads();
+  const double base = (double)n * kLog2Pi + w.logdet[i] + w.yWy[i];
+  for (int k = 0; k < K; ++k) {
+    const double* mk = mean + (size_t)k * ldN;
+    const double* Ck = cov + k * strideC;
+    for (int a = threadIdx.x; a < n; a += kT) mu[a] = mk[idx[a]];
+    __syncthreads();
+    double v[3] = {0.0, 0.0, 0.0};
+    for (int e = threadIdx.x; e < n * n; e += kT) {
+      const int a = e / n, b = e - a * n;
+      const double wab = W[e];
+      v[0] += wab * mu[a] * mu[b];
+      v[1] += wab * Ck[(size_t)idx[a] * ldN + idx[b]];
+    }
+    for (int a = threadIdx.x; a < n; a += kT) v[2] += p[a] * mu[a];
+    cta_sum<3>(v, red);
+    if (threadIdx.x == 0) {
+      // l_ik = -( 0.5 (n log 2pi + log|Psi| + z'Wz) + 0.5 sum(W o C_k) ),  z = y - mu   (CF.R:212-215, 746)
+      lk[k] = -0.5 * (base - 2.0 * v[2] + v[0]) - 0.5 * v[1];
+      ak[k] = v[0] + v[1];
+      ek[k] = v[2];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    double mx = lk[0];
+    for (int k = 1; k < K; ++k) mx = fmax(mx, lk[k]);
+    double den = 0.0;
+    for (int k = 0; k < K; ++k) {
+      logL[(size_t)i * K + k] = lk[k];
+      const double u = pi[k] * exp(lk[k] - mx);  // CF.R:755-757: max over l only, pi multiplied after
+      lk[k] = u;
+      den += u;
+    }
+    double Fi = 0.5 * base;
+    for (int k = 0; k < K; ++k) {
+      // fixed_tau: the caller supplied mu_k_param$tau_i_k (M-step callbacks on an explicit posterior)
+      const double tk = fixed_tau ? tau_new[(size_t)i * K + k] : lk[k] / den;
+      lk[k] = tk;
+      if (!fixed_tau) tau_new[(size_t)i * K + k] = tk;
+      Fi += tk * (0.5 * ak[k] - ek[k]);
+    }
+    w.Fi[i] = Fi;
+  }
+  __syncthreads();
+  // corr1 / corr2 with the NEW tau (they feed the M-step, CF.R:236-245)
+  double* c2 = w.c2 + dd.woff[i];
+  for (int e = threadIdx.x; e < n * n; e += kT) {
+    const int a = e / n, b = e - a * n;
+    double s = 0.0;
+    for (int k = 0; k < K; ++k) {
+      const double* mk = mean + (size_t)k * ldN;
+      s += lk[k] * (mk[idx[a]] * mk[idx[b]] + cov[k * strideC + (size_t)idx[a] * ldN + idx[b]]);
+    }
+    c2[e] = s;
+  }
+  for (int a = threadIdx.x; a < n; a += kT) {
+    double s = 0.0;
+    for (int k = 0; k < K; ++k) s += lk[k] * mean[(size_t)k * ldN + idx[a]];
+    w.c1[o0 + a] = s;
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// M-step objective + gradient for one individual (whole CTA cooperates). Results in out[0..3] (smem).
+// -------------------------------------------------------------------------------------------------
+struct EvalSmem {
+  double* A;   // (n+2) x ld bordered matrix, swept in place
+  double* X;   // n x ld : W * c2
+  double* t;   // n
+  double* y;   // n
+  double* c1;  // n
+  double* red; // 9 * (kT/32)
+};
+
+__device__ __forceinline__ EvalSmem carve_eval(double* sm, int nmax) {
+  EvalSmem s;
+  const int ntot = nmax + 2, ld = ntot | 1;
+  s.A = sm;
+  s.X = s.A + (size_t)ntot * ld;
+  s.t = s.X + (size_t)nmax * ld;
+  s.y = s.t + nmax;
+  s.c1 = s.y + nmax;
+  s.red = s.c1 + nmax;
+  return s;
+}
+
+size_t eval_smem_bytes(int nmax) {
+  const int ntot = nmax + 2, ld = ntot | 1;
+  return sizeof(double) * ((size_t)ntot * ld + (size_t)nmax * ld + 3 * (size_t)nmax + 9 * (kT / 32) + 8);
+}
+
+// f = F_i(theta); g = dF_i/dtheta (skipped when !want_grad). out[0]=f, out[1..3]=g; all threads must call.
+__device__ void indiv_eval_cta(const EvalSmem& s, int n, const double* __restrict__ c2g, double th1, double th2,
+                               double sg, bool want_grad, double* out, int* bad) {
+  const int ntot = n + 2, ld = ntot | 1;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const double* bord[2] = {s.y, s.c1};
+  __syncthreads();
+  build_bordered(s.A, ld, n, 2, s.t, bord, th1, th2, sg);
+  const double logdet = cta_sweep(s.A, n, ntot, ld, bad);
+  const double yWy = -s.A[n * ld + n];
+  const double yWc = -s.A[n * ld + n + 1];
+  // 0.5 sum(W o c2)   (W = -A block)
+  double v1[1] = {0.0};
+  for (int e = threadIdx.x; e < n * n; e += kT) {
+    const int a = e / n, b = e - a * n;
+    v1[0] -= s.A[a * ld + b] * c2g[e];
+  }
+  cta_sum<1>(v1, s.red);
+  const double f = 0.5 * ((double)n * kLog2Pi + logdet + yWy) - yWc + 0.5 * v1[0];
+  if (!want_grad) {
+    if (threadIdx.x == 0) out[0] = f;
+    __syncthreads();
+    return;
+  }
+  // X = W c2  (n x n)
+  for (int a = warp; a < n; a += kT / 32) {
+    const double* ra = s.A + a * ld;
+    for (int b = lane; b < n; b += 32) {
+      double acc = 0.0;
+      for (int l = 0; l < n; ++l) acc -= ra[l] * c2g[l * n + b];
+      s.X[a * ld + b] = acc;
+    }
+  }
+  __syncthreads();
+  // traces against dPsi/dth1 (SE kernel incl. its diagonal), dPsi/dth2 (zero diagonal) and I
+  const double hl = exp(-th2) / 2.0;
+  double v[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  for (int a = warp; a < n; a += kT / 32) {
+    const double* xa = s.X + a * ld;
+    const double pa = s.A[a * ld + n];
+    for (int b = lane; b < n; b += 32) {
+      const double* rb = s.A + b * ld;  // W symmetric: column b == row b
+      double h = 0.0;
+      for (int l = 0; l < n; ++l) h -= xa[l] * rb[l];
+      const double wab = -s.A[a * ld + b];
+      const double d = s.t[a] - s.t[b];
+      const double gg = hl * (d * d);
+      const double k0 = exp(th1 - gg);
+      const double k2 = gg * k0;
+      const double ub = rb[n] - 2.0 * rb[n + 1];  // (p - 2q)_b
+      v[0] += h * k0;  v[1] += h * k2;
+      v[3] += wab * k0; v[4] += wab * k2;
+      v[6] += pa * k0 * ub; v[7] += pa * k2 * ub;
+      if (a == b) { v[2] += h; v[5] += wab; v[8] += pa * ub; }
+    }
+  }
+  cta_sum<9>(v, s.red);
+  if (threadIdx.x == 0) {
+    out[0] = f;
+    out[1] = -0.5 * (v[6] + v[0] - v[3]);
+    out[2] = -0.5 * (v[7] + v[1] - v[4]);
+    out[3] = -sg * (v[8] + v[2] - v[5]);
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ void load_indiv(const EvalSmem& s, const IndivData& dd, const IndivWork& w, int i,
+                                           int& n) {
+  const int o0 = dd.off[i];
+  n = dd.off[i + 1] - o0;
+  for (int a = threadIdx.x; a < n; a += kT) {
+    s.t[a] = dd.t[o0 + a];
+    s.y[a] = dd.y[o0 + a];
+    s.c1[a] = w.c1[o0 + a];
+  }
+}
+
+// theta: [M][3] when theta_stride == 3, one shared [3] when theta_stride == 0.
+// f[M], g[M][3] per individual; if sum4 != NULL also atomically accumulates (f, g) into sum4[0..3].
+__global__ void __launch_bounds__(kT) indiv_eval_kernel(IndivData dd, IndivWork w, int nmax,
+                                                        const double* __restrict__ theta, int theta_stride,
+                                                        int want_grad, double* __restrict__ f,
+                                                        double* __restrict__ g, double* __restrict__ sum4,
+                                                        int* __restrict__ info) {
+  extern __shared__ double sm[];
+  __shared__ double out[4];
+  const int i = blockIdx.x;
+  EvalSmem s = carve_eval(sm, nmax);
+  int n;
+  load_indiv(s, dd, w, i, n);
+  const double* th = theta + (size_t)i * theta_stride;
+  indiv_eval_cta(s, n, w.c2 + dd.woff[i], th[0], th[1], th[2], want_grad != 0, out, info);
+  if (threadIdx.x == 0) {
+    if (f) f[i] = out[0];
+    if (g && want_grad) { g[3 * i] = out[1]; g[3 * i + 1] = out[2]; g[3 * i + 2] = out[3]; }
+    if (sum4) {
+      atomicAdd(sum4, out[0]);
+      if (want_grad) { atomicAdd(sum4 + 1, out[1]); atomicAdd(sum4 + 2, out[2]); atomicAdd(sum4 + 3, out[3]); }
+    }
+  }
+}
+
+// One CTA runs the whole L-BFGS optimisation of theta_i for its individual (CF.R:653-659): no host
+// round trips between objective evaluations.
+__global__ void __launch_bounds__(kT) indiv_mstep_kernel(IndivData dd, IndivWork w, int nmax,
+                                                         const double* __restrict__ theta0,
+                                                         double* __restrict__ theta_out, int maxit,
+                                                         int* __restrict__ nfev, int* __restrict__ niter,
+                                                         int* __restrict__ status, int* __restrict__ info) {
+  extern __shared__ double sm[];
+  __shared__ double out[4];
+  __shared__ Lbfgs opt;
+  __shared__ int st;
+  const int i = blockIdx.x;
+  EvalSmem s = carve_eval(sm, nmax);
+  int n;
+  load_indiv(s, dd, w, i, n);
+  if (threadIdx.x == 0) {
+    lb_init(opt, 3, theta0 + 3 * (size_t)i, maxit);
+    st = LB_EVAL;
+  }
+  __syncthreads();
+  const double* c2g = w.c2 + dd.woff[i];
+  int bad = 0;
+  while (true) {
+    const double a = opt.x[0], b = opt.x[1], c = opt.x[2];
+    indiv_eval_cta(s, n, c2g, a, b, c, true, out, &bad);
+    if (threadIdx.x == 0) st = lb_advance(opt, out[0], out + 1);
+    __syncthreads();
+    if (st != LB_EVAL) break;
+  }
+  if (threadIdx.x == 0) {
+    theta_out[3 * (size_t)i] = opt.x[0];
+    theta_out[3 * (size_t)i + 1] = opt.x[1];
+    theta_out[3 * (size_t)i + 2] = opt.x[2];
+    nfev[i] = opt.nfev;
+    niter[i] = opt.iter;
+    status[i] = st;
+    (void)info;
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// host launchers
+// -------------------------------------------------------------------------------------------------
+size_t factor_smem_bytes(int nmax) {
+  const int ntot = nmax + 1, ld = ntot | 1;
+  return sizeof(double) * ((size_t)ntot * ld + 2 * (size_t)nmax) + sizeof(int) * (size_t)nmax + 16;
+}
+size_t tau_smem_bytes(int nmax, int K) {
+  return sizeof(double) * ((size_t)nmax * nmax + 2 * (size_t)nmax + 3 * (size_t)K) + sizeof(int) * (size_t)nmax + 16;
+}
+
+static cudaError_t set_smem(const void* fn, size_t bytes) {
+  if (bytes <= 48 * 1024) return cudaSuccess;
+  return cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
+cudaError_t launch_factor_scatter(cudaStream_t s, const IndivData& dd, int M, int nmax, const double* theta_i,
+                                  const double* tau, int K, double* acc, int ldN, long long strideA, double* wk,
+                                  const IndivWork& w, int* info) {
+  const size_t sm = factor_smem_bytes(nmax);
+  cudaError_t e = set_smem((const void*)indiv_factor_scatter_kernel, sm);
+  if (e != cudaSuccess) return e;
+  indiv_factor_scatter_kernel<<<M, kT, sm, s>>>(dd, theta_i, tau, K, acc, ldN, strideA, wk, w, info);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_tau(cudaStream_t s, const IndivData& dd, int M, int nmax, int K, const double* mean,
+                       const double* cov, int ldN, long long strideC, const double* pi, const IndivWork& w,
+                       double* tau_new, double* logL, int fixed_tau) {
+  const size_t sm = tau_smem_bytes(nmax, K);
+  cudaError_t e = set_smem((const void*)indiv_tau_kernel, sm);
+  if (e != cudaSuccess) return e;
+  indiv_tau_kernel<<<M, kT, sm, s>>>(dd, K, mean, cov, ldN, strideC, pi, w, tau_new, logL, fixed_tau);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_indiv_eval(cudaStream_t s, const IndivData& dd, int M, int nmax, const IndivWork& w,
+                              const double* theta, int theta_stride, int want_grad, double* f, double* g,
+                              double* sum4, int* info) {
+  const size_t sm = eval_smem_bytes(nmax);
+  cudaError_t e = set_smem((const void*)indiv_eval_kernel, sm);
+  if (e != cudaSuccess) return e;
+  indiv_eval_kernel<<<M, kT, sm, s>>>(dd, w, nmax, theta, theta_stride, want_grad, f, g, sum4, info);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_indiv_mstep(cudaStream_t s, const IndivData& dd, int M, int nmax, const IndivWork& w,
+                               const double* theta0, double* theta_out, int maxit, int* nfev, int* niter,
+                               int* status, int* info) {
+  const size_t sm = eval_smem_bytes(nmax);
+  cudaError_t e = set_smem((const void*)indiv_mstep_kernel, sm);
+  if (e != cudaSuccess) return e;
+  indiv_mstep_kernel<<<M, kT, sm, s>>>(dd, w, nmax, theta0, theta_out, maxit, nfev, niter, status, info);
+  return cudaGetLastError();
+}
+
+}  // namespace mcb

@@ -1,0 +1,44 @@
+// Launchers of the per-individual kernels (indiv.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+namespace mcb {
+
+// the training set in CSR form (device pointers)
+struct IndivData {
+  const int* off;          // [M+1]
+  const long long* woff;   // [M+1] offsets into n_i^2-sized per-individual blocks
+  const int* gidx;         // [P] grid index of each row
+  const double* t;         // [P] timestamps
+  const double* y;         // [P] outputs
+};
+
+// per-individual results kept on the device between kernels
+struct IndivWork {
+  double* Winv;    // [sum n_i^2] Psi_i^-1 at the E-step's theta_i
+  double* pvec;    // [P] Psi_i^-1 y_i
+  double* yWy;     // [M]
+  double* logdet;  // [M] log|Psi_i|
+  double* c1;      // [P]  corr1 (CF.R:236-245)
+  double* c2;      // [sum n_i^2] corr2
+  double* Fi;      // [M] F_i at the E-step's theta_i with the new tau
+};
+
+size_t factor_smem_bytes(int nmax);
+size_t tau_smem_bytes(int nmax, int K);
+size_t eval_smem_bytes(int nmax);
+
+cudaError_t launch_factor_scatter(cudaStream_t s, const IndivData& dd, int M, int nmax, const double* theta_i,
+                                  const double* tau, int K, double* acc, int ldN, long long strideA, double* wk,
+                                  const IndivWork& w, int* info);
+cudaError_t launch_tau(cudaStream_t s, const IndivData& dd, int M, int nmax, int K, const double* mean,
+                       const double* cov, int ldN, long long strideC, const double* pi, const IndivWork& w,
+                       double* tau_new, double* logL, int fixed_tau);
+cudaError_t launch_indiv_eval(cudaStream_t s, const IndivData& dd, int M, int nmax, const IndivWork& w,
+                              const double* theta, int theta_stride, int want_grad, double* f, double* g,
+                              double* sum4, int* info);
+cudaError_t launch_indiv_mstep(cudaStream_t s, const IndivData& dd, int M, int nmax, const IndivWork& w,
+                               const double* theta0, double* theta_out, int maxit, int* nfev, int* niter,
+                               int* status, int* info);
+
+}  // namespace mcb

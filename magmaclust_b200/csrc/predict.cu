@@ -1,0 +1,343 @@
+// Prediction side of the path (sm_100a):
+//   mcb_posterior_mu_k  posterior_mu_k (MC.R:196-233): the hyper-posterior block of the E-step on a prediction
+//                       grid, theta_k[3] forced to 0.1 (MC.R:206), tau frozen
+//   mcb_predict         update_tau_star_k_EM (CF.R:764-786) + pred_gp_clust (MC.R:235-274), batched over new
+//                       individuals: one CTA per new individual, clusters in sequence
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "handle.h"
+
+using namespace mcb;
+
+#define H_CUDA(expr) MCB_CUDA(h, expr)
+static inline cudaError_t sync_copy(mcb_handle* h, void* dst, const void* src, size_t bytes, cudaMemcpyKind kind) {
+  cudaError_t e = cudaMemcpyAsync(dst, src, bytes, kind, h->st);
+  return e != cudaSuccess ? e : cudaStreamSynchronize(h->st);
+}
+static inline cudaError_t sync_copy2d(mcb_handle* h, void* dst, size_t dpitch, const void* src, size_t spitch,
+                                      size_t width, size_t height, cudaMemcpyKind kind) {
+  cudaError_t e = cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, height, kind, h->st);
+  return e != cudaSuccess ? e : cudaStreamSynchronize(h->st);
+}
+#define H_CHECK(cond, code, text) \
+  do {                            \
+    if (!(cond)) {                \
+      h->err = (text);            \
+      return (code);              \
+    }                             \
+  } while (0)
+
+namespace mcb {
+
+constexpr int kTP = 256;
+constexpr int kMaxObs = 64;  // observations per new individual supported by predict_kernel
+
+__device__ __forceinline__ double wsum_p(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Sweep of the bordered (n+1) x (n+1) matrix in shared memory with kTP threads (same algorithm as indiv.cu).
+__device__ double sweep_p(double* A, int n, int ntot, int ld, int* bad) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double logdet = 0.0;
+  __syncthreads();
+  for (int k = 0; k < n; ++k) {
+    const double d = A[k * ld + k];
+    const double inv_d = 1.0 / d;
+    logdet += log(d);
+    if (!(d > 0.0) && threadIdx.x == 0) *bad = 1;
+    const double* rk = A + k * ld;
+    for (int a = warp; a < ntot; a += kTP / 32) {
+      if (a == k) continue;
+      double* ra = A + a * ld;
+      const double ca = ra[k] * inv_d;
+      for (int b = lane; b < ntot; b += 32)
+        if (b != k) ra[b] -= ca * rk[b];
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < ntot; b += kTP) {
+      if (b == k) continue;
+      const double v = A[k * ld + b] * inv_d;
+      A[k * ld + b] = v;
+      A[b * ld + k] = v;
+    }
+    if (threadIdx.x == 0) A[k * ld + k] = -inv_d;
+    __syncthreads();
+  }
+  return logdet;
+}
+
+__global__ void __launch_bounds__(kTP) predict_kernel(int K, int T, int ldT, const double* __restrict__ pgrid,
+                                                      const double* __restrict__ pmean,
+                                                      const double* __restrict__ pcov, const int* __restrict__ off,
+                                                      const int* __restrict__ oidx, const double* __restrict__ yv,
+                                                      const double* __restrict__ theta, const double* __restrict__ pik,
+                                                      int Tp, const int* __restrict__ pidx, int nmax,
+                                                      double* __restrict__ out_tau, double* __restrict__ out_mean,
+                                                      double* __restrict__ out_var, int* __restrict__ info) {
+  extern __shared__ double sm[];
+  const int b = blockIdx.x;
+  const int o0 = off[b], n = off[b + 1] - o0;
+  const int ntot = n + 1, ld = ntot | 1;
+  double* A = sm;                               // (nmax+1) x ld
+  double* ts = A + (size_t)(nmax + 1) * ((nmax + 1) | 1);
+  double* lk = ts + nmax;                       // K
+  int* idx = (int*)(lk + K);
+  const double th1 = theta[0], th2 = theta[1], sg = theta[2];
+  const double hl = exp(-th2) / 2.0;
+  const double dg = exp(th1) + sg * sg;
+  for (int a = threadIdx.x; a < n; a += kTP) {
+    idx[a] = oidx[o0 + a];
+    ts[a] = pgrid[idx[a]];
+  }
+  __syncthreads();
+  const long long sC = (long long)T * ldT;
+  for (int k = 0; k < K; ++k) {
+    const double* Ck = pcov + k * sC;
+    const double* mk = pmean + (size_t)k * ldT;
+    // S = Psi* + C_k[t*,t*], bordered with z = y* - m_k[t*]   (CF.R:776-777)
+    for (int e = threadIdx.x; e < ntot * ntot; e += kTP) {
+      const int a = e / ntot, c = e - a * ntot;
+      double v;
+      if (a < n && c < n) {
+        const double d = ts[a] - ts[c];
+        v = ((a == c) ? dg : exp(th1 - hl * (d * d))) + Ck[(size_t)idx[a] * ldT + idx[c]];
+      } else if (a < n) {
+        v = yv[o0 + a] - mk[idx[a]];
+      } else if (c < n) {
+        v = yv[o0 + c] - mk[idx[c]];
+      } else {
+        v = 0.0;
+      }
+      A[a * ld + c] = v;
+    }
+    const double logdet = sweep_p(A, n, ntot, ld, info);
+    if (threadIdx.x == 0) lk[k] = -0.5 * ((double)n * kLog2Pi + logdet - A[n * ld + n]);  // dmvnorm, CF.R:780
+    if (out_mean) {
+      // Mean_k = m_k[tp] + Gamma' S^-1 z ; Var_k = diag(Sigma(tp) + C_k[tp,tp] - Gamma' S^-1 Gamma)  (MC.R:261-268)
+      for (int j = threadIdx.x; j < Tp; j += kTP) {
+        const int gj = pidx[j];
+        const double tj = pgrid[gj];
+        double gcol[kMaxObs];  // Gamma[:, j] = k(t*, tp_j) + C_k[t*, tp_j]   (MC.R:263)
+        double mean = mk[gj];
+        for (int a = 0; a < n; ++a) {
+          const double da = ts[a] - tj;
+          const double ga = exp(th1 - hl * (da * da)) + Ck[(size_t)idx[a] * ldT + gj];
+          gcol[a] = ga;
+          mean += ga * A[a * ld + n];
+        }
+        double quad = 0.0;
+        for (int a = 0; a < n; ++a) {
+          double row = 0.0;
+          for (int c = 0; c < n; ++c) row -= A[a * ld + c] * gcol[c];  // A block = -S^-1
+          quad += gcol[a] * row;
+        }
+        const size_t o = ((size_t)b * K + k) * Tp + j;
+        out_mean[o] = mean;
+        out_var[o] = dg + Ck[(size_t)gj * ldT + gj] - quad;
+      }
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    double mx = lk[0];
+    for (int k = 1; k < K; ++k) mx = fmax(mx, lk[k]);
+    double den = 0.0;
+    for (int k = 0; k < K; ++k) {
+      lk[k] = pik[k] * exp(lk[k] - mx);
+      den += lk[k];
+    }
+    for (int k = 0; k < K; ++k) out_tau[(size_t)b * K + k] = lk[k] / den;
+  }
+}
+
+}  // namespace mcb
+
+extern "C" int mcb_posterior_mu_k(mcb_handle* h, int T, const double* timestamps, const double* tau,
+                                  double* out_mean, double* out_cov) {
+  if (!h || !timestamps) return MCB_EINVAL;
+  H_CHECK(h->has_state, MCB_ESTATE, "mcb_posterior_mu_k: no trained state");
+  H_CHECK(tau != nullptr || h->has_post, MCB_ESTATE, "mcb_posterior_mu_k: pass tau or run the E-step first");
+  H_CHECK(T >= 1, MCB_EINVAL, "mcb_posterior_mu_k: T < 1");
+  for (int j = 1; j < T; ++j) H_CHECK(timestamps[j] > timestamps[j - 1], MCB_EINVAL, "mcb_posterior_mu_k: timestamps must be sorted and unique");
+  H_CUDA(cudaSetDevice(h->device));
+  const int M = h->M, K = h->K, N = h->N;
+  const int ldT = (T + 3) & ~3;
+  const long long sT = (long long)T * ldT;
+  // position of every training timestamp in the prediction grid (MC.R:323 builds t_pred as a superset)
+  std::vector<double> grid(N);
+  H_CUDA(sync_copy(h, grid.data(), h->grid.p, sizeof(double) * N, cudaMemcpyDeviceToHost));
+  std::vector<int> gpos(N);
+  for (int j = 0; j < N; ++j) {
+    const double* it = std::lower_bound(timestamps, timestamps + T, grid[j]);
+    H_CHECK(it != timestamps + T && *it == grid[j], MCB_EINVAL,
+            "mcb_posterior_mu_k: the prediction grid must contain every training timestamp");
+    gpos[j] = (int)(it - timestamps);
+  }
+  std::vector<int> gidx((size_t)h->P);
+  H_CUDA(sync_copy(h, gidx.data(), h->gidx.p, sizeof(int) * h->P, cudaMemcpyDeviceToHost));
+  for (auto& v : gidx) v = gpos[v];
+  H_CUDA(h->pmapidx.ensure(h->P));
+  H_CUDA(sync_copy(h, h->pmapidx.p, gidx.data(), sizeof(int) * h->P, cudaMemcpyHostToDevice));
+  H_CUDA(h->pgrid.ensure(T));
+  H_CUDA(sync_copy(h, h->pgrid.p, timestamps, sizeof(double) * T, cudaMemcpyHostToDevice));
+  H_CUDA(h->pKinv.ensure((size_t)K * sT)); H_CUDA(h->pcov.ensure((size_t)K * sT));
+  H_CUDA(h->pwk.ensure((size_t)K * ldT)); H_CUDA(h->pmean.ensure((size_t)K * ldT)); H_CUDA(h->plogdet.ensure(2 * K));
+  const double* tau_d = h->tau_new.p;
+  if (tau) {
+    H_CUDA(sync_copy(h, h->logL.p, tau, sizeof(double) * (size_t)M * K, cudaMemcpyHostToDevice));  // logL reused as staging
+    tau_d = h->logL.p;
+  }
+  h->spans.clear(); h->ev_next = 0; h->launches = 0;
+  // theta_k with the third entry forced to 0.1 (MC.R:206)
+  std::vector<double> thk(h->h_theta_k);
+  for (int k = 0; k < K; ++k) thk[3 * k + 2] = 0.1;
+  std::vector<int> gmap(K, -1);
+  std::vector<double> groups;
+  int G = 0;
+  for (int k = 0; k < K; ++k) {
+    for (int g = 0; g < G; ++g)
+      if (groups[3 * g] == thk[3 * k] && groups[3 * g + 1] == thk[3 * k + 1]) { gmap[k] = g; break; }
+    if (gmap[k] < 0) { gmap[k] = G++; groups.insert(groups.end(), thk.begin() + 3 * k, thk.begin() + 3 * k + 3); }
+  }
+  H_CUDA(sync_copy(h, h->egmap.p, gmap.data(), sizeof(int) * K, cudaMemcpyHostToDevice));
+  H_CUDA(sync_copy(h, h->etheta.p, groups.data(), sizeof(double) * 3 * G, cudaMemcpyHostToDevice));
+  // prior means on the prediction grid: scalar priors replicate; vector priors need T == N
+  std::vector<double> mk((size_t)K * h->ld), mkT((size_t)K * ldT, 0.0);
+  H_CUDA(sync_copy(h, mk.data(), h->mk.p, sizeof(double) * K * h->ld, cudaMemcpyDeviceToHost));
+  for (int k = 0; k < K; ++k) {
+    bool constant = true;
+    for (int j = 1; j < N; ++j) constant = constant && mk[(size_t)k * h->ld + j] == mk[(size_t)k * h->ld];
+    H_CHECK(constant || T == N, MCB_EINVAL, "mcb_posterior_mu_k: vector prior means need T == N");
+    for (int j = 0; j < T; ++j) mkT[(size_t)k * ldT + j] = constant ? mk[(size_t)k * h->ld] : mk[(size_t)k * h->ld + j];
+  }
+  H_CUDA(h->eX.ensure(std::max((size_t)K * ldT, h->eX.cap)));
+  double* mkT_d = h->pmean.p;  // staged here, overwritten by the result below
+  H_CUDA(sync_copy(h, mkT_d, mkT.data(), sizeof(double) * K * ldT, cudaMemcpyHostToDevice));
+  {
+    se_build(h->st, h->pKinv.p, nullptr, nullptr, T, ldT, sT, h->pgrid.p, h->etheta.p, 3, G, &h->launches);
+    H_CUDA(spd_inverse(h->st, h->pKinv.p, T, ldT, sT, G, h->plogdet.p, h->info.p, h->ws, &h->launches));
+    copy_mapped(h->st, T, ldT, sT, h->pKinv.p, h->egmap.p, h->pcov.p, K, h->rank == 0 ? 1.0 : 0.0, &h->launches);
+    if (h->rank == 0) symv_mapped(h->st, T, ldT, sT, h->pKinv.p, h->egmap.p, mkT_d, h->pwk.p, K, &h->launches);
+    else H_CUDA(cudaMemsetAsync(h->pwk.p, 0, sizeof(double) * K * ldT, h->st));
+    IndivData dd = h->idata();
+    dd.gidx = h->pmapidx.p;
+    H_CUDA(launch_factor_scatter(h->st, dd, M, h->nmax, h->theta_i.p, tau_d, K, h->pcov.p, ldT, sT, h->pwk.p,
+                                 h->iwork(), h->info.p));
+    ++h->launches;
+    MCB_TRY(comm_allreduce_sum(h, h->pcov.p, (size_t)K * sT));
+    MCB_TRY(comm_allreduce_sum(h, h->pwk.p, (size_t)K * ldT));
+    H_CUDA(spd_inverse(h->st, h->pcov.p, T, ldT, sT, K, h->plogdet.p + K, h->info.p, h->ws, &h->launches));
+    symv(h->st, T, h->pcov.p, ldT, sT, h->pwk.p, ldT, h->pmean.p, ldT, K, &h->launches);
+  }
+  int flag = 0;
+  H_CUDA(cudaMemcpyAsync(&flag, h->info.p, sizeof(int), cudaMemcpyDeviceToHost, h->st));
+  H_CUDA(cudaStreamSynchronize(h->st));
+  if (flag) {
+    cudaMemsetAsync(h->info.p, 0, sizeof(int), h->st);
+    h->err = "posterior_mu_k: a covariance matrix is not positive definite";
+    return MCB_ENOTPD;
+  }
+  // pi_k = mean_i tau_ik of the frozen tau (MC.R:141), kept for mcb_predict
+  tau_colsum(h->st, M, K, tau_d, h->plogdet.p, &h->launches);
+  MCB_TRY(comm_allreduce_sum(h, h->plogdet.p, K));
+  h->h_pi_pred.resize(K);
+  H_CUDA(sync_copy(h, h->h_pi_pred.data(), h->plogdet.p, sizeof(double) * K, cudaMemcpyDeviceToHost));
+  for (auto& v : h->h_pi_pred) v /= (double)h->M_total;
+  h->T = T; h->ldT = ldT; h->has_pred = true;
+  if (out_mean)
+    H_CUDA(sync_copy2d(h, out_mean, sizeof(double) * T, h->pmean.p, sizeof(double) * ldT, sizeof(double) * T, K, cudaMemcpyDeviceToHost));
+  if (out_cov)
+    for (int k = 0; k < K; ++k)
+      H_CUDA(sync_copy2d(h, out_cov + (size_t)k * T * T, sizeof(double) * T, h->pcov.p + k * sT, sizeof(double) * ldT,
+                          sizeof(double) * T, T, cudaMemcpyDeviceToHost));
+  return MCB_OK;
+}
+
+extern "C" int mcb_predict(mcb_handle* h, int B, const int* offsets, const int* obs_idx, const double* y,
+                           const double* theta_new, const double* pi_k, int Tp, const int* pred_idx,
+                           double* out_tau, double* out_mean, double* out_var) {
+  if (!h || !offsets || !obs_idx || !y || !theta_new || !out_tau) return MCB_EINVAL;
+  H_CHECK(h->has_pred, MCB_ESTATE, "mcb_predict: call mcb_posterior_mu_k first");
+  H_CHECK(B >= 1 && offsets[0] == 0, MCB_EINVAL, "mcb_predict: bad offsets");
+  H_CHECK((out_mean == nullptr) == (out_var == nullptr), MCB_EINVAL, "mcb_predict: pass both out_mean and out_var or neither");
+  H_CHECK(out_mean == nullptr || (Tp >= 1 && pred_idx), MCB_EINVAL, "mcb_predict: prediction targets missing");
+  const int K = h->K, T = h->T;
+  const long long Pn = offsets[B];
+  int nmax = 0;
+  for (int b = 0; b < B; ++b) {
+    const int n = offsets[b + 1] - offsets[b];
+    H_CHECK(n >= 1, MCB_EINVAL, "mcb_predict: empty new individual");
+    nmax = std::max(nmax, n);
+    for (int a = offsets[b]; a < offsets[b + 1]; ++a) {
+      H_CHECK(obs_idx[a] >= 0 && obs_idx[a] < T, MCB_EINVAL, "mcb_predict: obs_idx out of range");
+      H_CHECK(a == offsets[b] || obs_idx[a] > obs_idx[a - 1], MCB_EINVAL, "mcb_predict: observations must be sorted and unique");
+    }
+  }
+  if (out_mean) for (int j = 0; j < Tp; ++j) H_CHECK(pred_idx[j] >= 0 && pred_idx[j] < T, MCB_EINVAL, "mcb_predict: pred_idx out of range");
+  const size_t smem = sizeof(double) * ((size_t)(nmax + 1) * ((nmax + 1) | 1) + nmax + K) + sizeof(int) * nmax + 16;
+  H_CHECK(nmax <= kMaxObs && smem <= 227 * 1024, MCB_EINVAL,
+          "mcb_predict: more than 64 observations for one new individual is not supported yet");
+  H_CUDA(cudaSetDevice(h->device));
+  h->spans.clear(); h->ev_next = 0; h->launches = 0;
+  mcb::DevBuf<int> d_off, d_idx, d_pidx;
+  mcb::DevBuf<double> d_y, d_small, d_tau, d_mean, d_var;
+  auto cleanup = [&]() {
+    d_off.release(); d_idx.release(); d_pidx.release(); d_y.release(); d_small.release(); d_tau.release();
+    d_mean.release(); d_var.release();
+  };
+  cudaError_t e = cudaSuccess;
+  const size_t nout = out_mean ? (size_t)B * K * Tp : 0;
+  if ((e = d_off.ensure(B + 1)) || (e = d_idx.ensure(Pn)) || (e = d_y.ensure(Pn)) || (e = d_small.ensure(3 + K)) ||
+      (e = d_tau.ensure((size_t)B * K)) || (e = d_pidx.ensure(std::max(Tp, 1))) ||
+      (nout && ((e = d_mean.ensure(nout)) || (e = d_var.ensure(nout))))) {
+    cleanup();
+    h->err = std::string("mcb_predict: ") + cudaGetErrorString(e);
+    return MCB_ENOMEM;
+  }
+  std::vector<double> small(theta_new, theta_new + 3);
+  if (pi_k) small.insert(small.end(), pi_k, pi_k + K);
+  else small.insert(small.end(), h->h_pi_pred.begin(), h->h_pi_pred.end());
+  cudaMemcpyAsync(d_off.p, offsets, sizeof(int) * (B + 1), cudaMemcpyHostToDevice, h->st);
+  cudaMemcpyAsync(d_idx.p, obs_idx, sizeof(int) * Pn, cudaMemcpyHostToDevice, h->st);
+  cudaMemcpyAsync(d_y.p, y, sizeof(double) * Pn, cudaMemcpyHostToDevice, h->st);
+  cudaMemcpyAsync(d_small.p, small.data(), sizeof(double) * (3 + K), cudaMemcpyHostToDevice, h->st);
+  if (out_mean) cudaMemcpyAsync(d_pidx.p, pred_idx, sizeof(int) * Tp, cudaMemcpyHostToDevice, h->st);
+  if (smem > 48 * 1024) cudaFuncSetAttribute(predict_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  {
+    int e0 = (int)h->evpool.size();
+    cudaEvent_t a, b2;
+    cudaEventCreate(&a); cudaEventCreate(&b2);
+    h->evpool.push_back(a); h->evpool.push_back(b2);
+    cudaEventRecord(a, h->st);
+    predict_kernel<<<B, kTP, smem, h->st>>>(K, T, h->ldT, h->pgrid.p, h->pmean.p, h->pcov.p, d_off.p, d_idx.p, d_y.p,
+                                            d_small.p, d_small.p + 3, Tp, d_pidx.p, nmax, d_tau.p,
+                                            out_mean ? d_mean.p : nullptr, out_mean ? d_var.p : nullptr, h->info.p);
+    cudaEventRecord(b2, h->st);
+    h->spans.push_back({PH_PRED, e0, e0 + 1});
+    ++h->launches;
+  }
+  cudaMemcpyAsync(out_tau, d_tau.p, sizeof(double) * (size_t)B * K, cudaMemcpyDeviceToHost, h->st);
+  if (out_mean) {
+    cudaMemcpyAsync(out_mean, d_mean.p, sizeof(double) * nout, cudaMemcpyDeviceToHost, h->st);
+    cudaMemcpyAsync(out_var, d_var.p, sizeof(double) * nout, cudaMemcpyDeviceToHost, h->st);
+  }
+  int flag = 0;
+  cudaMemcpyAsync(&flag, h->info.p, sizeof(int), cudaMemcpyDeviceToHost, h->st);
+  e = cudaStreamSynchronize(h->st);
+  cleanup();
+  if (e != cudaSuccess) {
+    h->err = std::string("mcb_predict: ") + cudaGetErrorString(e);
+    return MCB_ECUDA;
+  }
+  if (flag) {
+    cudaMemsetAsync(h->info.p, 0, sizeof(int), h->st);
+    h->err = "mcb_predict: Psi* + C_k[t*,t*] is not positive definite";
+    return MCB_ENOTPD;
+  }
+  return MCB_OK;
+}

@@ -1,0 +1,263 @@
+"""Array-level wrapper over the C ABI: one `Engine` = one `mcb_handle` = one GPU.
+
+This is host plumbing only (numpy arrays in, numpy arrays out); all arithmetic happens in the CUDA
+library. `magmaclust_b200.magma` builds the reference's R-shaped API (dicts / named matrices) on top.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import McbError, dptr, f64, i32, iptr
+
+PHASES = ("indiv_factor_scatter", "dense_hyperpost", "indiv_tau", "mstep_indiv", "mstep_mean", "elbo",
+          "predict", "collectives")
+
+
+class Engine:
+    def __init__(self, device: int = 0):
+        self.lib = _lib.load()
+        if self.lib.mcb_device_count() <= 0:
+            raise RuntimeError("magmaclust_b200: no CUDA device visible and there is no CPU fallback")
+        h = _lib.H()
+        rc = self.lib.mcb_create(C.byref(h), device)
+        if rc != 0:
+            raise McbError(rc, (self.lib.mcb_last_error(None) or b"").decode())
+        self.h = h
+        self.M = self.N = self.K = 0
+        self.T = 0
+
+    # ------------------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.mcb_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise McbError(rc, (self.lib.mcb_last_error(self.h) or b"").decode())
+
+    # ------------------------------------------------------------------------------------------
+    def comm_init(self, nranks: int, rank: int, unique_id: bytes):
+        buf = (C.c_ubyte * 128).from_buffer_copy(unique_id)
+        self._ck(self.lib.mcb_comm_init(self.h, nranks, rank, buf))
+
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        lib = _lib.load()
+        buf = (C.c_ubyte * 128)()
+        rc = lib.mcb_comm_unique_id(buf)
+        if rc != 0:
+            raise McbError(rc, "mcb_comm_unique_id failed (NCCL not loadable?)")
+        return bytes(buf)
+
+    # ------------------------------------------------------------------------------------------
+    def set_data(self, offsets, grid_idx, y, grid, M_total=None):
+        offsets, grid_idx, y, grid = i32(offsets), i32(grid_idx), f64(y), f64(grid)
+        M, N, P = offsets.shape[0] - 1, grid.shape[0], y.shape[0]
+        self._ck(self.lib.mcb_set_data(self.h, M, N, P, iptr(offsets), iptr(grid_idx), dptr(y), dptr(grid),
+                                       M if M_total is None else M_total))
+        self.M, self.N, self.P = M, N, P
+        self.K = 0
+
+    def set_state(self, theta_k, theta_i, pi_k, m_k, tau):
+        theta_k, theta_i, pi_k, m_k, tau = f64(theta_k), f64(theta_i), f64(pi_k), f64(m_k).ravel(), f64(tau)
+        K = theta_k.shape[0]
+        assert theta_k.shape == (K, 3) and theta_i.shape == (self.M, 3) and tau.shape == (self.M, K)
+        self._ck(self.lib.mcb_set_state(self.h, K, dptr(theta_k), dptr(theta_i), dptr(pi_k), dptr(m_k),
+                                        m_k.shape[0], dptr(tau)))
+        self.K = K
+
+    def get_hp(self):
+        tk, ti, pi = np.empty((self.K, 3)), np.empty((self.M, 3)), np.empty(self.K)
+        self._ck(self.lib.mcb_get_hp(self.h, dptr(tk), dptr(ti), dptr(pi)))
+        return tk, ti, pi
+
+    def get_tau(self):
+        t = np.empty((self.M, self.K))
+        self._ck(self.lib.mcb_get_tau(self.h, dptr(t)))
+        return t
+
+    # ------------------------------------------------------------------------------------------
+    def e_step(self):
+        self._ck(self.lib.mcb_e_step(self.h))
+
+    def get_mean(self):
+        m = np.empty((self.K, self.N))
+        self._ck(self.lib.mcb_get_mean(self.h, dptr(m)))
+        return m
+
+    def get_cov(self, k=None):
+        if k is not None:
+            c = np.empty((self.N, self.N))
+            self._ck(self.lib.mcb_get_cov(self.h, k, dptr(c)))
+            return c
+        return np.stack([self.get_cov(kk) for kk in range(self.K)])
+
+    def get_tau_new(self):
+        t = np.empty((self.M, self.K))
+        self._ck(self.lib.mcb_get_tau_new(self.h, dptr(t)))
+        return t
+
+    def get_mat_logL(self):
+        t = np.empty((self.M, self.K))
+        self._ck(self.lib.mcb_get_mat_logL(self.h, dptr(t)))
+        return t
+
+    def get_logdet_cov(self):
+        t = np.empty(self.K)
+        self._ck(self.lib.mcb_get_logdet_cov(self.h, dptr(t)))
+        return t
+
+    def accept_tau(self):
+        self._ck(self.lib.mcb_accept_tau(self.h))
+
+    def e_step_VEM(self, theta_k, theta_i, pi_k, m_k, old_tau, want_cov=True, want_logL=False):
+        """host buffers in, host buffers out: the call the `.Call` shim makes for e_step_VEM"""
+        theta_k, theta_i, pi_k, m_k, old_tau = f64(theta_k), f64(theta_i), f64(pi_k), f64(m_k).ravel(), f64(old_tau)
+        K = theta_k.shape[0]
+        mean = np.empty((K, self.N))
+        cov = np.empty((K, self.N, self.N)) if want_cov else None
+        tau = np.empty((self.M, K))
+        logL = np.empty((self.M, K)) if want_logL else None
+        self._ck(self.lib.mcb_e_step_VEM(self.h, K, dptr(theta_k), dptr(theta_i), dptr(pi_k), dptr(m_k), m_k.shape[0],
+                                         dptr(old_tau), dptr(mean), dptr(cov), dptr(tau), dptr(logL)))
+        self.K = K
+        return mean, cov, tau, logL
+
+    def set_posterior(self, mean, cov, tau):
+        mean, cov, tau = f64(mean), f64(cov), f64(tau)
+        assert mean.shape == (self.K, self.N) and cov.shape == (self.K, self.N, self.N) and tau.shape == (self.M, self.K)
+        self._ck(self.lib.mcb_set_posterior(self.h, dptr(mean), dptr(cov), dptr(tau)))
+
+    # ------------------------------------------------------------------------------------------
+    def eval_indiv(self, theta, grad=True):
+        theta = f64(theta)
+        assert theta.shape == (self.M, 3)
+        f = np.empty(self.M)
+        g = np.empty((self.M, 3)) if grad else None
+        self._ck(self.lib.mcb_eval_indiv(self.h, dptr(theta), dptr(f), dptr(g)))
+        return f, g
+
+    def eval_indiv_common(self, theta, grad=True):
+        theta = f64(theta)
+        f = np.empty(1)
+        g = np.empty(3) if grad else None
+        self._ck(self.lib.mcb_eval_indiv_common(self.h, dptr(theta), dptr(f), dptr(g)))
+        return float(f[0]), g
+
+    def eval_mean(self, k, theta, pen_diag=0.0, grad=True):
+        theta = f64(theta)
+        nhp = theta.shape[0]
+        f = np.empty(1)
+        g = np.empty(nhp) if grad else None
+        self._ck(self.lib.mcb_eval_mean(self.h, k, dptr(theta), nhp, float(pen_diag), dptr(f), dptr(g)))
+        return float(f[0]), g
+
+    def eval_mean_common(self, theta, pen_diag=0.0, grad=True):
+        theta = f64(theta)
+        nhp = theta.shape[0]
+        f = np.empty(1)
+        g = np.empty(nhp) if grad else None
+        self._ck(self.lib.mcb_eval_mean_common(self.h, dptr(theta), nhp, float(pen_diag), dptr(f), dptr(g)))
+        return float(f[0]), g
+
+    def elbo(self, theta_k=None, theta_i=None):
+        out = np.empty(2)
+        tk = f64(theta_k) if theta_k is not None else None
+        ti = f64(theta_i) if theta_i is not None else None
+        self._ck(self.lib.mcb_elbo(self.h, dptr(tk), dptr(ti), dptr(out)))
+        return float(out[0]), float(out[1])
+
+    def m_step(self, common_hp_k=True, common_hp_i=True):
+        tk, ti, pi = np.empty((self.K, 3)), np.empty((self.M, 3)), np.empty(self.K)
+        stats = np.zeros(4, dtype=np.int32)
+        self._ck(self.lib.mcb_m_step(self.h, int(common_hp_k), int(common_hp_i), dptr(tk), dptr(ti), dptr(pi),
+                                     iptr(stats)))
+        return tk, ti, pi, {"nfev_i": int(stats[0]), "nfev_k": int(stats[1]), "nit_i": int(stats[2]),
+                            "nit_k": int(stats[3])}
+
+    def get_new_hp(self):
+        tk, ti, pi = np.empty((self.K, 3)), np.empty((self.M, 3)), np.empty(self.K)
+        self._ck(self.lib.mcb_get_new_hp(self.h, dptr(tk), dptr(ti), dptr(pi)))
+        return tk, ti, pi
+
+    def accept_hp(self):
+        self._ck(self.lib.mcb_accept_hp(self.h))
+
+    def vem_iteration(self, common_hp_k=True, common_hp_i=True):
+        out = np.empty(3)
+        self._ck(self.lib.mcb_vem_iteration(self.h, int(common_hp_k), int(common_hp_i), dptr(out)))
+        return float(out[0]), float(out[1]), bool(out[2] != 0.0)
+
+    # ------------------------------------------------------------------------------------------
+    def posterior_mu_k(self, timestamps, tau=None, want_mean=True, want_cov=True):
+        ts = f64(timestamps)
+        T = ts.shape[0]
+        mean = np.empty((self.K, T)) if want_mean else None
+        cov = np.empty((self.K, T, T)) if want_cov else None
+        t = f64(tau) if tau is not None else None
+        self._ck(self.lib.mcb_posterior_mu_k(self.h, T, dptr(ts), dptr(t), dptr(mean), dptr(cov)))
+        self.T = T
+        return mean, cov
+
+    def predict(self, offsets, obs_idx, y, theta_new, pred_idx=None, pi_k=None):
+        offsets, obs_idx, y, theta_new = i32(offsets), i32(obs_idx), f64(y), f64(theta_new)
+        B = offsets.shape[0] - 1
+        tau = np.empty((B, self.K))
+        pi = f64(pi_k) if pi_k is not None else None
+        if pred_idx is None:
+            self._ck(self.lib.mcb_predict(self.h, B, iptr(offsets), iptr(obs_idx), dptr(y), dptr(theta_new), dptr(pi), 0,
+                                          None, dptr(tau), None, None))
+            return tau, None, None
+        pred_idx = i32(pred_idx)
+        Tp = pred_idx.shape[0]
+        mean = np.empty((B, self.K, Tp))
+        var = np.empty((B, self.K, Tp))
+        self._ck(self.lib.mcb_predict(self.h, B, iptr(offsets), iptr(obs_idx), dptr(y), dptr(theta_new), dptr(pi), Tp,
+                                      iptr(pred_idx), dptr(tau), dptr(mean), dptr(var)))
+        return tau, mean, var
+
+    # ------------------------------------------------------------------------------------------
+    def last_timings(self):
+        ms = (C.c_float * 8)()
+        n = C.c_longlong(0)
+        self._ck(self.lib.mcb_last_timings(self.h, ms, C.byref(n)))
+        return {p: float(ms[i]) for i, p in enumerate(PHASES)}, int(n.value)
+
+    def last_mstep_stats(self):
+        out = (C.c_longlong * 6)()
+        self._ck(self.lib.mcb_last_mstep_stats(self.h, out))
+        return {"nfev_i_max": out[0], "nfev_k": out[1], "nit_i": out[2], "nit_k": out[3], "nfev_i_sum": out[4],
+                "M_local": out[5]}
+
+    def pin(self, arr):
+        """page-lock a numpy array in place (cudaHostRegister); returns True on success"""
+        return self.lib.mcb_pin_host(arr.ctypes.data_as(C.c_void_p), arr.nbytes) == 0
+
+    def unpin(self, arr):
+        self.lib.mcb_unpin_host(arr.ctypes.data_as(C.c_void_p))
+
+    def timer_start(self):
+        self._ck(self.lib.mcb_timer_start(self.h))
+
+    def timer_stop(self):
+        ms = C.c_float(0)
+        self._ck(self.lib.mcb_timer_stop(self.h, C.byref(ms)))
+        return float(ms.value)
+
+    def flush_l2(self):
+        self._ck(self.lib.mcb_flush_l2(self.h))
+
+    def measure_fp64_peaks(self):
+        out = np.empty(2)
+        self._ck(self.lib.mcb_measure_fp64_peaks(self.h, dptr(out)))
+        return {"dfma_tflops": float(out[0]), "dmma_tflops": float(out[1])}

@@ -1,0 +1,451 @@
+"""Host-side mirror of the reference's R interface for the VEM hot path, on top of the CUDA library.
+
+Same function names, argument order and nested-list result shapes as `/root/reference/
+Computing_functions.R` (CF.R) and `MAGMAclust.R` (MC.R), with R lists rendered as dicts:
+
+    db        {'ID': array, 'Timestamp': array, 'Output': array}          (tibble columns, MC.R:22)
+    m_k       {'K1': 0.0, ...}                                            (prior means, MC.R:16)
+    hp        {'theta_k': {k: [a, b, sigma]}, 'theta_i': {id: [a, b, sigma]}, 'pi_k': array[K]}
+    tau_i_k   {k: {id: tau}}                                              (CF.R:757-761)
+    param     {'mean': {k: {'Timestamp', 'Output'}}, 'cov': {k: NamedMat}, 'tau_i_k': ...}   (CF.R:628)
+
+Everything numerical runs on the GPU through `Engine` (the C ABI); this module only reshapes. Kernels are
+passed as the sentinels `kernel` / `kernel_mu` (both the squared-exponential of CF.R:43-59): the reference
+hard-codes SE derivatives (CF.R:436-446), so any other closure is rejected rather than silently ignored.
+R itself is not available in the build image; the `.Call` shim that exposes the same C ABI to R is in
+`r/` (source only) and INTEGRATION.md.
+"""
+from __future__ import annotations
+
+import time
+
+import numpy as np
+
+from .engine import Engine
+
+
+# ---------------------------------------------------------------------------------------------
+def kernel(mat, theta=(1.0, 0.5)):
+    """CF.R:43-50 — the SE kernel on squared distances (host formula kept for documentation/tests;
+    the GPU path recognises this function object and evaluates the same formula on the device)."""
+    return np.exp(theta[0] - np.exp(-theta[1]) / 2.0 * np.asarray(mat, dtype=np.float64))
+
+
+def kernel_mu(mat, theta=(1.0, 0.5)):
+    """CF.R:52-59 — same SE kernel, used for the mean processes."""
+    return np.exp(theta[0] - np.exp(-theta[1]) / 2.0 * np.asarray(mat, dtype=np.float64))
+
+
+def _check_kernels(*kerns):
+    for k in kerns:
+        if k is not kernel and k is not kernel_mu:
+            raise ValueError("only the reference's squared-exponential kernels (kernel, kernel_mu) are "
+                             "implemented on the GPU path; other closures are rejected (no fallback)")
+
+
+class NamedMat:
+    """Square matrix named by timestamps, standing in for R's dimnames 'X<t>' (CF.R:83,146)."""
+
+    __slots__ = ("m", "t", "_pos")
+
+    def __init__(self, m, t):
+        self.m = np.asarray(m, dtype=np.float64)
+        self.t = np.asarray(t, dtype=np.float64)
+        self._pos = None
+
+    def pos(self, ts):
+        if self._pos is None:
+            self._pos = {float(v): j for j, v in enumerate(self.t)}
+        return np.array([self._pos[float(v)] for v in np.atleast_1d(ts)], dtype=np.int64)
+
+    def sub(self, rows, cols=None):
+        r = self.pos(rows)
+        c = r if cols is None else self.pos(cols)
+        return self.m[np.ix_(r, c)]
+
+
+# ---------------------------------------------------------------------------------------------
+class Canon:
+    """CSR canonicalisation of a `db` (replaces tibble filtering and string-named indexing)."""
+
+    def __init__(self, db):
+        ids = np.asarray(db["ID"])
+        ts = np.asarray(db["Timestamp"], dtype=np.float64)
+        ys = np.asarray(db["Output"], dtype=np.float64)
+        _, first = np.unique(ids, return_index=True)
+        self.ids = [i.item() if isinstance(i, np.generic) else i for i in ids[np.sort(first)]]  # unique(db$ID)
+        order = np.concatenate([np.nonzero(ids == i)[0] for i in self.ids]) if len(self.ids) else np.zeros(0, int)
+        counts = np.array([(ids == i).sum() for i in self.ids], dtype=np.int64)
+        self.offsets = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
+        self.grid = np.unique(ts)  # sort(unique(db$Timestamp)), CF.R:601
+        self.t = ts[order]
+        self.y = np.ascontiguousarray(ys[order])
+        self.grid_idx = np.searchsorted(self.grid, self.t).astype(np.int32)
+        for a in range(len(self.ids)):
+            seg = self.grid_idx[self.offsets[a]:self.offsets[a + 1]]
+            if np.any(np.diff(seg) <= 0):
+                raise ValueError(f"rows of individual {self.ids[a]!r} must be sorted by Timestamp and unique "
+                                 "(the reference assumes it, SURVEY.md §8.0 Q2)")
+        self.M, self.N = len(self.ids), self.grid.shape[0]
+        self.fingerprint = (ids.shape[0], float(ts.sum()), float(ys.sum()), self.M)
+
+
+class Session:
+    """One GPU engine plus the bookkeeping that lets R-style stateless calls reuse resident device state."""
+
+    def __init__(self, device: int = 0):
+        self.eng = Engine(device)
+        self.canon = None
+        self._post_token = None
+        self._epoch = 0
+
+    def close(self):
+        self.eng.close()
+
+    # -- data ------------------------------------------------------------------------------------
+    def ensure_data(self, db):
+        fp = None
+        if self.canon is not None:
+            ids = np.asarray(db["ID"])
+            fp = (ids.shape[0], float(np.asarray(db["Timestamp"], dtype=np.float64).sum()),
+                  float(np.asarray(db["Output"], dtype=np.float64).sum()), self.canon.M)
+        if self.canon is None or fp != self.canon.fingerprint:
+            c = Canon(db)
+            self.eng.set_data(c.offsets, c.grid_idx, c.y, c.grid)
+            self.canon = c
+            self._post_token = None
+        return self.canon
+
+    # -- packing -----------------------------------------------------------------------------------
+    def pack_hp(self, hp, names_k):
+        c = self.canon
+        theta_k = np.array([np.asarray(hp["theta_k"][k], dtype=np.float64)[:3] for k in names_k])
+        theta_i = np.array([np.asarray(hp["theta_i"][i], dtype=np.float64).ravel()[:3] for i in c.ids])
+        return theta_k, theta_i
+
+    def pack_tau(self, tau_i_k, names_k):
+        c = self.canon
+        return np.array([[tau_i_k[k][i] for k in names_k] for i in c.ids], dtype=np.float64)
+
+    def unpack_tau(self, arr, names_k):
+        c = self.canon
+        return {k: {i: float(arr[r, ck]) for r, i in enumerate(c.ids)} for ck, k in enumerate(names_k)}
+
+    def pack_mk(self, m_k, names_k):
+        vals = [np.atleast_1d(np.asarray(m_k[k], dtype=np.float64)) for k in names_k]
+        if all(v.shape[0] == 1 for v in vals):
+            return np.array([v[0] for v in vals])
+        N = self.canon.N
+        return np.concatenate([np.repeat(v, N) if v.shape[0] == 1 else v for v in vals])
+
+    def param_from_device(self, names_k, tau_arr, want_cov=True):
+        c = self.canon
+        mean = self.eng.get_mean()
+        out = {"mean": {k: {"Timestamp": c.grid, "Output": mean[ck]} for ck, k in enumerate(names_k)},
+               "tau_i_k": self.unpack_tau(tau_arr, names_k)}
+        if want_cov:
+            out["cov"] = {k: NamedMat(self.eng.get_cov(ck), c.grid) for ck, k in enumerate(names_k)}
+        self._epoch += 1
+        self._post_token = (id(self), self._epoch)
+        out["_token"] = self._post_token
+        return out
+
+    def ensure_posterior(self, hp, m_k, param):
+        """make (hp, param) the resident state; no copies when `param` is what the last E-step left"""
+        names_k = list(param["mean"].keys())
+        if param.get("_token") is not None and param.get("_token") == self._post_token and \
+                self._hp_matches(hp, names_k):
+            return names_k
+        theta_k, theta_i = self.pack_hp(hp, names_k)
+        tau = self.pack_tau(param["tau_i_k"], names_k)
+        pi = np.asarray(hp.get("pi_k", np.full(len(names_k), 1.0 / len(names_k))), dtype=np.float64)
+        self.eng.set_state(theta_k, theta_i, pi, self.pack_mk(m_k, names_k), tau)
+        mean = np.array([np.asarray(param["mean"][k]["Output"], dtype=np.float64) for k in names_k])
+        cov = np.array([param["cov"][k].m for k in names_k])
+        self.eng.set_posterior(mean, cov, tau)
+        self._post_token = None
+        return names_k
+
+    def _hp_matches(self, hp, names_k):
+        tk, ti, _ = self.eng.get_hp()
+        a, b = self.pack_hp(hp, names_k)
+        return np.array_equal(tk, a) and np.array_equal(ti, b)
+
+
+_default_session = None
+
+
+def default_session():
+    global _default_session
+    if _default_session is None:
+        _default_session = Session(0)
+    return _default_session
+
+
+# ---------------------------------------------------------------------------------------------
+# E step / M step (CF.R:589-687)
+# ---------------------------------------------------------------------------------------------
+def e_step_VEM(db, m_k, kern_0, kern_i, hp, old_tau_i_k, session=None, want_cov=True):
+    """CF.R:589-629 -> list(mean, cov, tau_i_k)."""
+    _check_kernels(kern_0, kern_i)
+    s = session or default_session()
+    s.ensure_data(db)
+    names_k = list(m_k.keys())
+    theta_k, theta_i = s.pack_hp(hp, names_k)
+    s.eng.set_state(theta_k, theta_i, np.asarray(hp["pi_k"], dtype=np.float64), s.pack_mk(m_k, names_k),
+                    s.pack_tau(old_tau_i_k, names_k))
+    s.eng.e_step()
+    out = s.param_from_device(names_k, s.eng.get_tau_new(), want_cov)
+    out["mat_logL"] = s.eng.get_mat_logL().T  # K x M like CF.R:738
+    return out
+
+
+def m_step_VEM(db, old_hp, list_mu_param, kern_0, kern_i, m_k, common_hp_k, common_hp_i, session=None, stats=None):
+    """CF.R:631-687 -> list(theta_k, theta_i, pi_k); optimiser = the library's L-BFGS (csrc/lbfgs.h)."""
+    _check_kernels(kern_0, kern_i)
+    s = session or default_session()
+    c = s.ensure_data(db)
+    names_k = s.ensure_posterior(old_hp, m_k, list_mu_param)
+    tk, ti, pi, st = s.eng.m_step(common_hp_k, common_hp_i)
+    if stats is not None:
+        stats.update(st)
+    return {"theta_k": {k: tk[ck] for ck, k in enumerate(names_k)},
+            "theta_i": {i: ti[r] for r, i in enumerate(c.ids)}, "pi_k": pi}
+
+
+# ---------------------------------------------------------------------------------------------
+# optimiser callbacks (CF.R:194-325, 448-586) — each is one evaluation on the device
+# ---------------------------------------------------------------------------------------------
+def _indiv_rows(s, hp3, i):
+    c = s.canon
+    _, ti, _ = s.eng.get_hp()
+    ti = ti.copy()
+    ti[c.ids.index(i)] = hp3
+    return ti, c.ids.index(i)
+
+
+def _require_token(s, mu_k_param, what):
+    if mu_k_param.get("_token") is None or mu_k_param.get("_token") != s._post_token:
+        raise ValueError(f"{what}: pass the param object returned by the last e_step_VEM of this session, "
+                         "or call Session.ensure_posterior(hp, m_k, param) first")
+
+
+def logL_clust_multi_GP(hp, db, mu_k_param, kern, session=None):
+    """CF.R:218-248 for the single individual in `db` (3 hyper-parameters)."""
+    _check_kernels(kern)
+    s = session or default_session()
+    _require_token(s, mu_k_param, "logL_clust_multi_GP")
+    i = np.asarray(db["ID"])[0]
+    i = i.item() if isinstance(i, np.generic) else i
+    th, r = _indiv_rows(s, np.asarray(hp, dtype=np.float64)[:3], i)
+    f, _ = s.eng.eval_indiv(th, grad=False)
+    return float(f[r])
+
+
+def gr_clust_multi_GP(hp, db, mu_k_param, kern, session=None):
+    """CF.R:477-508."""
+    _check_kernels(kern)
+    s = session or default_session()
+    _require_token(s, mu_k_param, "gr_clust_multi_GP")
+    i = np.asarray(db["ID"])[0]
+    i = i.item() if isinstance(i, np.generic) else i
+    th, r = _indiv_rows(s, np.asarray(hp, dtype=np.float64)[:3], i)
+    _, g = s.eng.eval_indiv(th, grad=True)
+    return g[r]
+
+
+def logL_clust_multi_GP_common_hp_i(hp, db, mu_k_param, kern, session=None):
+    """CF.R:280-325."""
+    _check_kernels(kern)
+    s = session or default_session()
+    _require_token(s, mu_k_param, "logL_clust_multi_GP_common_hp_i")
+    return s.eng.eval_indiv_common(np.asarray(hp, dtype=np.float64)[:3], grad=False)[0]
+
+
+def gr_clust_multi_GP_common_hp_i(hp, db, mu_k_param, kern, session=None):
+    """CF.R:539-586."""
+    _check_kernels(kern)
+    s = session or default_session()
+    _require_token(s, mu_k_param, "gr_clust_multi_GP_common_hp_i")
+    return s.eng.eval_indiv_common(np.asarray(hp, dtype=np.float64)[:3], grad=True)[1]
+
+
+def logL_GP_mod(hp, k, pen_diag=None, session=None):
+    """CF.R:194-216 for mean process number `k` of the resident hyper-posterior (db = mean_k, mean = m_k,
+    new_cov = cov_k are the resident ones)."""
+    s = session or default_session()
+    return s.eng.eval_mean(k, np.asarray(hp, dtype=np.float64), 0.0 if pen_diag is None else pen_diag, grad=False)[0]
+
+
+def gr_GP_mod(hp, k, pen_diag=None, session=None):
+    """CF.R:448-475."""
+    s = session or default_session()
+    return s.eng.eval_mean(k, np.asarray(hp, dtype=np.float64), 0.0 if pen_diag is None else pen_diag, grad=True)[1]
+
+
+def logL_GP_mod_common_hp_k(hp, pen_diag=None, session=None):
+    """CF.R:250-278."""
+    s = session or default_session()
+    return s.eng.eval_mean_common(np.asarray(hp, dtype=np.float64), 0.0 if pen_diag is None else pen_diag, grad=False)[0]
+
+
+def gr_GP_mod_common_hp_k(hp, pen_diag=None, session=None):
+    """CF.R:510-537."""
+    s = session or default_session()
+    return s.eng.eval_mean_common(np.asarray(hp, dtype=np.float64), 0.0 if pen_diag is None else pen_diag, grad=True)[1]
+
+
+def logL_monitoring_VEM(hp, db, kern_i, kern_0, mu_k_param, m_k, session=None):
+    """CF.R:327-352 at `hp` against the resident hyper-posterior."""
+    _check_kernels(kern_i, kern_0)
+    s = session or default_session()
+    s.ensure_data(db)
+    _require_token(s, mu_k_param, "logL_monitoring_VEM")
+    names_k = list(m_k.keys())
+    theta_k, theta_i = s.pack_hp(hp, names_k)
+    return s.eng.elbo(theta_k, theta_i)[0]
+
+
+# ---------------------------------------------------------------------------------------------
+# drivers (MC.R)
+# ---------------------------------------------------------------------------------------------
+def training_VEM(db, prior_mean_k, ini_hp=None, kern_0=kernel_mu, kern_i=kernel, ini_tau_i_k=None,
+                 common_hp_k=True, common_hp_i=True, n_loop_max=15, session=None, verbose=False):
+    """MC.R:16-99. The whole loop runs against device-resident state (one `mcb_vem_iteration` per pass);
+    host copies happen once at the end. `ini_tau_i_k` is required (the reference's default is an unseeded
+    stats::kmeans, MC.R:37, which is outside this path)."""
+    _check_kernels(kern_0, kern_i)
+    if ini_tau_i_k is None:
+        raise ValueError("ini_tau_i_k is required")
+    if ini_hp is None:
+        ini_hp = {"theta_k": np.array([1.0, 1.0, 0.2]), "theta_i": np.array([1.0, 1.0, 0.2])}
+    s = session or default_session()
+    c = s.ensure_data(db)
+    names_k = list(prior_mean_k.keys())
+    K = len(names_k)
+    tau0 = s.pack_tau(ini_tau_i_k, names_k)
+    theta_k = np.tile(np.asarray(ini_hp["theta_k"], dtype=np.float64)[:3], (K, 1))
+    theta_i = np.tile(np.asarray(ini_hp["theta_i"], dtype=np.float64)[:3], (c.M, 1))
+    pi = tau0.mean(axis=0)  # MC.R:39
+    t1 = time.time()
+    s.eng.set_state(theta_k, theta_i, pi, s.pack_mk(prior_mean_k, names_k), tau0)
+    seq_logL = []
+    cv = False
+    for it in range(n_loop_max):
+        elbo, eps, conv = s.eng.vem_iteration(common_hp_k, common_hp_i)
+        seq_logL.append(elbo)
+        if verbose:
+            print(it + 1, elbo, "eps", eps)
+        if conv:
+            cv = True
+            break
+    # MC.R:95 returns hp = new_hp (the last M-step's candidate) with the param of the preceding E-step (Q7)
+    tk, ti, pik = s.eng.get_new_hp()
+    param = s.param_from_device(names_k, s.eng.get_tau_new())
+    t2 = time.time()
+    hp = {"theta_k": {k: tk[ck] for ck, k in enumerate(names_k)},
+          "theta_i": {i: ti[r] for r, i in enumerate(c.ids)}, "pi_k": pik}
+    return {"hp": hp, "convergence": cv, "param": param, "Time_train": t2 - t1,
+            "logL_iterations": np.array(seq_logL)}
+
+
+def posterior_mu_k(db, timestamps, m_k, kern_0, kern_i, list_hp, session=None):
+    """MC.R:196-233."""
+    _check_kernels(kern_0, kern_i)
+    s = session or default_session()
+    c = s.ensure_data(db)
+    names_k = list(list_hp["hp"]["theta_k"].keys())
+    theta_k, theta_i = s.pack_hp(list_hp["hp"], names_k)
+    tau = s.pack_tau(list_hp["param"]["tau_i_k"], names_k)
+    pi = np.asarray(list_hp["hp"].get("pi_k", tau.mean(axis=0)), dtype=np.float64)
+    tk, ti, _ = (s.eng.get_hp() if s.eng.K == len(names_k) else (None, None, None))
+    if tk is None or not (np.array_equal(tk, theta_k) and np.array_equal(ti, theta_i)):
+        s.eng.set_state(theta_k, theta_i, pi, s.pack_mk(m_k, names_k), tau)
+        s._post_token = None
+    ts = np.asarray(timestamps, dtype=np.float64)
+    mean, cov = s.eng.posterior_mu_k(ts, tau)
+    return {"mean": {k: {"Timestamp": ts, "Output": mean[ck]} for ck, k in enumerate(names_k)},
+            "cov": {k: NamedMat(cov[ck], ts) for ck, k in enumerate(names_k)},
+            "tau_i_k": list_hp["param"]["tau_i_k"], "_pred_session": id(s)}
+
+
+def _csr_new(new_dbs, ts):
+    offs, idx, ys = [0], [], []
+    for d in new_dbs:
+        t = np.asarray(d["Timestamp"], dtype=np.float64)
+        p = np.searchsorted(ts, t)
+        if np.any(p >= ts.shape[0]) or np.any(ts[np.minimum(p, ts.shape[0] - 1)] != t):
+            raise ValueError("every observation timestamp must belong to the prediction grid")
+        idx.append(p)
+        ys.append(np.asarray(d["Output"], dtype=np.float64))
+        offs.append(offs[-1] + t.shape[0])
+    return np.array(offs, np.int32), np.concatenate(idx).astype(np.int32), np.concatenate(ys)
+
+
+def update_tau_star_k_EM(db, mean_k, cov_k, kern, hp, pi_k, session=None):
+    """CF.R:764-786 against the resident prediction posterior (the one `posterior_mu_k` just produced)."""
+    _check_kernels(kern)
+    s = session or default_session()
+    names_k = list(mean_k.keys())
+    ts = np.asarray(mean_k[names_k[0]]["Timestamp"], dtype=np.float64)
+    off, idx, y = _csr_new([db], ts)
+    pi = np.array([pi_k[k] for k in names_k], dtype=np.float64) if isinstance(pi_k, dict) else np.asarray(pi_k)
+    tau, _, _ = s.eng.predict(off, idx, y, np.asarray(hp, dtype=np.float64)[:3], None, pi)
+    return {k: float(tau[0, ck]) for ck, k in enumerate(names_k)}
+
+
+def train_new_gp_EM(db, param_mu_k, ini_hp=None, kern_i=kernel, hp_i=None, session=None):
+    """MC.R:137-141,187-192 — fixed-hp branch (the free-hp branch is broken upstream)."""
+    if hp_i is None:
+        raise NotImplementedError("free-hp branch of train_new_gp_EM is broken in the reference (Q9)")
+    pi_k = {k: float(np.mean(list(v.values()))) for k, v in param_mu_k["tau_i_k"].items()}
+    new_hp = np.asarray(next(iter(hp_i["hp"]["theta_i"].values())), dtype=np.float64).ravel()[:3]
+    tau_k = update_tau_star_k_EM(db, param_mu_k["mean"], param_mu_k["cov"], kern_i, new_hp, pi_k, session)
+    return {"theta_new": new_hp, "tau_k": tau_k}
+
+
+def pred_gp_clust(db, timestamps, list_mu, kern, hp, session=None):
+    """MC.R:235-274 -> {k: {'Timestamp', 'Mean', 'Var', 'tau_k'}}."""
+    _check_kernels(kern)
+    s = session or default_session()
+    names_k = list(list_mu["mean"].keys())
+    ts = np.asarray(list_mu["mean"][names_k[0]]["Timestamp"], dtype=np.float64)
+    tn = np.asarray(db["Timestamp"], dtype=np.float64)
+    if timestamps is None:
+        raise ValueError("timestamps must be given (and belong to the grid of list_mu)")
+    tp = np.asarray(timestamps, dtype=np.float64)
+    pidx = np.searchsorted(ts, tp)
+    if np.any(pidx >= ts.shape[0]) or np.any(ts[np.minimum(pidx, ts.shape[0] - 1)] != tp):
+        raise ValueError("prediction timestamps must belong to the grid of list_mu (MC.R:323 guarantees it)")
+    off, idx, y = _csr_new([db], ts)
+    _, mean, var = s.eng.predict(off, idx, y, np.asarray(hp["theta_new"], dtype=np.float64)[:3], pidx.astype(np.int32),
+                                 np.full(len(names_k), 1.0 / len(names_k)))
+    return {k: {"Timestamp": tp, "Mean": mean[0, ck], "Var": var[0, ck], "tau_k": hp["tau_k"][k]}
+            for ck, k in enumerate(names_k)}
+
+
+def full_algo_clust(db, new_db, timestamps, kern_i, ini_tau_i_k=None, common_hp_k=True, common_hp_i=True,
+                    prior_mean=None, kern_0=None, list_hp=None, mu_k=None, ini_hp=None, hp_new_i=None, session=None):
+    """MC.R:301-347."""
+    s = session or default_session()
+    if list_hp is None:
+        list_hp = training_VEM(db, prior_mean, ini_hp, kern_0, kern_i, ini_tau_i_k, common_hp_k, common_hp_i,
+                               session=s)
+    t_pred = np.unique(np.r_[np.asarray(timestamps, dtype=np.float64), np.asarray(db["Timestamp"], dtype=np.float64),
+                             np.asarray(new_db["Timestamp"], dtype=np.float64)])
+    if mu_k is None:
+        mu_k = posterior_mu_k(db, t_pred, prior_mean, kern_0, kern_i, list_hp, session=s)
+    if hp_new_i is None:
+        hp_new_i = train_new_gp_EM(new_db, mu_k, ini_hp, kern_i, hp_i=list_hp if common_hp_i else None, session=s)
+    pred = pred_gp_clust(new_db, timestamps, mu_k, kern_i, hp_new_i, session=s)
+    return {"Prediction": pred, "Mean_processes": mu_k,
+            "Hyperparameters": {"other_i": list_hp, "new_i": hp_new_i},
+            "logL_iterations": list_hp.get("logL_iterations")}
+
+
+def pred_max_cluster(tau_i_k):
+    """MC.R:349-355: which.max per individual (first maximum wins), 1-based."""
+    names_k = list(tau_i_k.keys())
+    ids = list(tau_i_k[names_k[0]].keys())
+    mat = np.array([[tau_i_k[k][i] for k in names_k] for i in ids])
+    return np.argmax(mat, axis=1) + 1

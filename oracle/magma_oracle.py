@@ -459,6 +459,7 @@ def m_step_VEM(db, old_hp, list_mu_param, kern_0, kern_i, m_k, common_hp_k, comm
     per_id = split_db(db)
     list_ID_i = list(per_id.keys())
     nfev = 0
+    t1 = time.perf_counter()
     if common_hp_i:
         par, res = _lbfgsb(logL_clust_multi_GP_common_hp_i, gr_clust_multi_GP_common_hp_i,
                            old_hp["theta_i"][list_ID_i[0]], (db, list_mu_param, kern_i))
@@ -471,6 +472,7 @@ def m_step_VEM(db, old_hp, list_mu_param, kern_0, kern_i, m_k, common_hp_k, comm
                                (per_id[i], list_mu_param, kern_i))
             nfev += res.nfev
             new_theta_i[i] = par
+    t2 = time.perf_counter()
     pen_diag = float(np.mean([new_theta_i[i][2] for i in list_ID_i]))
     nfev_k = 0
     if common_hp_k:
@@ -492,6 +494,8 @@ def m_step_VEM(db, old_hp, list_mu_param, kern_0, kern_i, m_k, common_hp_k, comm
     if stats is not None:
         stats["nfev_i"] = stats.get("nfev_i", 0) + nfev
         stats["nfev_k"] = stats.get("nfev_k", 0) + nfev_k
+        stats["t_i"] = stats.get("t_i", 0.0) + (t2 - t1)                      # 'indiv:' of CF.R:685
+        stats["t_k"] = stats.get("t_k", 0.0) + (time.perf_counter() - t2)     # 'mu_k:'  of CF.R:685
     return {"theta_k": new_theta_k, "theta_i": new_theta_i, "pi_k": pi_k}
 
 

@@ -1,0 +1,54 @@
+"""GPU parity of the E-step (e_step_VEM, CF.R:589-629) against the CPU oracle, through the C ABI."""
+import numpy as np
+import pytest
+
+from oracle import magma_oracle as O
+from helpers import NAMES3, RTOL_LL, assert_param_close, gold_dataset, load_gold, rel_err, small_problem
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("d", [0, 1, 2, 29, 57])
+def test_estep_golden_fixture(session, d):
+    """stored reference outputs (hp, tau) of fixture dataset d as inputs: GPU E-step == oracle E-step"""
+    from magmaclust_b200 import magma
+    db, hp, tau, m_k = gold_dataset(load_gold(), d)
+    ref = O.e_step_VEM(db, m_k, O.kernel_mu, O.kernel, hp, tau, return_logL=True)
+    got = magma.e_step_VEM(db, m_k, magma.kernel_mu, magma.kernel, hp, tau, session=session)
+    assert_param_close(got, ref, NAMES3)
+    assert rel_err(got["mat_logL"], ref["mat_logL"]) < RTOL_LL
+    # the reference's stored tau is a near fixed point of the E-step: identical hard assignments
+    stored = O.tau_to_array(tau)
+    assert np.array_equal(O.tau_to_array(got["tau_i_k"]).argmax(1), stored.argmax(1))
+
+
+@pytest.mark.parametrize("seed,common", [(0, False), (1, True), (2, False)])
+def test_estep_small_ragged(session, seed, common):
+    from magmaclust_b200 import magma
+    db, hp, tau, m_k = small_problem(seed=seed, common_hp_i=common)
+    ref = O.e_step_VEM(db, m_k, O.kernel_mu, O.kernel, hp, tau, return_logL=True)
+    got = magma.e_step_VEM(db, m_k, magma.kernel_mu, magma.kernel, hp, tau, session=session)
+    assert_param_close(got, ref, list(m_k.keys()))
+    assert rel_err(got["mat_logL"], ref["mat_logL"]) < RTOL_LL
+
+
+def test_estep_single_observation_individual(session):
+    """n_i = 1 takes the scalar branch of kern_to_inv (CF.R:167-170)"""
+    from magmaclust_b200 import magma
+    db, hp, tau, m_k = small_problem(M=8, n=(1, 5), seed=5)
+    ref = O.e_step_VEM(db, m_k, O.kernel_mu, O.kernel, hp, tau)
+    got = magma.e_step_VEM(db, m_k, magma.kernel_mu, magma.kernel, hp, tau, session=session)
+    assert_param_close(got, ref, list(m_k.keys()))
+
+
+def test_estep_one_hot_tau_and_vector_prior(session):
+    from magmaclust_b200 import magma
+    db, hp, tau, m_k = small_problem(M=10, seed=7)
+    ids = list(O.split_db(db).keys())
+    names = list(m_k.keys())
+    tau = {k: {i: 1.0 if (r % len(names)) == c else 0.0 for r, i in enumerate(ids)} for c, k in enumerate(names)}
+    N = np.unique(db["Timestamp"]).shape[0]
+    m_k = {k: np.linspace(0, 1, N) * (c + 1) for c, k in enumerate(names)}
+    ref = O.e_step_VEM(db, m_k, O.kernel_mu, O.kernel, hp, tau)
+    got = magma.e_step_VEM(db, m_k, magma.kernel_mu, magma.kernel, hp, tau, session=session)
+    assert_param_close(got, ref, names)

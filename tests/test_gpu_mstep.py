@@ -1,0 +1,121 @@
+"""GPU parity of the M-step callbacks (CF.R:194-325, 448-586), the ELBO monitor (CF.R:327-352, MC.R:51-53)
+and the built-in optimiser (m_step_VEM, CF.R:631-687) against the CPU oracle."""
+import numpy as np
+import pytest
+
+from oracle import magma_oracle as O
+from helpers import NAMES3, RTOL_LL, gold_dataset, load_gold, rel_err, small_problem
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(session, db, hp, tau, m_k):
+    from magmaclust_b200 import magma
+    ref = O.e_step_VEM(db, m_k, O.kernel_mu, O.kernel, hp, tau)
+    got = magma.e_step_VEM(db, m_k, magma.kernel_mu, magma.kernel, hp, tau, session=session)
+    return ref, got
+
+
+@pytest.mark.parametrize("case", ["gold0", "small0", "small3"])
+def test_indiv_objective_and_gradient(session, case):
+    from magmaclust_b200 import magma
+    if case.startswith("gold"):
+        db, hp, tau, m_k = gold_dataset(load_gold(), 0)
+    else:
+        db, hp, tau, m_k = small_problem(seed=int(case[-1]))
+    ref, got = _setup(session, db, hp, tau, m_k)
+    per_id = O.split_db(db)
+    rng = np.random.default_rng(3)
+    th = np.array([np.asarray(hp["theta_i"][i]) + 0.2 * rng.standard_normal(3) for i in per_id])
+    f, g = session.eng.eval_indiv(th)
+    for r, (i, d) in enumerate(per_id.items()):
+        fr = O.logL_clust_multi_GP(th[r], d, ref, O.kernel)
+        gr = O.gr_clust_multi_GP(th[r], d, ref, O.kernel)
+        assert abs(f[r] - fr) <= RTOL_LL * max(1.0, abs(fr))
+        assert np.max(np.abs(g[r] - gr)) <= RTOL_LL * max(1.0, np.max(np.abs(gr)))
+    # shared theta: CF.R:280-325 / 539-586
+    th0 = np.array([0.9, 0.6, 0.4])
+    fc, gc = session.eng.eval_indiv_common(th0)
+    frc = O.logL_clust_multi_GP_common_hp_i(th0, db, ref, O.kernel)
+    grc = O.gr_clust_multi_GP_common_hp_i(th0, db, ref, O.kernel)
+    assert abs(fc - frc) <= RTOL_LL * abs(frc)
+    assert np.max(np.abs(gc - grc)) <= RTOL_LL * max(1.0, np.max(np.abs(grc)))
+    # R-shaped single-individual callbacks
+    i0 = next(iter(per_id))
+    assert abs(magma.logL_clust_multi_GP(th[0], per_id[i0], got, magma.kernel, session=session) -
+               O.logL_clust_multi_GP(th[0], per_id[i0], ref, O.kernel)) <= RTOL_LL * abs(f[0])
+
+
+@pytest.mark.parametrize("case", ["gold1", "small1"])
+def test_mean_objective_and_gradient(session, case):
+    if case.startswith("gold"):
+        db, hp, tau, m_k = gold_dataset(load_gold(), 1)
+    else:
+        db, hp, tau, m_k = small_problem(seed=1)
+    ref, got = _setup(session, db, hp, tau, m_k)
+    names = list(m_k.keys())
+    th3 = np.array([1.4, 0.9, 0.35])
+    for ck, k in enumerate(names):
+        for nhp in (2, 3):
+            f, g = session.eng.eval_mean(ck, th3[:nhp], pen_diag=0.27)
+            fr = O.logL_GP_mod(th3[:nhp], ref["mean"][k], m_k[k], O.kernel_mu, ref["cov"][k], 0.27)
+            gr = O.gr_GP_mod(th3[:nhp], ref["mean"][k], m_k[k], O.kernel_mu, ref["cov"][k], 0.27)
+            assert abs(f - fr) <= RTOL_LL * max(1.0, abs(fr))
+            assert np.max(np.abs(g - gr)) <= RTOL_LL * max(1.0, np.max(np.abs(gr)))
+    for nhp in (2, 3):
+        f, g = session.eng.eval_mean_common(th3[:nhp], pen_diag=0.27)
+        fr = O.logL_GP_mod_common_hp_k(th3[:nhp], ref["mean"], m_k, O.kernel_mu, ref["cov"], 0.27)
+        gr = O.gr_GP_mod_common_hp_k(th3[:nhp], ref["mean"], m_k, O.kernel_mu, ref["cov"], 0.27)
+        assert abs(f - fr) <= RTOL_LL * max(1.0, abs(fr))
+        assert np.max(np.abs(g - gr)) <= RTOL_LL * max(1.0, np.max(np.abs(gr)))
+
+
+@pytest.mark.parametrize("case", ["gold0", "small2"])
+def test_elbo(session, case):
+    from magmaclust_b200 import magma
+    if case.startswith("gold"):
+        db, hp, tau, m_k = gold_dataset(load_gold(), 0)
+    else:
+        db, hp, tau, m_k = small_problem(seed=2)
+    ref, got = _setup(session, db, hp, tau, m_k)
+    l0, l1 = session.eng.elbo()
+    r0 = O.logL_monitoring_VEM(hp, db, O.kernel, O.kernel_mu, ref, m_k)
+    r1 = O.elbo_VEM(hp, db, O.kernel, O.kernel_mu, ref, m_k)
+    assert abs(l0 - r0) <= RTOL_LL * abs(r0)
+    assert abs(l1 - r1) <= RTOL_LL * abs(r1)
+    # at another hp, through the R-shaped call
+    hp2 = {"theta_k": {k: np.asarray(v) + 0.1 for k, v in hp["theta_k"].items()},
+           "theta_i": {i: np.asarray(v) - 0.05 for i, v in hp["theta_i"].items()}, "pi_k": hp["pi_k"]}
+    l2 = magma.logL_monitoring_VEM(hp2, db, magma.kernel, magma.kernel_mu, got, m_k, session=session)
+    r2 = O.logL_monitoring_VEM(hp2, db, O.kernel, O.kernel_mu, ref, m_k)
+    assert abs(l2 - r2) <= RTOL_LL * abs(r2)
+
+
+@pytest.mark.parametrize("common_k,common_i", [(True, True), (True, False), (False, False), (False, True)])
+def test_m_step_matches_oracle_optimum(session, common_k, common_i):
+    """Optimiser trajectories are not pinned by the reference (third-party L-BFGS-B); the contract is that
+    both optimisers reach the same optimum of the same objective: objective values agree and the GPU
+    optimum is not worse."""
+    from magmaclust_b200 import magma
+    db, hp, tau, m_k = small_problem(M=10, seed=4, common_hp_i=common_i)
+    if common_k:
+        first = next(iter(hp["theta_k"].values()))
+        hp["theta_k"] = {k: first.copy() for k in hp["theta_k"]}
+    ref, got = _setup(session, db, hp, tau, m_k)
+    new_ref = O.m_step_VEM(db, hp, ref, O.kernel_mu, O.kernel, m_k, common_k, common_i)
+    new_got = magma.m_step_VEM(db, hp, got, magma.kernel_mu, magma.kernel, m_k, common_k, common_i, session=session)
+    assert np.allclose(new_got["pi_k"], new_ref["pi_k"], rtol=0, atol=1e-12)
+    # individuals' part of the objective at the returned theta_i (CF.R:218-248 summed): GPU optimum not worse
+    per_id = O.split_db(db)
+    fi_ref = sum(O.logL_clust_multi_GP(new_ref["theta_i"][i], d, ref, O.kernel) for i, d in per_id.items())
+    fi_got = sum(O.logL_clust_multi_GP(new_got["theta_i"][i], d, ref, O.kernel) for i, d in per_id.items())
+    fi_old = sum(O.logL_clust_multi_GP(hp["theta_i"][i], d, ref, O.kernel) for i, d in per_id.items())
+    assert fi_got < fi_old
+    assert fi_got <= fi_ref + 1e-6 * abs(fi_ref)
+    for i in new_ref["theta_i"]:
+        assert np.allclose(new_got["theta_i"][i], new_ref["theta_i"][i], atol=5e-3), i
+    # mean processes: (a, b) optimised, third entry = pen_diag = mean_i theta_i[3] (signed)
+    for k in new_ref["theta_k"]:
+        assert np.allclose(new_got["theta_k"][k], new_ref["theta_k"][k], atol=5e-3), k
+    pen = np.mean([new_got["theta_i"][i][2] for i in new_got["theta_i"]])
+    assert abs(new_got["theta_k"][next(iter(m_k))][2] - pen) < 1e-12
