@@ -153,10 +153,10 @@ extern "C" int mcb_set_data(mcb_handle* h, int M, int N, long long P, const int*
     }
   }
   H_CHECK(eval_smem_bytes(nmax) <= 227 * 1024, MCB_EINVAL,
-          "mcb_set_data: an individual has too many observations for the shared-memory path (n_i <= ~115)");
+          "mcb_set_data: an individual has too many observations for the shared-memory path (n_i <= 80)");
   H_CUDA(cudaSetDevice(h->device));
   h->K = 0;  // forces the state buffers to be re-sized for the new N
-  h->M = M; h->N = N; h->ld = (N + 3) & ~3; h->P = P; h->nmax = nmax; h->M_total = M_total; h->W2 = woff[M];
+  h->M = M; h->N = N; h->ld = (N + 15) & ~15; h->P = P; h->nmax = nmax; h->M_total = M_total; h->W2 = woff[M];
   H_CUDA(h->off.ensure(M + 1)); H_CUDA(h->gidx.ensure(P)); H_CUDA(h->woff.ensure(M + 1));
   H_CUDA(h->t.ensure(P)); H_CUDA(h->y.ensure(P)); H_CUDA(h->grid.ensure(N));
   H_CUDA(cudaMemcpyAsync(h->off.p, offsets, sizeof(int) * (M + 1), cudaMemcpyHostToDevice, h->st));
@@ -192,6 +192,11 @@ static int alloc_state(mcb_handle* h, int K) {
   H_CUDA(h->eCsum.ensure(KNN)); H_CUDA(h->eX.ensure(KNN));
   H_CUDA(h->etheta.ensure(3 * K)); H_CUDA(h->ered.ensure(16 * (size_t)K)); H_CUDA(h->elogdet.ensure(K));
   H_CUDA(h->egmap.ensure(K));
+  H_CUDA(spd_inverse_reserve(h->ws, h->N, K));
+  // the dense kernels rely on zero padding of every row up to ld: clear whatever an earlier shape left behind
+  mcb::DevBuf<double>* dense[] = {&h->Kinv, &h->cov, &h->eK, &h->eD1, &h->eD2, &h->eCsum, &h->eX,
+                                  &h->mk, &h->wk, &h->mean, &h->rvec, &h->pz};
+  for (auto* b : dense) H_CUDA(cudaMemsetAsync(b->p, 0, sizeof(double) * b->cap, h->st));
   return MCB_OK;
 }
 

@@ -46,8 +46,10 @@ struct DevBuf {
     p = nullptr;
     cap = 0;
     cudaError_t e = cudaMalloc(&p, n * sizeof(T));
-    if (e == cudaSuccess) cap = n;
-    return e;
+    if (e != cudaSuccess) return e;
+    cap = n;
+    // zero fill: dense buffers rely on zero padding of every row up to ld (ld % 16 == 0)
+    return cudaMemset(p, 0, n * sizeof(T));
   }
   void release() {
     if (p) cudaFree(p);
@@ -75,6 +77,7 @@ void se_build(cudaStream_t s, double* Kmat, double* D1, double* D2, int N, int l
 // In-place inverse of Z symmetric positive definite matrices by a blocked symmetric sweep (block
 // Gauss-Jordan). logdet[z] (device) receives log det of the ORIGINAL matrix; *info (device int) is set
 // non-zero if a non-positive pivot is met. Both triangles are read and written.
+cudaError_t spd_inverse_reserve(DenseWs& ws, int N, int Z);  // pre-size the workspace (no allocation later)
 cudaError_t spd_inverse(cudaStream_t s, double* A, int N, int ld, long long stride, int Z, double* logdet,
                         int* info, DenseWs& ws, long long* launches);
 

@@ -66,6 +66,14 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
                : "d"(a), "d"(b));
 }
 
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
+
 enum { EPI_STORE = 0, EPI_SWEEP = 1, EPI_TRACE = 2 };
 
 struct GemmParams {
@@ -83,80 +91,112 @@ struct GemmParams {
 constexpr int kBK = 16;
 constexpr int kPad = 4;  // row stride kBK+kPad doubles: (4r + c) mod 16 distinct over a DMMA fragment
 
-// CTA tile (2*WT) x (2*WT), 4 warps as 2 x 2, each warp WT x WT (WT = 32 or 16) in m8n8k4 tiles.
-template <int WT, int MODE>
+// C tile BM x BN per CTA, 4 warps as 2 x 2, each warp (BM/2) x (BN/2) in m8n8k4 tiles; the K loop streams
+// 16-wide slabs of A and B rows through a 2-stage cp.async pipeline.
+// Contract: rows of A and B are zero-padded up to a multiple of 16 columns (every dense buffer of this
+// library has ld % 16 == 0 and zero pads), so the K loop needs no column guards; row indices past M / N are
+// clamped (their results are discarded by the epilogue).
+template <int BM, int BN, int MODE>
 __global__ void __launch_bounds__(128) gemm_nt_kernel(GemmParams p) {
-  constexpr int BT = 2 * WT;
-  constexpr int F = WT / 8;  // fragments per warp per dimension
-  __shared__ double As[BT][kBK + kPad];
-  __shared__ double Bs[BT][kBK + kPad];
+  constexpr int FM = BM / 16, FN = BN / 16;  // fragments per warp per dimension
+  __shared__ __align__(16) double As[2][BM][kBK + kPad];
+  __shared__ __align__(16) double Bs[2][BN][kBK + kPad];
   const int z = blockIdx.z;
-  const int m0 = blockIdx.y * BT, n0 = blockIdx.x * BT;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int wm = (warp >> 1) * WT, wn = (warp & 1) * WT;
+  const int wm = (warp >> 1) * (BM / 2), wn = (warp & 1) * (BN / 2);
   const double* A = p.A + z * p.sA;
   const double* B = p.B + z * p.sB;
 
-  double acc[F][F][2];
+  double acc[FM][FN][2];
 #pragma unroll
-  for (int i = 0; i < F; ++i)
+  for (int i = 0; i < FM; ++i)
 #pragma unroll
-    for (int j = 0; j < F; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    for (int j = 0; j < FN; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-  for (int k0 = 0; k0 < p.K; k0 += kBK) {
+  auto load_tile = [&](int st, int k0) {
 #pragma unroll
-    for (int e = tid; e < BT * kBK; e += 128) {
-      const int r = e / kBK, c = e % kBK;
-      const int gk = k0 + c;
-      const int ga = m0 + r, gb = n0 + r;
-      As[r][c] = (ga < p.M && gk < p.K) ? A[(size_t)ga * p.lda + gk] : 0.0;
-      Bs[r][c] = (gb < p.N && gk < p.K) ? B[(size_t)gb * p.ldb + gk] : 0.0;
+    for (int c = tid; c < BM * (kBK / 2); c += 128) {
+      const int r = c / (kBK / 2), c2 = (c % (kBK / 2)) * 2;
+      const int gr = min(m0 + r, p.M - 1);
+      cp_async16(&As[st][r][c2], A + (size_t)gr * p.lda + k0 + c2);
+    }
+#pragma unroll
+    for (int c = tid; c < BN * (kBK / 2); c += 128) {
+      const int r = c / (kBK / 2), c2 = (c % (kBK / 2)) * 2;
+      const int gr = min(n0 + r, p.N - 1);
+      cp_async16(&Bs[st][r][c2], B + (size_t)gr * p.ldb + k0 + c2);
+    }
+    cp_async_commit();
+  };
+
+  const int nk = (p.K + kBK - 1) / kBK;
+  load_tile(0, 0);
+  for (int kt = 0; kt < nk; ++kt) {
+    const int st = kt & 1;
+    if (kt + 1 < nk) {
+      load_tile(st ^ 1, (kt + 1) * kBK);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
     }
     __syncthreads();
 #pragma unroll
     for (int kk = 0; kk < kBK; kk += 4) {
-      double af[F], bf[F];
+      double af[FM], bf[FN];
 #pragma unroll
-      for (int i = 0; i < F; ++i) af[i] = As[wm + 8 * i + (lane >> 2)][kk + (lane & 3)];
+      for (int i = 0; i < FM; ++i) af[i] = As[st][wm + 8 * i + (lane >> 2)][kk + (lane & 3)];
 #pragma unroll
-      for (int j = 0; j < F; ++j) bf[j] = Bs[wn + 8 * j + (lane >> 2)][kk + (lane & 3)];
+      for (int j = 0; j < FN; ++j) bf[j] = Bs[st][wn + 8 * j + (lane >> 2)][kk + (lane & 3)];
 #pragma unroll
-      for (int i = 0; i < F; ++i)
+      for (int i = 0; i < FM; ++i)
 #pragma unroll
-        for (int j = 0; j < F; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+        for (int j = 0; j < FN; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
     }
     __syncthreads();
   }
 
   double t1 = 0, t2 = 0, t0 = 0;
 #pragma unroll
-  for (int i = 0; i < F; ++i) {
+  for (int i = 0; i < FM; ++i) {
+    const int gi = m0 + wm + 8 * i + (lane >> 2);
 #pragma unroll
-    for (int j = 0; j < F; ++j) {
-#pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        const int gi = m0 + wm + 8 * i + (lane >> 2);
-        const int gj = n0 + wn + 8 * j + (lane & 3) * 2 + q;
-        if (gi >= p.M || gj >= p.N) continue;
-        const double v = acc[i][j][q];
-        if (MODE == EPI_STORE) {
-          double* c = p.C + z * p.sC + (size_t)gi * p.ldc + gj;
-          *c = (p.beta == 0.0) ? p.alpha * v : p.alpha * v + p.beta * *c;
-        } else if (MODE == EPI_SWEEP) {
-          double* c = p.C + z * p.sC + (size_t)gi * p.ldc + gj;
-          const bool ip = gi >= p.c0 && gi < p.c0 + p.nb;
-          const bool jp = gj >= p.c0 && gj < p.c0 + p.nb;
-          double r;
-          if (!ip && !jp) r = *c - v;
-          else if (jp) r = p.Pbuf[z * p.sP + (size_t)gi * kNB + (gj - p.c0)];
-          else r = p.Pbuf[z * p.sP + (size_t)gj * kNB + (gi - p.c0)];
-          *c = p.sign * r;
+    for (int j = 0; j < FN; ++j) {
+      const int gj = n0 + wn + 8 * j + (lane & 3) * 2;
+      if (gi >= p.M || gj >= p.N) continue;
+      const bool two = (gj + 1 < p.N);
+      if (MODE == EPI_STORE) {
+        double* c = p.C + z * p.sC + (size_t)gi * p.ldc + gj;
+        if (p.beta == 0.0) {
+          c[0] = p.alpha * acc[i][j][0];
+          if (two) c[1] = p.alpha * acc[i][j][1];
         } else {
-          const size_t o = z * p.sD + (size_t)gi * p.ldd + gj;
-          double d1 = p.D1[o];
-          if (gi == gj) { t0 += v; }
-          t1 += v * d1;
-          t2 += v * p.D2[o];
+          c[0] = p.alpha * acc[i][j][0] + p.beta * c[0];
+          if (two) c[1] = p.alpha * acc[i][j][1] + p.beta * c[1];
+        }
+      } else if (MODE == EPI_SWEEP) {
+        double* c = p.C + z * p.sC + (size_t)gi * p.ldc + gj;
+        const bool ip = gi >= p.c0 && gi < p.c0 + p.nb;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          if (q == 1 && !two) break;
+          const int gq = gj + q;
+          const bool jp = gq >= p.c0 && gq < p.c0 + p.nb;
+          double r;
+          if (!ip && !jp) r = c[q] - acc[i][j][q];
+          else if (jp) r = p.Pbuf[z * p.sP + (size_t)gi * kNB + (gq - p.c0)];
+          else r = p.Pbuf[z * p.sP + (size_t)gq * kNB + (gi - p.c0)];
+          c[q] = p.sign * r;
+        }
+      } else {
+        const size_t o = z * p.sD + (size_t)gi * p.ldd + gj;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          if (q == 1 && !two) break;
+          const double v = acc[i][j][q];
+          if (gi == gj + q) t0 += v;
+          t1 += v * p.D1[o + q];
+          t2 += v * p.D2[o + q];
         }
       }
     }
@@ -180,14 +220,14 @@ __global__ void __launch_bounds__(128) gemm_nt_kernel(GemmParams p) {
 
 template <int MODE>
 static void launch_gemm(cudaStream_t s, const GemmParams& p, int Z, long long* launches) {
-  // small problems: 32x32 CTA tiles so that more SMs take part
-  long long ctas64 = (long long)((p.M + 63) / 64) * ((p.N + 63) / 64) * Z;
+  // small problems: 32 x 64 CTA tiles so that more SMs take part
+  const long long ctas64 = (long long)((p.M + 63) / 64) * ((p.N + 63) / 64) * Z;
   if (ctas64 >= 2 * 148) {
     dim3 grd((p.N + 63) / 64, (p.M + 63) / 64, Z);
-    gemm_nt_kernel<32, MODE><<<grd, 128, 0, s>>>(p);
+    gemm_nt_kernel<64, 64, MODE><<<grd, 128, 0, s>>>(p);
   } else {
-    dim3 grd((p.N + 31) / 32, (p.M + 31) / 32, Z);
-    gemm_nt_kernel<16, MODE><<<grd, 128, 0, s>>>(p);
+    dim3 grd((p.N + 63) / 64, (p.M + 31) / 32, Z);
+    gemm_nt_kernel<32, 64, MODE><<<grd, 128, 0, s>>>(p);
   }
   if (launches) ++*launches;
 }
@@ -218,90 +258,110 @@ void gemm_nt_trace(cudaStream_t s, int N, const double* A, int lda, long long sA
 // -------------------------------------------------------------------------------------------------
 // blocked symmetric sweep
 // -------------------------------------------------------------------------------------------------
-// Panel step for pivot block b (nb <= 32 columns starting at c0). One CTA per 128 rows, thread = row.
-//   D = L L'            Cholesky of the pivot block (warp 0; pivots feed log det and the PD check)
-//   V[i] = A[i,b] L^-T  forward substitution per row   -> trailing update uses V V' (= A[:,b] D^-1 A[b,:])
-//   P[i] = V[i] L^-1    back substitution per row      -> new block column A[:,b] = A[:,b] D^-1
+// Panel step for pivot block b (nb <= 32 columns starting at c0); one CTA per 32 rows, 256 threads.
+//   D = L L'            every CTA eliminates the 32 x 32 pivot block redundantly (32 steps, one barrier each):
+//                       D = Lu Delta Lu' with unit-lower Lu, carrying W = Lu^-1 along, so L^-1 = Delta^-1/2 W
+//   V[i] = A[i,b] L^-T  -> trailing update uses V V' (= A[:,b] D^-1 A[b,:])
+//   P[i] = V[i] L^-1    -> new block column A[:,b] = A[:,b] D^-1
 // Rows of the pivot block itself carry the identity instead of A[b,b], so their P is D^-1 (stored negated).
-// The triangular solves keep the update as stable as a blocked Cholesky: multiplying by an explicitly
-// inverted D loses cond(D) digits, which is fatal for smooth SE kernels with small jitter.
-constexpr int kPanelRows = 128;
+// Working with L^-1 (condition sqrt(cond D)) and the V V' form keeps the un-swept part evolving exactly like a
+// right-looking blocked Cholesky; multiplying by an explicitly inverted D instead loses cond(D) digits, which is
+// fatal for smooth SE kernels with a small jitter.
+constexpr int kPanelRows = 32;
 
-__global__ void __launch_bounds__(kPanelRows) sweep_panel_kernel(const double* __restrict__ Aall, int N, int ld,
-                                                                 long long stride, int c0, int nb,
-                                                                 double* __restrict__ Vbuf,
-                                                                 double* __restrict__ Pbuf, long long sP,
-                                                                 double* __restrict__ logdet,
-                                                                 int* __restrict__ info) {
-  __shared__ double L[kNB][kNB + 1];
-  __shared__ double Rw[kPanelRows][kNB + 1];
+__global__ void __launch_bounds__(256) sweep_panel_kernel(const double* __restrict__ Aall, int N, int ld,
+                                                          long long stride, int c0, int nb,
+                                                          double* __restrict__ Vbuf, double* __restrict__ Pbuf,
+                                                          long long sP, double* __restrict__ logdet,
+                                                          int* __restrict__ info) {
+  __shared__ double D[kNB][kNB + 1];
+  __shared__ double W[kNB][kNB + 1];
+  __shared__ double R[kPanelRows][kNB + 1];
+  __shared__ double V[kPanelRows][kNB + 1];
+  __shared__ double piv[kNB];
   const int z = blockIdx.z;
   const int r0 = blockIdx.x * kPanelRows;
-  const int tid = threadIdx.x, lane = tid & 31;
+  const int tid = threadIdx.x;
+  const int ti = tid >> 3, tc = (tid & 7) * 4;  // this thread's row and first of its 4 columns
   const double* A = Aall + z * stride;
-  for (int e = tid; e < kNB * kNB; e += kPanelRows) {
-    const int a = e >> 5, b = e & 31;
-    L[a][b] = (a < nb && b < nb) ? A[(size_t)(c0 + a) * ld + c0 + b] : 0.0;
-  }
-  // own rows of the block column, coalesced over the 32 columns
-  for (int e = tid; e < kPanelRows * kNB; e += kPanelRows) {
-    const int a = e >> 5, b = e & 31;
-    const int gr = r0 + a;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int c = tc + q;
+    // identity padding keeps a partial last block a no-op for the extra pivots
+    D[ti][c] = (ti < nb && c < nb) ? A[(size_t)(c0 + ti) * ld + c0 + c] : (ti == c ? 1.0 : 0.0);
+    W[ti][c] = (ti == c) ? 1.0 : 0.0;
+    const int gr = r0 + ti;
     double v = 0.0;
-    if (gr < N && b < nb) {
-      if (gr >= c0 && gr < c0 + nb) v = (gr - c0 == b) ? 1.0 : 0.0;
-      else v = A[(size_t)gr * ld + c0 + b];
+    if (gr < N && c < nb) {
+      if (gr >= c0 && gr < c0 + nb) v = (gr - c0 == c) ? 1.0 : 0.0;
+      else v = A[(size_t)gr * ld + c0 + c];
     }
-    Rw[a][b] = v;
+    R[ti][c] = v;
   }
   __syncthreads();
+  for (int k = 0; k < kNB; ++k) {
+    const double d = D[k][k];
+    if (tid == 0) piv[k] = d;
+    if (ti > k) {
+      const double m = D[ti][k] / d;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int c = tc + q;
+        if (c <= k) W[ti][c] -= m * W[k][c];
+        else if (c <= ti) D[ti][c] -= m * D[c][k];
+      }
+    }
+    __syncthreads();
+  }
   if (tid < 32) {
-    // right-looking Cholesky, lane = row; lower triangle of L
-    double ldsum = 0.0;
-    bool bad = false;
-    for (int k = 0; k < nb; ++k) {
-      const double dkk = L[k][k];
-      if (!(dkk > 0.0)) bad = true;
-      const double sk = sqrt(dkk), inv = 1.0 / sk;
-      ldsum += log(dkk);
-      __syncwarp();
-      double l = 0.0;
-      if (lane > k && lane < nb) { l = L[lane][k] * inv; L[lane][k] = l; }
-      if (lane == k) L[k][k] = sk;
-      __syncwarp();
-      if (lane > k && lane < nb)
-        for (int j = k + 1; j <= lane; ++j) L[lane][j] -= l * L[j][k];
-      __syncwarp();
-    }
-    if (lane == 0) {
-      if (bad) *info = 1;
-      if (r0 <= c0 && c0 < r0 + kPanelRows) logdet[z] += ldsum;  // exactly one CTA owns the pivot rows
+    const double d = piv[tid];
+    double lg = log(d);
+    const bool bad = !(d > 0.0);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) lg += __shfl_xor_sync(0xffffffffu, lg, o);
+    if (__any_sync(0xffffffffu, bad) && tid == 0) *info = 1;
+    if (tid == 0 && r0 == c0) logdet[z] += lg;  // exactly one CTA owns the pivot rows
+  }
+  {
+    // L^-1 = Delta^-1/2 W (lower triangular), kept in D's storage
+    const double s = rsqrt(piv[ti]);
+    const double sfix = s * (1.5 - 0.5 * piv[ti] * s * s);  // one Newton step: full double accuracy
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int c = tc + q;
+      D[ti][c] = (c <= ti) ? W[ti][c] * sfix : 0.0;
     }
   }
   __syncthreads();
-  const int gr = r0 + tid;
-  double* row = Rw[tid];
-  // forward: v L' = r  ->  v_k = (r_k - sum_{j<k} v_j L[k][j]) / L[k][k]
-  for (int k = 0; k < nb; ++k) {
-    double acc = row[k];
-    for (int j = 0; j < k; ++j) acc -= row[j] * L[k][j];
-    row[k] = acc / L[k][k];
+  const int gr = r0 + ti;
+  // V = R L^-T : V[r][c] = sum_{b<=c} R[r][b] Linv[c][b]
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int c = tc + q;
+    double acc = 0.0;
+    for (int b = 0; b <= c; ++b) acc += R[ti][b] * D[c][b];
+    V[ti][c] = acc;
+    if (gr < N) Vbuf[z * sP + (size_t)gr * kNB + c] = acc;
   }
-  if (gr < N) {
-    double* vo = Vbuf + z * sP + (size_t)gr * kNB;
-    for (int k = 0; k < kNB; ++k) vo[k] = (k < nb) ? row[k] : 0.0;
+  __syncthreads();
+  // P = V L^-1 : P[r][c] = sum_{b>=c} V[r][b] Linv[b][c]
+  const double sgn = (gr >= c0 && gr < c0 + nb) ? -1.0 : 1.0;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int c = tc + q;
+    double acc = 0.0;
+    for (int b = c; b < kNB; ++b) acc += V[ti][b] * D[b][c];
+    if (gr < N) Pbuf[z * sP + (size_t)gr * kNB + c] = sgn * acc;
   }
-  // backward: p L = v  ->  p_k = (v_k - sum_{j>k} p_j L[j][k]) / L[k][k]
-  for (int k = nb - 1; k >= 0; --k) {
-    double acc = row[k];
-    for (int j = k + 1; j < nb; ++j) acc -= row[j] * L[j][k];
-    row[k] = acc / L[k][k];
-  }
-  if (gr < N) {
-    const double sgn = (gr >= c0 && gr < c0 + nb) ? -1.0 : 1.0;
-    double* po = Pbuf + z * sP + (size_t)gr * kNB;
-    for (int k = 0; k < kNB; ++k) po[k] = (k < nb) ? sgn * row[k] : 0.0;
-  }
+}
+
+cudaError_t spd_inverse_reserve(DenseWs& ws, int N, int Z) {
+  const int nblk = (N + kNB - 1) / kNB;
+  const size_t need = (size_t)nblk * kNB * kNB * Z;
+  cudaError_t e;
+  if ((e = ws.Pbuf.ensure(need)) != cudaSuccess) return e;
+  return ws.Cold.ensure(need);
 }
 
 cudaError_t spd_inverse(cudaStream_t s, double* A, int N, int ld, long long stride, int Z, double* logdet,
@@ -309,16 +369,15 @@ cudaError_t spd_inverse(cudaStream_t s, double* A, int N, int ld, long long stri
   const int nblk = (N + kNB - 1) / kNB;
   const long long sP = (long long)nblk * kNB * kNB;
   cudaError_t e;
-  if ((e = ws.Pbuf.ensure((size_t)sP * Z)) != cudaSuccess) return e;
-  if ((e = ws.Cold.ensure((size_t)sP * Z)) != cudaSuccess) return e;
+  if ((e = spd_inverse_reserve(ws, N, Z)) != cudaSuccess) return e;
   if ((e = cudaMemsetAsync(logdet, 0, sizeof(double) * Z, s)) != cudaSuccess) return e;
   for (int b = 0; b < nblk; ++b) {
     const int c0 = b * kNB;
     const int nb = (N - c0 < kNB) ? N - c0 : kNB;
-    sweep_panel_kernel<<<dim3((N + kPanelRows - 1) / kPanelRows, 1, Z), kPanelRows, 0, s>>>(
-        A, N, ld, stride, c0, nb, ws.Cold.p, ws.Pbuf.p, sP, logdet, info);
+    sweep_panel_kernel<<<dim3(nblk, 1, Z), 256, 0, s>>>(A, N, ld, stride, c0, nb, ws.Cold.p, ws.Pbuf.p, sP,
+                                                        logdet, info);
     GemmParams p{};
-    p.M = N; p.N = N; p.K = nb;
+    p.M = N; p.N = N; p.K = kNB;
     p.A = ws.Cold.p; p.lda = kNB; p.sA = sP;   // V
     p.B = ws.Cold.p; p.ldb = kNB; p.sB = sP;   // V
     p.C = A; p.ldc = ld; p.sC = stride;

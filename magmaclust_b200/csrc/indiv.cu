@@ -16,10 +16,9 @@
 #include "common.cuh"
 #include "indiv.cuh"
 #include "lbfgs.h"
+#include "indiv_eval.cuh"
 
 namespace mcb {
-
-constexpr int kT = 128;  // threads per CTA
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -242,113 +241,13 @@ __global__ void __launch_bounds__(kT) indiv_tau_kernel(IndivData dd, int K, cons
 }
 
 // -------------------------------------------------------------------------------------------------
-// M-step objective + gradient for one individual (whole CTA cooperates). Results in out[0..3] (smem).
+// M-step objective + gradient kernels (device function in indiv_eval.cuh)
 // -------------------------------------------------------------------------------------------------
-struct EvalSmem {
-  double* A;   // (n+2) x ld bordered matrix, swept in place
-  double* X;   // n x ld : W * c2
-  double* t;   // n
-  double* y;   // n
-  double* c1;  // n
-  double* red; // 9 * (kT/32)
-};
-
-__device__ __forceinline__ EvalSmem carve_eval(double* sm, int nmax) {
-  EvalSmem s;
-  const int ntot = nmax + 2, ld = ntot | 1;
-  s.A = sm;
-  s.X = s.A + (size_t)ntot * ld;
-  s.t = s.X + (size_t)nmax * ld;
-  s.y = s.t + nmax;
-  s.c1 = s.y + nmax;
-  s.red = s.c1 + nmax;
-  return s;
-}
-
-size_t eval_smem_bytes(int nmax) {
-  const int ntot = nmax + 2, ld = ntot | 1;
-  return sizeof(double) * ((size_t)ntot * ld + (size_t)nmax * ld + 3 * (size_t)nmax + 9 * (kT / 32) + 8);
-}
-
-// f = F_i(theta); g = dF_i/dtheta (skipped when !want_grad). out[0]=f, out[1..3]=g; all threads must call.
-__device__ void indiv_eval_cta(const EvalSmem& s, int n, const double* __restrict__ c2g, double th1, double th2,
-                               double sg, bool want_grad, double* out, int* bad) {
-  const int ntot = n + 2, ld = ntot | 1;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const double* bord[2] = {s.y, s.c1};
-  __syncthreads();
-  build_bordered(s.A, ld, n, 2, s.t, bord, th1, th2, sg);
-  const double logdet = cta_sweep(s.A, n, ntot, ld, bad);
-  const double yWy = -s.A[n * ld + n];
-  const double yWc = -s.A[n * ld + n + 1];
-  // 0.5 sum(W o c2)   (W = -A block)
-  double v1[1] = {0.0};
-  for (int e = threadIdx.x; e < n * n; e += kT) {
-    const int a = e / n, b = e - a * n;
-    v1[0] -= s.A[a * ld + b] * c2g[e];
-  }
-  cta_sum<1>(v1, s.red);
-  const double f = 0.5 * ((double)n * kLog2Pi + logdet + yWy) - yWc + 0.5 * v1[0];
-  if (!want_grad) {
-    if (threadIdx.x == 0) out[0] = f;
-    __syncthreads();
-    return;
-  }
-  // X = W c2  (n x n)
-  for (int a = warp; a < n; a += kT / 32) {
-    const double* ra = s.A + a * ld;
-    for (int b = lane; b < n; b += 32) {
-      double acc = 0.0;
-      for (int l = 0; l < n; ++l) acc -= ra[l] * c2g[l * n + b];
-      s.X[a * ld + b] = acc;
-    }
-  }
-  __syncthreads();
-  // traces against dPsi/dth1 (SE kernel incl. its diagonal), dPsi/dth2 (zero diagonal) and I
-  const double hl = exp(-th2) / 2.0;
-  double v[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-  for (int a = warp; a < n; a += kT / 32) {
-    const double* xa = s.X + a * ld;
-    const double pa = s.A[a * ld + n];
-    for (int b = lane; b < n; b += 32) {
-      const double* rb = s.A + b * ld;  // W symmetric: column b == row b
-      double h = 0.0;
-      for (int l = 0; l < n; ++l) h -= xa[l] * rb[l];
-      const double wab = -s.A[a * ld + b];
-      const double d = s.t[a] - s.t[b];
-      const double gg = hl * (d * d);
-      const double k0 = exp(th1 - gg);
-      const double k2 = gg * k0;
-      const double ub = rb[n] - 2.0 * rb[n + 1];  // (p - 2q)_b
-      v[0] += h * k0;  v[1] += h * k2;
-      v[3] += wab * k0; v[4] += wab * k2;
-      v[6] += pa * k0 * ub; v[7] += pa * k2 * ub;
-      if (a == b) { v[2] += h; v[5] += wab; v[8] += pa * ub; }
-    }
-  }
-  cta_sum<9>(v, s.red);
-  if (threadIdx.x == 0) {
-    out[0] = f;
-    out[1] = -0.5 * (v[6] + v[0] - v[3]);
-    out[2] = -0.5 * (v[7] + v[1] - v[4]);
-    out[3] = -sg * (v[8] + v[2] - v[5]);
-  }
-  __syncthreads();
-}
-
-__device__ __forceinline__ void load_indiv(const EvalSmem& s, const IndivData& dd, const IndivWork& w, int i,
-                                           int& n) {
-  const int o0 = dd.off[i];
-  n = dd.off[i + 1] - o0;
-  for (int a = threadIdx.x; a < n; a += kT) {
-    s.t[a] = dd.t[o0 + a];
-    s.y[a] = dd.y[o0 + a];
-    s.c1[a] = w.c1[o0 + a];
-  }
-}
+size_t eval_smem_bytes(int nmax) { return sizeof(double) * eval_smem_doubles(nmax); }
 
 // theta: [M][3] when theta_stride == 3, one shared [3] when theta_stride == 0.
 // f[M], g[M][3] per individual; if sum4 != NULL also atomically accumulates (f, g) into sum4[0..3].
+template <int E>
 __global__ void __launch_bounds__(kT) indiv_eval_kernel(IndivData dd, IndivWork w, int nmax,
                                                         const double* __restrict__ theta, int theta_stride,
                                                         int want_grad, double* __restrict__ f,
@@ -357,11 +256,11 @@ __global__ void __launch_bounds__(kT) indiv_eval_kernel(IndivData dd, IndivWork 
   extern __shared__ double sm[];
   __shared__ double out[4];
   const int i = blockIdx.x;
-  EvalSmem s = carve_eval(sm, nmax);
-  int n;
-  load_indiv(s, dd, w, i, n);
+  const int o0 = dd.off[i], n = dd.off[i + 1] - o0;
+  EvalSm s = eval_carve(sm, nmax);
+  eval_load(s, n, dd.t + o0, dd.y + o0, w.c1 + o0, w.c2 + dd.woff[i]);
   const double* th = theta + (size_t)i * theta_stride;
-  indiv_eval_cta(s, n, w.c2 + dd.woff[i], th[0], th[1], th[2], want_grad != 0, out, info);
+  indiv_eval_v1<E>(s, n, th[0], th[1], th[2], want_grad != 0, out, info);
   if (threadIdx.x == 0) {
     if (f) f[i] = out[0];
     if (g && want_grad) { g[3 * i] = out[1]; g[3 * i + 1] = out[2]; g[3 * i + 2] = out[3]; }
@@ -372,8 +271,9 @@ __global__ void __launch_bounds__(kT) indiv_eval_kernel(IndivData dd, IndivWork 
   }
 }
 
-// One CTA runs the whole L-BFGS optimisation of theta_i for its individual (CF.R:653-659): no host
-// round trips between objective evaluations.
+// One CTA runs the whole L-BFGS optimisation of theta_i for its individual (CF.R:653-659): corr2 stays in
+// shared memory and there are no host round trips between objective evaluations.
+template <int E>
 __global__ void __launch_bounds__(kT) indiv_mstep_kernel(IndivData dd, IndivWork w, int nmax,
                                                          const double* __restrict__ theta0,
                                                          double* __restrict__ theta_out, int maxit,
@@ -384,19 +284,18 @@ __global__ void __launch_bounds__(kT) indiv_mstep_kernel(IndivData dd, IndivWork
   __shared__ Lbfgs opt;
   __shared__ int st;
   const int i = blockIdx.x;
-  EvalSmem s = carve_eval(sm, nmax);
-  int n;
-  load_indiv(s, dd, w, i, n);
+  const int o0 = dd.off[i], n = dd.off[i + 1] - o0;
+  EvalSm s = eval_carve(sm, nmax);
+  eval_load(s, n, dd.t + o0, dd.y + o0, w.c1 + o0, w.c2 + dd.woff[i]);
   if (threadIdx.x == 0) {
     lb_init(opt, 3, theta0 + 3 * (size_t)i, maxit);
     st = LB_EVAL;
   }
   __syncthreads();
-  const double* c2g = w.c2 + dd.woff[i];
   int bad = 0;
   while (true) {
     const double a = opt.x[0], b = opt.x[1], c = opt.x[2];
-    indiv_eval_cta(s, n, c2g, a, b, c, true, out, &bad);
+    indiv_eval_v1<E>(s, n, a, b, c, true, out, &bad);
     if (threadIdx.x == 0) st = lb_advance(opt, out[0], out + 1);
     __syncthreads();
     if (st != LB_EVAL) break;
@@ -448,13 +347,28 @@ cudaError_t launch_tau(cudaStream_t s, const IndivData& dd, int M, int nmax, int
   return cudaGetLastError();
 }
 
+template <class K>
+static cudaError_t set_smem_t(K fn, size_t bytes) {
+  if (bytes <= 48 * 1024) return cudaSuccess;
+  return cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
 cudaError_t launch_indiv_eval(cudaStream_t s, const IndivData& dd, int M, int nmax, const IndivWork& w,
                               const double* theta, int theta_stride, int want_grad, double* f, double* g,
                               double* sum4, int* info) {
   const size_t sm = eval_smem_bytes(nmax);
-  cudaError_t e = set_smem((const void*)indiv_eval_kernel, sm);
-  if (e != cudaSuccess) return e;
-  indiv_eval_kernel<<<M, kT, sm, s>>>(dd, w, nmax, theta, theta_stride, want_grad, f, g, sum4, info);
+  const int E = eval_blocks_per_thread(nmax);
+  cudaError_t e;
+#define MCB_LAUNCH_EVAL(EE)                                                                                   \
+  do {                                                                                                        \
+    if ((e = set_smem_t(indiv_eval_kernel<EE>, sm)) != cudaSuccess) return e;                                 \
+    indiv_eval_kernel<EE><<<M, kT, sm, s>>>(dd, w, nmax, theta, theta_stride, want_grad, f, g, sum4, info);   \
+  } while (0)
+  if (E <= 1) MCB_LAUNCH_EVAL(1);
+  else if (E == 2) MCB_LAUNCH_EVAL(2);
+  else if (E <= 4) MCB_LAUNCH_EVAL(4);
+  else return cudaErrorInvalidValue;
+#undef MCB_LAUNCH_EVAL
   return cudaGetLastError();
 }
 
@@ -462,9 +376,18 @@ cudaError_t launch_indiv_mstep(cudaStream_t s, const IndivData& dd, int M, int n
                                const double* theta0, double* theta_out, int maxit, int* nfev, int* niter,
                                int* status, int* info) {
   const size_t sm = eval_smem_bytes(nmax);
-  cudaError_t e = set_smem((const void*)indiv_mstep_kernel, sm);
-  if (e != cudaSuccess) return e;
-  indiv_mstep_kernel<<<M, kT, sm, s>>>(dd, w, nmax, theta0, theta_out, maxit, nfev, niter, status, info);
+  const int E = eval_blocks_per_thread(nmax);
+  cudaError_t e;
+#define MCB_LAUNCH_MSTEP(EE)                                                                                  \
+  do {                                                                                                        \
+    if ((e = set_smem_t(indiv_mstep_kernel<EE>, sm)) != cudaSuccess) return e;                                \
+    indiv_mstep_kernel<EE><<<M, kT, sm, s>>>(dd, w, nmax, theta0, theta_out, maxit, nfev, niter, status, info); \
+  } while (0)
+  if (E <= 1) MCB_LAUNCH_MSTEP(1);
+  else if (E == 2) MCB_LAUNCH_MSTEP(2);
+  else if (E <= 4) MCB_LAUNCH_MSTEP(4);
+  else return cudaErrorInvalidValue;
+#undef MCB_LAUNCH_MSTEP
   return cudaGetLastError();
 }
 

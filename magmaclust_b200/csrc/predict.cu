@@ -166,7 +166,7 @@ extern "C" int mcb_posterior_mu_k(mcb_handle* h, int T, const double* timestamps
   for (int j = 1; j < T; ++j) H_CHECK(timestamps[j] > timestamps[j - 1], MCB_EINVAL, "mcb_posterior_mu_k: timestamps must be sorted and unique");
   H_CUDA(cudaSetDevice(h->device));
   const int M = h->M, K = h->K, N = h->N;
-  const int ldT = (T + 3) & ~3;
+  const int ldT = (T + 15) & ~15;
   const long long sT = (long long)T * ldT;
   // position of every training timestamp in the prediction grid (MC.R:323 builds t_pred as a superset)
   std::vector<double> grid(N);
@@ -187,6 +187,8 @@ extern "C" int mcb_posterior_mu_k(mcb_handle* h, int T, const double* timestamps
   H_CUDA(sync_copy(h, h->pgrid.p, timestamps, sizeof(double) * T, cudaMemcpyHostToDevice));
   H_CUDA(h->pKinv.ensure((size_t)K * sT)); H_CUDA(h->pcov.ensure((size_t)K * sT));
   H_CUDA(h->pwk.ensure((size_t)K * ldT)); H_CUDA(h->pmean.ensure((size_t)K * ldT)); H_CUDA(h->plogdet.ensure(2 * K));
+  H_CUDA(cudaMemsetAsync(h->pKinv.p, 0, sizeof(double) * h->pKinv.cap, h->st));  // zero row padding (ld % 16 == 0)
+  H_CUDA(cudaMemsetAsync(h->pcov.p, 0, sizeof(double) * h->pcov.cap, h->st));
   const double* tau_d = h->tau_new.p;
   if (tau) {
     H_CUDA(sync_copy(h, h->logL.p, tau, sizeof(double) * (size_t)M * K, cudaMemcpyHostToDevice));  // logL reused as staging

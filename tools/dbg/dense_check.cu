@@ -37,10 +37,9 @@ int main() {
   int* info; CK(cudaMalloc(&info, 16)); CK(cudaMemset(info, 0, 16));
   // ---- gemm_nt
   for (int N : {8, 33, 70, 401}) {
-    int ld = (N + 3) & ~3;
-    std::vector<double> A((size_t)N * ld), B((size_t)N * ld), C((size_t)N * ld, 0.0);
-    for (auto& v : A) v = nd(rng);
-    for (auto& v : B) v = nd(rng);
+    int ld = (N + 15) & ~15;
+    std::vector<double> A((size_t)N * ld, 0.0), B((size_t)N * ld, 0.0), C((size_t)N * ld, 0.0);
+    for (int i = 0; i < N; ++i) for (int j = 0; j < N; ++j) { A[(size_t)i * ld + j] = nd(rng); B[(size_t)i * ld + j] = nd(rng); }
     double *dA, *dB, *dC;
     CK(cudaMalloc(&dA, A.size() * 8)); CK(cudaMalloc(&dB, A.size() * 8)); CK(cudaMalloc(&dC, A.size() * 8));
     CK(cudaMemcpy(dA, A.data(), A.size() * 8, cudaMemcpyHostToDevice));
@@ -59,7 +58,7 @@ int main() {
   // ---- spd_inverse
   for (int N : {5, 20, 32, 33, 64, 100, 195, 401}) {
     for (int Z : {1, 3}) {
-      int ld = (N + 3) & ~3;
+      int ld = (N + 15) & ~15;
       long long sN = (long long)N * ld;
       std::vector<double> A((size_t)Z * sN, 0.0);
       std::vector<std::vector<double>> dense(Z);
