@@ -107,19 +107,21 @@ extern "C" void mcb_destroy(mcb_handle* h) {
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->st);
   comm_destroy(h);
+  for (auto& kv : h->eval_graphs) cudaGraphExecDestroy(kv.second.exec);
   for (auto e : h->evpool) cudaEventDestroy(e);
   mcb::DevBuf<double>* dbl[] = {&h->t, &h->y, &h->grid, &h->theta_i, &h->theta_k, &h->pi, &h->mk, &h->tau,
                                 &h->theta_i_new, &h->theta_k_new, &h->pi_new, &h->tau_new, &h->logL, &h->Winv,
                                 &h->pvec, &h->yWy, &h->logdet_i, &h->c1, &h->c2, &h->Fi, &h->fi_tmp, &h->gi_tmp,
                                 &h->theta_g, &h->Kinv, &h->cov, &h->wk, &h->mean, &h->rvec, &h->pz, &h->logdetK,
                                 &h->logdetA, &h->eK, &h->eD1, &h->eD2, &h->eCsum, &h->eX, &h->etheta, &h->ered,
-                                &h->elogdet, &h->ws.Pbuf, &h->ws.Cold, &h->ws.red, &h->scal, &h->pgrid, &h->pKinv,
+                                &h->elogdet, &h->ws.Pbuf, &h->ws.Cold, &h->ws.red, &h->ws.slabV, &h->ws.slabP, &h->ws.slabL, &h->scal, &h->pgrid, &h->pKinv,
                                 &h->pcov, &h->pwk, &h->pmean, &h->plogdet};
   for (auto* b : dbl) b->release();
   mcb::DevBuf<int>* ints[] = {&h->off, &h->gidx, &h->nfev_i, &h->niter_i, &h->status_i, &h->gmap_d, &h->egmap,
                               &h->info, &h->pmapidx};
   for (auto* b : ints) b->release();
   h->woff.release();
+  h->ws.bar.release();
   h->flush.release();
   if (h->tm0) { cudaEventDestroy(h->tm0); cudaEventDestroy(h->tm1); }
   if (h->hbuf) cudaFreeHost(h->hbuf);
@@ -177,7 +179,13 @@ extern "C" int mcb_set_data(mcb_handle* h, int M, int N, long long P, const int*
 }
 
 // ---- state -------------------------------------------------------------------------------------------
+static void drop_graphs(mcb_handle* h) {
+  for (auto& kv : h->eval_graphs) cudaGraphExecDestroy(kv.second.exec);
+  h->eval_graphs.clear();
+}
+
 static int alloc_state(mcb_handle* h, int K) {
+  drop_graphs(h);
   const size_t KN = (size_t)K * h->ld, KNN = (size_t)K * h->N * h->ld;
   H_CUDA(h->theta_k.ensure(3 * K)); H_CUDA(h->theta_k_new.ensure(3 * K));
   H_CUDA(h->pi.ensure(K)); H_CUDA(h->pi_new.ensure(K));
@@ -483,14 +491,13 @@ extern "C" int mcb_set_posterior(mcb_handle* h, const double* mean, const double
 // clusters z with gmap_h[z] == g (gmap -1: cluster not evaluated). f_out[g] and g_out[g][3] (d/da, d/db,
 // d/dsigma) follow logL_GP_mod(_common_hp_k) / gr_GP_mod(_common_hp_k) (CF.R:194-216, 250-278, 448-475,
 // 510-537). use_resident: take K^-1 and log|K| from the last E-step instead of building them.
-static int eval_mean_groups(mcb_handle* h, int G, const double* theta_h, const int* gmap_h, bool want_grad,
-                            bool use_resident, double* f_out, double* g_out) {
+// Stream work of one evaluation (no host synchronisation): reads theta / gmap from the pinned staging area,
+// leaves the reductions, log|K| and the not-PD flag in the pinned result area. Captured into a CUDA graph.
+static int eval_mean_enqueue(mcb_handle* h, int G, bool want_grad, bool use_resident) {
   const int N = h->N, ld = h->ld, K = h->K;
   const long long sN = (long long)N * ld;
   double* stage = h->hbuf + 1024;
   int* stage_i = (int*)(h->hbuf + 2048);
-  memcpy(stage, theta_h, sizeof(double) * 3 * G);
-  memcpy(stage_i, gmap_h, sizeof(int) * K);
   H_CUDA(cudaMemcpyAsync(h->etheta.p, stage, sizeof(double) * 3 * G, cudaMemcpyHostToDevice, h->st));
   H_CUDA(cudaMemcpyAsync(h->egmap.p, stage_i, sizeof(int) * K, cudaMemcpyHostToDevice, h->st));
   const double* Kinv;
@@ -505,13 +512,8 @@ static int eval_mean_groups(mcb_handle* h, int G, const double* theta_h, const i
     Kinv = h->eK.p;
     logdetK = h->elogdet.p;
   }
-  // sum of the hyper-posterior covariances of each group (theta independent: cached per E-step + grouping)
-  std::vector<int> gm(gmap_h, gmap_h + K);
-  if (!h->csum_valid || gm != h->csum_gmap) {
-    sum_groups(h->st, N, ld, sN, h->cov.p, h->egmap.p, K, h->eCsum.p, G, &h->launches);
-    h->csum_gmap = gm;
-    h->csum_valid = true;
-  }
+  // sum of the hyper-posterior covariances of each group
+  sum_groups(h->st, N, ld, sN, h->cov.p, h->egmap.p, K, h->eCsum.p, G, &h->launches);
   symv_mapped(h->st, N, ld, sN, Kinv, h->egmap.p, h->rvec.p, h->pz.p, K, &h->launches);
   double* redg = h->ered.p;          // [G][4]
   double* redz = redg + 4 * K;       // [K][4]
@@ -529,7 +531,58 @@ static int eval_mean_groups(mcb_handle* h, int G, const double* theta_h, const i
   double* hr = h->hbuf + 4096;
   H_CUDA(cudaMemcpyAsync(hr, h->ered.p, sizeof(double) * 12 * K, cudaMemcpyDeviceToHost, h->st));
   H_CUDA(cudaMemcpyAsync(hr + 12 * K, logdetK, sizeof(double) * G, cudaMemcpyDeviceToHost, h->st));
-  MCB_TRY(check_info(h, "mean-process objective"));
+  H_CUDA(cudaMemcpyAsync(h->hbuf + 8000, h->info.p, sizeof(int), cudaMemcpyDeviceToHost, h->st));
+  return MCB_OK;
+}
+
+// Evaluates G groups of clusters, group g with hyper-parameters theta_h[g] = (a, b, sigma) shared by the
+// clusters z with gmap_h[z] == g (gmap -1: cluster not evaluated). f_out[g] and g_out[g][3] (d/da, d/db,
+// d/dsigma) follow logL_GP_mod(_common_hp_k) / gr_GP_mod(_common_hp_k) (CF.R:194-216, 250-278, 448-475,
+// 510-537). use_resident: take K^-1 and log|K| from the last E-step instead of building them.
+// The ~40 kernels of one evaluation are replayed from a CUDA graph (one per shape), so the optimiser loop pays
+// one graph launch + one synchronisation per objective evaluation instead of ~40 launch calls.
+static int eval_mean_groups(mcb_handle* h, int G, const double* theta_h, const int* gmap_h, bool want_grad,
+                            bool use_resident, double* f_out, double* g_out) {
+  const int N = h->N, K = h->K;
+  double* stage = h->hbuf + 1024;
+  int* stage_i = (int*)(h->hbuf + 2048);
+  memcpy(stage, theta_h, sizeof(double) * 3 * G);
+  memcpy(stage_i, gmap_h, sizeof(int) * K);
+  static const bool no_graph = getenv("MCB_NO_GRAPH") != nullptr;
+  if (no_graph) {
+    MCB_TRY(eval_mean_enqueue(h, G, want_grad, use_resident));
+  } else {
+    const int key = ((G * 2 + (want_grad ? 1 : 0)) * 2 + (use_resident ? 1 : 0));
+    auto it = h->eval_graphs.find(key);
+    if (it == h->eval_graphs.end()) {
+      cudaGraph_t graph = nullptr;
+      cudaGraphExec_t exec = nullptr;
+      const long long before = h->launches;
+      H_CUDA(cudaStreamBeginCapture(h->st, cudaStreamCaptureModeThreadLocal));
+      const int rc = eval_mean_enqueue(h, G, want_grad, use_resident);
+      cudaError_t ce = cudaStreamEndCapture(h->st, &graph);
+      if (rc != MCB_OK || ce != cudaSuccess) {
+        if (graph) cudaGraphDestroy(graph);
+        if (rc == MCB_OK) { h->err = std::string("graph capture failed: ") + cudaGetErrorString(ce); return MCB_ECUDA; }
+        return rc;
+      }
+      H_CUDA(cudaGraphInstantiate(&exec, graph, 0));
+      cudaGraphDestroy(graph);
+      mcb_handle::EvalGraph eg{exec, h->launches - before};
+      h->launches = before;
+      it = h->eval_graphs.emplace(key, eg).first;
+    }
+    H_CUDA(cudaGraphLaunch(it->second.exec, h->st));
+    h->launches += it->second.kernels;
+  }
+  H_CUDA(cudaStreamSynchronize(h->st));
+  if (*(int*)(h->hbuf + 8000)) {
+    cudaMemsetAsync(h->info.p, 0, sizeof(int), h->st);
+    h->err = "mean-process objective: a covariance matrix is not positive definite (non-positive pivot); "
+             "the reference would silently fall back to MASS::ginv here";
+    return MCB_ENOTPD;
+  }
+  const double* hr = h->hbuf + 4096;
   const double* hg = hr;
   const double* hz = hr + 4 * K;
   const double* ht = hr + 8 * K;

@@ -65,6 +65,8 @@ constexpr int kNB = 32;  // pivot block of the blocked symmetric sweep
 struct DenseWs {
   DevBuf<double> Pbuf, Cold;  // [Z][Npad][kNB] panels of the blocked sweep
   DevBuf<double> red;         // scratch for reductions
+  DevBuf<double> slabV, slabP, slabL;  // panel exchange buffers of the persistent slab inverse (double-buffered)
+  DevBuf<unsigned> bar;                // its per-matrix barrier counters
 };
 
 // K[z] = SE covariance on `grid` with theta[z] = (a, b, sigma): exp(a - exp(-b)/2 d^2) off-diagonal,
@@ -78,6 +80,11 @@ void se_build(cudaStream_t s, double* Kmat, double* D1, double* D2, int N, int l
 // Gauss-Jordan). logdet[z] (device) receives log det of the ORIGINAL matrix; *info (device int) is set
 // non-zero if a non-positive pivot is met. Both triangles are read and written.
 cudaError_t spd_inverse_reserve(DenseWs& ws, int N, int Z);  // pre-size the workspace (no allocation later)
+// dense_slab.cu: persistent shared-memory-resident variant for N <= 768 (chosen automatically by spd_inverse)
+bool spd_inverse_slab_ok(int N, int ld);
+cudaError_t spd_inverse_slab_reserve(DenseWs& ws, int N, int Z);
+cudaError_t spd_inverse_slab(cudaStream_t s, double* A, int N, int ld, long long stride, int Z, double* logdet,
+                             int* info, DenseWs& ws, long long* launches);
 cudaError_t spd_inverse(cudaStream_t s, double* A, int N, int ld, long long stride, int Z, double* logdet,
                         int* info, DenseWs& ws, long long* launches);
 

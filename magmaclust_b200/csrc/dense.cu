@@ -357,6 +357,8 @@ __global__ void __launch_bounds__(256) sweep_panel_kernel(const double* __restri
 }
 
 cudaError_t spd_inverse_reserve(DenseWs& ws, int N, int Z) {
+  const int ld16 = (N + 15) & ~15;
+  if (spd_inverse_slab_ok(N, ld16)) return spd_inverse_slab_reserve(ws, N, Z);
   const int nblk = (N + kNB - 1) / kNB;
   const size_t need = (size_t)nblk * kNB * kNB * Z;
   cudaError_t e;
@@ -366,10 +368,17 @@ cudaError_t spd_inverse_reserve(DenseWs& ws, int N, int Z) {
 
 cudaError_t spd_inverse(cudaStream_t s, double* A, int N, int ld, long long stride, int Z, double* logdet,
                         int* info, DenseWs& ws, long long* launches) {
+  static const bool no_slab = getenv("MCB_NO_SLAB") != nullptr;
+  if (!no_slab && ld % 16 == 0 && spd_inverse_slab_ok(N, ld))
+    return spd_inverse_slab(s, A, N, ld, stride, Z, logdet, info, ws, launches);
   const int nblk = (N + kNB - 1) / kNB;
   const long long sP = (long long)nblk * kNB * kNB;
   cudaError_t e;
-  if ((e = spd_inverse_reserve(ws, N, Z)) != cudaSuccess) return e;
+  {
+    const size_t need = (size_t)sP * Z;
+    if ((e = ws.Pbuf.ensure(need)) != cudaSuccess) return e;
+    if ((e = ws.Cold.ensure(need)) != cudaSuccess) return e;
+  }
   if ((e = cudaMemsetAsync(logdet, 0, sizeof(double) * Z, s)) != cudaSuccess) return e;
   for (int b = 0; b < nblk; ++b) {
     const int c0 = b * kNB;

@@ -1,6 +1,8 @@
 // The opaque handle behind the C ABI: one GPU, its stream, the resident training set, model state and
 // workspaces.
 #pragma once
+#include <map>
+
 #include "common.cuh"
 #include "indiv.cuh"
 
@@ -45,6 +47,8 @@ struct mcb_handle {
   mcb::DevBuf<int> egmap;
   bool csum_valid = false;
   std::vector<int> csum_gmap;
+  struct EvalGraph { cudaGraphExec_t exec; long long kernels; };
+  std::map<int, EvalGraph> eval_graphs;   // captured evaluation sequences, keyed by (G, want_grad, resident)
   mcb::DenseWs ws;
   mcb::DevBuf<int> info;
   mcb::DevBuf<double> scal;        // small device scalars
