@@ -1,0 +1,119 @@
+"""CPU: the oracle against the reference's own stored outputs (tests/golden/hoo_diff_time.npz, made by
+tests/golden/make_golden.py from Simulations/Data + Simulations/Training of the reference)."""
+import numpy as np
+import pytest
+
+from oracle import magma_oracle as O
+from helpers import NAMES3, gold_dataset, load_gold
+
+
+def test_pi_k_is_row_mean_of_tau_all_100_datasets():
+    """CF.R:682: pi_k = mean_i tau_ik — holds to one unit in the last place in every stored model (R sums
+    sequentially, numpy pairwise)"""
+    g = load_gold()
+    pi = g["tau_i_k"].mean(axis=1)
+    assert np.max(np.abs(pi - g["pi_k"])) <= 2.3e-16
+
+
+def test_stored_models_use_common_hp_and_valid_tau():
+    g = load_gold()
+    assert np.all(g["theta_k"][:, 0, :] == g["theta_k"][:, 1, :])
+    assert np.all(g["theta_i"][:, 0, :] == g["theta_i"][:, 5, :])
+    assert np.allclose(g["tau_i_k"].sum(axis=2), 1.0, atol=1e-12)
+    # pen_diag = mean of the (common) individual noise sd (CF.R:662,668)
+    assert np.allclose(g["theta_k"][:, 0, 2], g["theta_i"][:, 0, 2], rtol=0, atol=1e-15)
+    # noise sd is optimised unconstrained and is negative in some stored models
+    assert (g["theta_i"][:, 0, 2] < 0).sum() == 8
+
+
+@pytest.mark.parametrize("d", list(range(0, 100, 4)))
+def test_estep_near_fixed_point(d):
+    """the stored tau is a near fixed point of e_step_VEM at the stored hp: identical hard assignments"""
+    db, hp, tau, m_k = gold_dataset(load_gold(), d)
+    out = O.e_step_VEM(db, m_k, O.kernel_mu, O.kernel, hp, tau)
+    A, B = O.tau_to_array(out["tau_i_k"]), O.tau_to_array(tau)
+    assert np.array_equal(A.argmax(1), B.argmax(1))
+    assert np.max(np.abs(A - B)) < 7e-2
+    for k in NAMES3:
+        c = out["cov"][k].m
+        assert np.allclose(c, c.T, rtol=0, atol=1e-9 * np.abs(c).max())
+        assert np.all(np.linalg.eigvalsh((c + c.T) / 2) > 0)
+
+
+def test_estep_fixed_point_is_tight_on_well_separated_datasets():
+    g = load_gold()
+    worst = []
+    for d in (0, 1, 2):
+        db, hp, tau, m_k = gold_dataset(g, d)
+        out = O.e_step_VEM(db, m_k, O.kernel_mu, O.kernel, hp, tau)
+        worst.append(np.max(np.abs(O.tau_to_array(out["tau_i_k"]) - O.tau_to_array(tau))))
+    assert max(worst) < 1e-6
+
+
+@pytest.mark.parametrize("d", [0, 7])
+def test_gradients_match_finite_differences(d):
+    db, hp, tau, m_k = gold_dataset(load_gold(), d)
+    param = O.e_step_VEM(db, m_k, O.kernel_mu, O.kernel, hp, tau)
+    th = np.array([1.3, 0.7, 0.4])
+    eps = 1e-6
+
+    def fd(f, x):
+        g = np.zeros_like(x)
+        for j in range(x.shape[0]):
+            e = np.zeros_like(x)
+            e[j] = eps
+            g[j] = (f(x + e) - f(x - e)) / (2 * eps)
+        return g
+
+    g1 = O.gr_clust_multi_GP_common_hp_i(th, db, param, O.kernel)
+    n1 = fd(lambda x: O.logL_clust_multi_GP_common_hp_i(x, db, param, O.kernel), th)
+    assert np.allclose(g1, n1, rtol=1e-5, atol=1e-5)
+    per = O.split_db(db)
+    i0 = next(iter(per))
+    g2 = O.gr_clust_multi_GP(th, per[i0], param, O.kernel)
+    n2 = fd(lambda x: O.logL_clust_multi_GP(x, per[i0], param, O.kernel), th)
+    assert np.allclose(g2, n2, rtol=1e-5, atol=1e-6)
+    for nhp in (2, 3):
+        g3 = O.gr_GP_mod_common_hp_k(th[:nhp], param["mean"], m_k, O.kernel_mu, param["cov"], 0.3)
+        n3 = fd(lambda x: O.logL_GP_mod_common_hp_k(x, param["mean"], m_k, O.kernel_mu, param["cov"], 0.3), th[:nhp])
+        assert np.allclose(g3, n3, rtol=1e-5, atol=1e-5)
+        g4 = O.gr_GP_mod(th[:nhp], param["mean"]["K2"], m_k["K2"], O.kernel_mu, param["cov"]["K2"], 0.3)
+        n4 = fd(lambda x: O.logL_GP_mod(x, param["mean"]["K2"], m_k["K2"], O.kernel_mu, param["cov"]["K2"], 0.3), th[:nhp])
+        assert np.allclose(g4, n4, rtol=1e-5, atol=1e-5)
+
+
+def test_training_recovers_the_stored_clustering():
+    """training_VEM from the study's start state and the stored clustering as tau_0 ends on the stored
+    clustering, and the planted clusters of the simulation are recovered up to label permutation"""
+    g = load_gold()
+    d = 0
+    db, hp, tau, m_k = gold_dataset(g, d)
+    ids = list(O.split_db(db).keys())
+    lab = O.tau_to_array(tau).argmax(1)
+    tau0 = {k: {i: 1.0 if lab[r] == c else 0.0 for r, i in enumerate(ids)} for c, k in enumerate(NAMES3)}
+    out = O.training_VEM(db, m_k, {"theta_k": g["ini_hp_theta_k"], "theta_i": g["ini_hp_theta_i"]},
+                         O.kernel_mu, O.kernel, tau0, True, True)
+    assert out["convergence"] and 1 <= out["n_iter"] <= 15
+    assert np.array_equal(O.pred_max_cluster(out["param"]["tau_i_k"]), lab + 1)
+    truth = g["true_cluster"][d]
+    # close to the planted partition up to label permutation (the study reports a mean ARI of 0.889)
+    import itertools
+    acc = max(np.mean(np.array(p)[lab] == truth) for p in itertools.permutations([1, 2, 3]))
+    assert acc >= 0.85
+    assert out["hp"]["pi_k"].shape == (3,) and abs(out["hp"]["pi_k"].sum() - 1) < 1e-12
+
+
+def test_prediction_shapes_and_identities():
+    g = load_gold()
+    db, hp, tau, m_k = gold_dataset(g, 3)
+    param = O.e_step_VEM(db, m_k, O.kernel_mu, O.kernel, hp, tau)
+    list_hp = {"hp": hp, "param": param}
+    new_db = {"ID": np.array([99] * 4), "Timestamp": np.array([1.0, 3.0, 5.5, 7.25]), "Output": np.array([20.0, 25.0, 31.0, 28.0])}
+    targets = np.array([0.5, 2.0, 6.0, 9.5])
+    out = O.full_algo_clust(db, new_db, targets, O.kernel, prior_mean=m_k, kern_0=O.kernel_mu, list_hp=list_hp)
+    tk = out["Hyperparameters"]["new_i"]["tau_k"]
+    assert abs(sum(tk.values()) - 1) < 1e-12
+    for k in NAMES3:
+        p = out["Prediction"][k]
+        assert p["Mean"].shape == (4,) and np.all(p["Var"] > 0)
+    assert np.array_equal(O.pred_max_cluster(tau), O.tau_to_array(tau).argmax(1) + 1)
