@@ -1,0 +1,180 @@
+/* mcb_shim.c — thin .Call marshalling between R and libmagmaclust_b200.so (include/mcb.h).
+ *
+ * SOURCE ONLY: R and its headers are not installed in the build image nor on the GPU box, so this file has
+ * never been compiled or run. It contains no arithmetic: every entry point copies
+ * pointers/lengths out of SEXPs, calls one mcb_* function and wraps the result. The executable tests of the
+ * same C ABI go through Python ctypes (tests/).
+ *
+ * Build (where R exists):  R CMD SHLIB mcb_shim.c -I../../include -L../../magmaclust_b200/lib -lmagmaclust_b200
+ */
+#include <R.h>
+#include <Rinternals.h>
+
+#include "mcb.h"
+
+static void handle_finalizer(SEXP ptr) {
+  mcb_handle* h = (mcb_handle*)R_ExternalPtrAddr(ptr);
+  if (h) {
+    mcb_destroy(h);
+    R_ClearExternalPtr(ptr);
+  }
+}
+
+static mcb_handle* get_handle(SEXP ptr) {
+  mcb_handle* h = (mcb_handle*)R_ExternalPtrAddr(ptr);
+  if (!h) Rf_error("magmaclust_b200: handle was destroyed");
+  return h;
+}
+
+/* Rf_error long-jumps: nothing allocated with malloc may be live when it is raised. All buffers below are R
+ * vectors (PROTECTed), so the only thing to release before raising is the PROTECT stack. */
+static void check(mcb_handle* h, int rc, int nprotect) {
+  if (rc == MCB_OK) return;
+  const char* msg = mcb_last_error(h);
+  UNPROTECT(nprotect);
+  Rf_error("libmagmaclust_b200 error %d: %s", rc, msg ? msg : "");
+}
+
+SEXP mcbR_create(SEXP device) {
+  mcb_handle* h = NULL;
+  int rc = mcb_create(&h, Rf_asInteger(device));
+  if (rc != MCB_OK) Rf_error("mcb_create failed (%d): %s", rc, mcb_last_error(NULL));
+  SEXP ptr = PROTECT(R_MakeExternalPtr(h, R_NilValue, R_NilValue));
+  R_RegisterCFinalizerEx(ptr, handle_finalizer, TRUE);
+  UNPROTECT(1);
+  return ptr;
+}
+
+/* offsets, grid_idx: integer (0-based); y, grid: double */
+SEXP mcbR_set_data(SEXP hp, SEXP offsets, SEXP grid_idx, SEXP y, SEXP grid) {
+  mcb_handle* h = get_handle(hp);
+  int M = Rf_length(offsets) - 1, N = Rf_length(grid);
+  long long P = Rf_xlength(y);
+  check(h, mcb_set_data(h, M, N, P, INTEGER(offsets), INTEGER(grid_idx), REAL(y), REAL(grid), M), 0);
+  return R_NilValue;
+}
+
+/* theta_k: 3 x K, theta_i: 3 x M (column-major = [K][3] / [M][3] row-major), tau: K x M (= [M][K]) */
+SEXP mcbR_e_step_VEM(SEXP hp, SEXP theta_k, SEXP theta_i, SEXP pi_k, SEXP m_k, SEXP old_tau, SEXP N_) {
+  mcb_handle* h = get_handle(hp);
+  int K = Rf_length(pi_k), M = Rf_length(theta_i) / 3, N = Rf_asInteger(N_);
+  SEXP mean = PROTECT(Rf_allocMatrix(REALSXP, N, K));      /* column k = mean of cluster k */
+  SEXP cov = PROTECT(Rf_alloc3DArray(REALSXP, N, N, K));   /* symmetric: row/column major agree */
+  SEXP tau = PROTECT(Rf_allocMatrix(REALSXP, K, M));
+  SEXP logL = PROTECT(Rf_allocMatrix(REALSXP, K, M));
+  check(h, mcb_e_step_VEM(h, K, REAL(theta_k), REAL(theta_i), REAL(pi_k), REAL(m_k), Rf_length(m_k), REAL(old_tau),
+                          REAL(mean), REAL(cov), REAL(tau), REAL(logL)), 4);
+  SEXP out = PROTECT(Rf_allocVector(VECSXP, 4));
+  SET_VECTOR_ELT(out, 0, mean);
+  SET_VECTOR_ELT(out, 1, cov);
+  SET_VECTOR_ELT(out, 2, tau);
+  SET_VECTOR_ELT(out, 3, logL);
+  UNPROTECT(5);
+  return out;
+}
+
+/* optimiser callbacks: fn and gr of optimr::opm(..., method = "L-BFGS-B") become one .Call each */
+SEXP mcbR_eval_indiv_common(SEXP hp, SEXP theta, SEXP want_grad) {
+  mcb_handle* h = get_handle(hp);
+  SEXP out = PROTECT(Rf_allocVector(REALSXP, 4));
+  double* o = REAL(out);
+  check(h, mcb_eval_indiv_common(h, REAL(theta), o, Rf_asLogical(want_grad) ? o + 1 : NULL), 1);
+  UNPROTECT(1);
+  return out;
+}
+
+SEXP mcbR_eval_indiv(SEXP hp, SEXP theta /* 3 x M */, SEXP want_grad) {
+  mcb_handle* h = get_handle(hp);
+  int M = Rf_length(theta) / 3;
+  SEXP f = PROTECT(Rf_allocVector(REALSXP, M));
+  SEXP g = PROTECT(Rf_allocMatrix(REALSXP, 3, M));
+  check(h, mcb_eval_indiv(h, REAL(theta), REAL(f), Rf_asLogical(want_grad) ? REAL(g) : NULL), 2);
+  SEXP out = PROTECT(Rf_allocVector(VECSXP, 2));
+  SET_VECTOR_ELT(out, 0, f);
+  SET_VECTOR_ELT(out, 1, g);
+  UNPROTECT(3);
+  return out;
+}
+
+SEXP mcbR_eval_mean(SEXP hp, SEXP k /* 0-based, -1 = common */, SEXP theta, SEXP pen_diag, SEXP want_grad) {
+  mcb_handle* h = get_handle(hp);
+  int nhp = Rf_length(theta), kk = Rf_asInteger(k);
+  SEXP out = PROTECT(Rf_allocVector(REALSXP, 1 + nhp));
+  double* o = REAL(out);
+  double* g = Rf_asLogical(want_grad) ? o + 1 : NULL;
+  int rc = kk < 0 ? mcb_eval_mean_common(h, REAL(theta), nhp, Rf_asReal(pen_diag), o, g)
+                  : mcb_eval_mean(h, kk, REAL(theta), nhp, Rf_asReal(pen_diag), o, g);
+  check(h, rc, 1);
+  UNPROTECT(1);
+  return out;
+}
+
+SEXP mcbR_elbo(SEXP hp, SEXP theta_k, SEXP theta_i) {
+  mcb_handle* h = get_handle(hp);
+  SEXP out = PROTECT(Rf_allocVector(REALSXP, 2));
+  int resident = Rf_isNull(theta_k);
+  check(h, mcb_elbo(h, resident ? NULL : REAL(theta_k), resident ? NULL : REAL(theta_i), REAL(out)), 1);
+  UNPROTECT(1);
+  return out;
+}
+
+/* built-in M-step (GPU-resident L-BFGS); returns list(theta_k 3 x K, theta_i 3 x M, pi_k, stats) */
+SEXP mcbR_m_step(SEXP hp, SEXP common_hp_k, SEXP common_hp_i, SEXP K_, SEXP M_) {
+  mcb_handle* h = get_handle(hp);
+  int K = Rf_asInteger(K_), M = Rf_asInteger(M_);
+  SEXP tk = PROTECT(Rf_allocMatrix(REALSXP, 3, K));
+  SEXP ti = PROTECT(Rf_allocMatrix(REALSXP, 3, M));
+  SEXP pi = PROTECT(Rf_allocVector(REALSXP, K));
+  SEXP st = PROTECT(Rf_allocVector(INTSXP, 4));
+  check(h, mcb_m_step(h, Rf_asLogical(common_hp_k), Rf_asLogical(common_hp_i), REAL(tk), REAL(ti), REAL(pi), INTEGER(st)), 4);
+  SEXP out = PROTECT(Rf_allocVector(VECSXP, 4));
+  SET_VECTOR_ELT(out, 0, tk);
+  SET_VECTOR_ELT(out, 1, ti);
+  SET_VECTOR_ELT(out, 2, pi);
+  SET_VECTOR_ELT(out, 3, st);
+  UNPROTECT(5);
+  return out;
+}
+
+SEXP mcbR_set_state(SEXP hp, SEXP theta_k, SEXP theta_i, SEXP pi_k, SEXP m_k, SEXP tau) {
+  mcb_handle* h = get_handle(hp);
+  check(h, mcb_set_state(h, Rf_length(pi_k), REAL(theta_k), REAL(theta_i), REAL(pi_k), REAL(m_k), Rf_length(m_k), REAL(tau)), 0);
+  return R_NilValue;
+}
+
+SEXP mcbR_vem_iteration(SEXP hp, SEXP common_hp_k, SEXP common_hp_i) {
+  mcb_handle* h = get_handle(hp);
+  SEXP out = PROTECT(Rf_allocVector(REALSXP, 3));
+  check(h, mcb_vem_iteration(h, Rf_asLogical(common_hp_k), Rf_asLogical(common_hp_i), REAL(out)), 1);
+  UNPROTECT(1);
+  return out;
+}
+
+SEXP mcbR_posterior_mu_k(SEXP hp, SEXP timestamps, SEXP tau, SEXP K_) {
+  mcb_handle* h = get_handle(hp);
+  int T = Rf_length(timestamps), K = Rf_asInteger(K_);
+  SEXP mean = PROTECT(Rf_allocMatrix(REALSXP, T, K));
+  SEXP cov = PROTECT(Rf_alloc3DArray(REALSXP, T, T, K));
+  check(h, mcb_posterior_mu_k(h, T, REAL(timestamps), Rf_isNull(tau) ? NULL : REAL(tau), REAL(mean), REAL(cov)), 2);
+  SEXP out = PROTECT(Rf_allocVector(VECSXP, 2));
+  SET_VECTOR_ELT(out, 0, mean);
+  SET_VECTOR_ELT(out, 1, cov);
+  UNPROTECT(3);
+  return out;
+}
+
+SEXP mcbR_predict(SEXP hp, SEXP offsets, SEXP obs_idx, SEXP y, SEXP theta_new, SEXP pi_k, SEXP pred_idx, SEXP K_) {
+  mcb_handle* h = get_handle(hp);
+  int B = Rf_length(offsets) - 1, K = Rf_asInteger(K_), Tp = Rf_length(pred_idx);
+  SEXP tau = PROTECT(Rf_allocMatrix(REALSXP, K, B));
+  SEXP mean = PROTECT(Rf_alloc3DArray(REALSXP, Tp, K, B));
+  SEXP var = PROTECT(Rf_alloc3DArray(REALSXP, Tp, K, B));
+  check(h, mcb_predict(h, B, INTEGER(offsets), INTEGER(obs_idx), REAL(y), REAL(theta_new),
+                       Rf_isNull(pi_k) ? NULL : REAL(pi_k), Tp, INTEGER(pred_idx), REAL(tau), REAL(mean), REAL(var)), 3);
+  SEXP out = PROTECT(Rf_allocVector(VECSXP, 3));
+  SET_VECTOR_ELT(out, 0, tau);
+  SET_VECTOR_ELT(out, 1, mean);
+  SET_VECTOR_ELT(out, 2, var);
+  UNPROTECT(4);
+  return out;
+}
