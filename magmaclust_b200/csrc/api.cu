@@ -48,13 +48,14 @@ static int ev_get(mcb_handle* h) {
 struct PhaseScope {
   mcb_handle* h;
   int phase, e0;
-  PhaseScope(mcb_handle* h_, int ph) : h(h_), phase(ph) {
+  cudaStream_t s;
+  PhaseScope(mcb_handle* h_, int ph, cudaStream_t s_ = nullptr) : h(h_), phase(ph), s(s_ ? s_ : h_->st) {
     e0 = ev_get(h);
-    cudaEventRecord(h->evpool[e0], h->st);
+    cudaEventRecord(h->evpool[e0], s);
   }
   ~PhaseScope() {
     int e1 = ev_get(h);
-    cudaEventRecord(h->evpool[e1], h->st);
+    cudaEventRecord(h->evpool[e1], s);
     h->spans.push_back({phase, e0, e1});
   }
 };
@@ -91,6 +92,10 @@ extern "C" int mcb_create(mcb_handle** out, int device) {
   mcb_handle* h = new mcb_handle();
   h->device = device;
   if ((e = cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking)) != cudaSuccess ||
+      (e = cudaStreamCreateWithFlags(&h->st2, cudaStreamNonBlocking)) != cudaSuccess ||
+      (e = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming)) != cudaSuccess ||
+      (e = cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming)) != cudaSuccess ||
+      (e = h->mstep_ctl.ensure(2 + 1024)) != cudaSuccess ||
       (e = cudaMallocHost(&h->hbuf, sizeof(double) * mcb_handle::kHbuf)) != cudaSuccess ||
       (e = h->info.ensure(4)) != cudaSuccess || (e = h->scal.ensure(64)) != cudaSuccess) {
     g_create_err = cudaGetErrorString(e);
@@ -125,6 +130,10 @@ extern "C" void mcb_destroy(mcb_handle* h) {
   h->flush.release();
   if (h->tm0) { cudaEventDestroy(h->tm0); cudaEventDestroy(h->tm1); }
   if (h->hbuf) cudaFreeHost(h->hbuf);
+  if (h->st2) { cudaStreamSynchronize(h->st2); cudaStreamDestroy(h->st2); }
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
+  h->mstep_ctl.release();
   if (h->st) cudaStreamDestroy(h->st);
   delete h;
 }
@@ -741,10 +750,25 @@ extern "C" int mcb_elbo(mcb_handle* h, const double* theta_k, const double* thet
   return elbo_impl(h, theta_k, ti, out);
 }
 
+// pen_diag = mean_i theta_i[3] over all ranks (CF.R:662)
+static int compute_pen_diag(mcb_handle* h, double* pen_diag) {
+  double* d = h->scal.p + 40;
+  theta3_sum(h->st, h->M, h->theta_i_new.p, d, &h->launches);
+  MCB_TRY(comm_allreduce_sum(h, d, 1));
+  H_CUDA(cudaMemcpyAsync(h->hbuf + 700, d, sizeof(double), cudaMemcpyDeviceToHost, h->st));
+  H_CUDA(cudaStreamSynchronize(h->st));
+  *pen_diag = h->hbuf[700] / (double)h->M_total;
+  return MCB_OK;
+}
+
 // ---- M-step ------------------------------------------------------------------------------------------
 static int m_step_impl(mcb_handle* h, int common_hp_k, int common_hp_i, int* stats) {
   const int M = h->M, K = h->K;
   int nfev_i = 0, nit_i = 0, nfev_k = 0, nit_k = 0;
+  // With individual-specific theta_i and a shared theta_k the two optimisations are independent (pen_diag only
+  // replaces the third entry of theta_k afterwards, CF.R:666-668): run them concurrently.
+  static const bool no_overlap = getenv("MCB_NO_OVERLAP") != nullptr;
+  const bool overlap = !no_overlap && !common_hp_i && common_hp_k && spd_inverse_slab_ok(h->N, h->ld);
   // --- individuals (CF.R:645-660)
   {
     PhaseScope ps(h, PH_MSTEP_I);
@@ -776,24 +800,29 @@ static int m_step_impl(mcb_handle* h, int common_hp_k, int common_hp_i, int* sta
       for (int i = 0; i < M; ++i) { rep[3 * i] = opt.x[0]; rep[3 * i + 1] = opt.x[1]; rep[3 * i + 2] = opt.x[2]; }
       H_CUDA(cudaMemcpyAsync(h->theta_i_new.p, rep.data(), sizeof(double) * 3 * M, cudaMemcpyHostToDevice, h->st));
       H_CUDA(cudaStreamSynchronize(h->st));
-    } else {
+    } else if (!overlap) {
       H_CUDA(launch_indiv_mstep(h->st, h->idata(), M, h->nmax, h->iwork(), h->theta_i.p, h->theta_i_new.p, 100,
-                                h->nfev_i.p, h->niter_i.p, h->status_i.p, h->info.p));
+                                h->nfev_i.p, h->niter_i.p, h->status_i.p, h->mstep_ctl.p, 0));
       ++h->launches;
     }
   }
-  // pen_diag = mean_i theta_i[3] (CF.R:662)
-  double pen_diag;
-  {
-    double* d = h->scal.p + 40;
-    theta3_sum(h->st, M, h->theta_i_new.p, d, &h->launches);
-    MCB_TRY(comm_allreduce_sum(h, d, 1));
-    H_CUDA(cudaMemcpyAsync(h->hbuf + 700, d, sizeof(double), cudaMemcpyDeviceToHost, h->st));
-    H_CUDA(cudaStreamSynchronize(h->st));
-    pen_diag = h->hbuf[700] / (double)h->M_total;
+  if (overlap) {
+    // theta_i optimisations on the second stream, leaving `reserve` SMs to the theta_k evaluations below
+    H_CUDA(cudaEventRecord(h->ev_fork, h->st));
+    H_CUDA(cudaStreamWaitEvent(h->st2, h->ev_fork, 0));
+    {
+      PhaseScope ps(h, PH_MSTEP_I, h->st2);
+      const int nblk = (h->N + kNB - 1) / kNB;
+      H_CUDA(launch_indiv_mstep(h->st2, h->idata(), M, h->nmax, h->iwork(), h->theta_i.p, h->theta_i_new.p, 100,
+                                h->nfev_i.p, h->niter_i.p, h->status_i.p, h->mstep_ctl.p, nblk));
+      ++h->launches;
+    }
+    H_CUDA(cudaEventRecord(h->ev_join, h->st2));
   }
   // --- mean processes (CF.R:664-680)
   h->h_theta_k_new.assign(3 * K, 0.0);
+  double pen_diag = 0.0;
+  if (!overlap) MCB_TRY(compute_pen_diag(h, &pen_diag));
   {
     PhaseScope ps(h, PH_MSTEP_K);
     if (common_hp_k) {
@@ -809,6 +838,11 @@ static int m_step_impl(mcb_handle* h, int common_hp_k, int common_hp_i, int* sta
         st = lb_advance(opt, f, g);
       }
       nfev_k = opt.nfev; nit_k = opt.iter;
+      if (overlap) {
+        // join the theta_i stream, then pen_diag = mean_i theta_i[3]
+        H_CUDA(cudaStreamWaitEvent(h->st, h->ev_join, 0));
+        MCB_TRY(compute_pen_diag(h, &pen_diag));
+      }
       for (int k = 0; k < K; ++k) {
         h->h_theta_k_new[3 * k] = opt.x[0];
         h->h_theta_k_new[3 * k + 1] = opt.x[1];

@@ -9,6 +9,9 @@
 struct mcb_handle {
   int device = 0;
   cudaStream_t st = nullptr;
+  cudaStream_t st2 = nullptr;              // second stream: theta_i optimisations overlapped with theta_k
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  mcb::DevBuf<int> mstep_ctl;               // work queue + SM reservation flags of indiv_mstep_kernel
   std::string err;
 
   // ---- communicator (NCCL, loaded lazily; nranks == 1 means single GPU) ----

@@ -271,43 +271,76 @@ __global__ void __launch_bounds__(kT) indiv_eval_kernel(IndivData dd, IndivWork 
   }
 }
 
-// One CTA runs the whole L-BFGS optimisation of theta_i for its individual (CF.R:653-659): corr2 stays in
-// shared memory and there are no host round trips between objective evaluations.
+// Persistent M-step kernel for individual-specific hyper-parameters (CF.R:653-659). Each CTA pulls individuals
+// from a global work queue and runs the WHOLE L-BFGS optimisation of theta_i in-kernel: corr2 stays in shared
+// memory across all objective evaluations and there are no host round trips.
+//
+// SM reservation: the theta_k optimiser (shared theta_k, CF.R:666-669) does not depend on theta_i, so m_step_impl
+// runs it concurrently on another stream. Its persistent slab inverse needs whole SMs (150 KB of shared memory per
+// CTA), which this kernel would otherwise keep occupied for milliseconds; so the first `reserve` SMs that report in
+// are left alone: CTAs that land on them exit immediately and their work flows to the others through the queue.
+// ctl[0] = work queue, ctl[1] = number of SMs decided so far, ctl[2 + smid] = 0 undecided / 3 deciding / 1 work / 2 reserved.
 template <int E>
-__global__ void __launch_bounds__(kT) indiv_mstep_kernel(IndivData dd, IndivWork w, int nmax,
+__global__ void __launch_bounds__(kT) indiv_mstep_kernel(IndivData dd, IndivWork w, int nmax, int M,
                                                          const double* __restrict__ theta0,
                                                          double* __restrict__ theta_out, int maxit,
                                                          int* __restrict__ nfev, int* __restrict__ niter,
-                                                         int* __restrict__ status, int* __restrict__ info) {
+                                                         int* __restrict__ status, int* __restrict__ ctl,
+                                                         int reserve) {
   extern __shared__ double sm[];
   __shared__ double out[4];
   __shared__ Lbfgs opt;
-  __shared__ int st;
-  const int i = blockIdx.x;
-  const int o0 = dd.off[i], n = dd.off[i + 1] - o0;
-  EvalSm s = eval_carve(sm, nmax);
-  eval_load(s, n, dd.t + o0, dd.y + o0, w.c1 + o0, w.c2 + dd.woff[i]);
+  __shared__ int st, cur;
   if (threadIdx.x == 0) {
-    lb_init(opt, 3, theta0 + 3 * (size_t)i, maxit);
-    st = LB_EVAL;
+    int role = 1;
+    if (reserve > 0) {
+      unsigned smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      int* flag = ctl + 2 + (smid & 1023);
+      const int old = atomicCAS(flag, 0, 3);
+      if (old == 0) {
+        role = (atomicAdd(ctl + 1, 1) < reserve) ? 2 : 1;
+        __threadfence();
+        atomicExch(flag, role);
+      } else {
+        role = old;
+        while (role == 3) role = *((volatile int*)flag);
+      }
+    }
+    cur = (role == 2) ? -1 : 0;
   }
   __syncthreads();
+  if (cur < 0) return;
+  EvalSm s = eval_carve(sm, nmax);
   int bad = 0;
-  while (true) {
-    const double a = opt.x[0], b = opt.x[1], c = opt.x[2];
-    indiv_eval_v1<E>(s, n, a, b, c, true, out, &bad);
-    if (threadIdx.x == 0) st = lb_advance(opt, out[0], out + 1);
+  for (;;) {
     __syncthreads();
-    if (st != LB_EVAL) break;
-  }
-  if (threadIdx.x == 0) {
-    theta_out[3 * (size_t)i] = opt.x[0];
-    theta_out[3 * (size_t)i + 1] = opt.x[1];
-    theta_out[3 * (size_t)i + 2] = opt.x[2];
-    nfev[i] = opt.nfev;
-    niter[i] = opt.iter;
-    status[i] = st;
-    (void)info;
+    if (threadIdx.x == 0) cur = atomicAdd(ctl, 1);
+    __syncthreads();
+    const int i = cur;
+    if (i >= M) break;
+    const int o0 = dd.off[i], n = dd.off[i + 1] - o0;
+    eval_load(s, n, dd.t + o0, dd.y + o0, w.c1 + o0, w.c2 + dd.woff[i]);
+    if (threadIdx.x == 0) {
+      lb_init(opt, 3, theta0 + 3 * (size_t)i, maxit);
+      st = LB_EVAL;
+    }
+    __syncthreads();
+    while (true) {
+      const double a = opt.x[0], b = opt.x[1], c = opt.x[2];
+      indiv_eval_v1<E>(s, n, a, b, c, true, out, &bad);
+      if (threadIdx.x == 0) st = lb_advance(opt, out[0], out + 1);
+      __syncthreads();
+      if (st != LB_EVAL) break;
+    }
+    if (threadIdx.x == 0) {
+      theta_out[3 * (size_t)i] = opt.x[0];
+      theta_out[3 * (size_t)i + 1] = opt.x[1];
+      theta_out[3 * (size_t)i + 2] = opt.x[2];
+      nfev[i] = opt.nfev;
+      niter[i] = opt.iter;
+      status[i] = st;
+    }
   }
 }
 
@@ -374,14 +407,24 @@ cudaError_t launch_indiv_eval(cudaStream_t s, const IndivData& dd, int M, int nm
 
 cudaError_t launch_indiv_mstep(cudaStream_t s, const IndivData& dd, int M, int nmax, const IndivWork& w,
                                const double* theta0, double* theta_out, int maxit, int* nfev, int* niter,
-                               int* status, int* info) {
+                               int* status, int* ctl, int reserve_sms) {
   const size_t sm = eval_smem_bytes(nmax);
   const int E = eval_blocks_per_thread(nmax);
   cudaError_t e;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if ((e = cudaMemsetAsync(ctl, 0, sizeof(int) * (2 + 1024), s)) != cudaSuccess) return e;
 #define MCB_LAUNCH_MSTEP(EE)                                                                                  \
   do {                                                                                                        \
     if ((e = set_smem_t(indiv_mstep_kernel<EE>, sm)) != cudaSuccess) return e;                                \
-    indiv_mstep_kernel<EE><<<M, kT, sm, s>>>(dd, w, nmax, theta0, theta_out, maxit, nfev, niter, status, info); \
+    int per_sm = 1;                                                                                           \
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, indiv_mstep_kernel<EE>, kT, sm);                   \
+    if (per_sm < 1) per_sm = 1;                                                                               \
+    int grid = per_sm * sms;                                                                                  \
+    if (grid > M && reserve_sms == 0) grid = M;                                                               \
+    indiv_mstep_kernel<EE><<<grid, kT, sm, s>>>(dd, w, nmax, M, theta0, theta_out, maxit, nfev, niter, status, \
+                                                ctl, reserve_sms);                                            \
   } while (0)
   if (E <= 1) MCB_LAUNCH_MSTEP(1);
   else if (E == 2) MCB_LAUNCH_MSTEP(2);
