@@ -6,11 +6,11 @@
 // a global-memory barrier (~1 us) instead of kernel boundaries.
 //
 // Same algorithm as dense.cu (blocked symmetric sweep in Cholesky form), per pivot block b:
-//   phase 1  CTA b: eliminate its diagonal block D = Lu Delta Lu' in registers (1 barrier per pivot), publish
-//            L^-1 = Delta^-1/2 Lu^-1 and add sum(log pivots) to log det                         | grid barrier
 //   phase 2  every CTA: V_I = A[I,b] L^-T, P_I = V_I L^-1 (DMMA), publish V_I and P_I          | grid barrier
-//   phase 3  every CTA: slab[:, J] -= V_I V_J' for J != b (DMMA, V_J streamed from L2), slab[:, b] = P_I;
-//            CTA b instead: slab[:, J] = P_J', slab[:, b] = -D^-1
+//   phase 3  CTA I != b, b+1: slab[:, J] -= V_I V_J' for J != b (DMMA, V_J streamed from L2), slab[:, b] = P_I;
+//            CTA b: slab[:, J] = P_J', slab[:, b] = -D^-1;
+//            CTA b+1 (lookahead): updates only its diagonal block and eliminates it, D = Lu Delta Lu', in
+//            registers (1 CTA barrier per pivot), publishing L^-1 = Delta^-1/2 Lu^-1 for the next step  | grid barrier
 // After the last block the slabs hold -A^-1; they are negated on the way back to global memory.
 #include <cooperative_groups.h>
 
@@ -104,6 +104,7 @@ spd_inverse_slab_kernel(double* __restrict__ Aall, int N, int ld, long long stri
   double logdet_part = 0.0;  // lanes of warp 0: sum of log pivots of the blocks this CTA factored
   const long long sPz = (long long)Npad * kNB;          // per-matrix panel size
   const long long sPall = sPz * gridDim.y;              // per-parity size
+  const int ti = tid >> 3, tc = (tid & 7) * 4;          // factorisation ownership: row ti, columns tc..tc+3
 
   // ---- load the slab (rows r0..r0+31, all ld columns incl. zero pads) ----------------------------------
   for (int e = tid; e < kNB * (ld / 2); e += kSlabThreads) {
@@ -115,88 +116,92 @@ spd_inverse_slab_kernel(double* __restrict__ Aall, int N, int ld, long long stri
   }
   __syncthreads();
 
-  const int ti = tid >> 3, tc = (tid & 7) * 4;  // phase-1 ownership: row ti, columns tc..tc+3
+  // Factor this CTA's diagonal block (pivot block bb): D = Lu Delta Lu', publish L^-1 = Delta^-1/2 Lu^-1.
+  // One register per (row ti, column c): it holds D[ti][c] until pivot c has been eliminated and Lu^-1[ti][c]
+  // afterwards. Per pivot k a single shared vector u travels: u[c < k] = Lu^-1[k][c], u[k] = 1, u[c > k] = D[c][k],
+  // u[32] = 1 / pivot; every thread below the pivot row does 4 FMAs, one barrier per pivot.
+  auto factor_block = [&](int bb) {
+    const int c0 = bb * kNB;
+    const int nb = min(kNB, N - c0);
+    double* Lg = Lbuf + ((size_t)(bb & 1) * gridDim.y + z) * kNB * kNB;
+    double reg[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int c = tc + q;
+      // identity padding keeps a partial last block a no-op for the extra pivots
+      reg[q] = (ti < nb && c < nb) ? slab[(size_t)ti * lds + c0 + c] : (ti == c ? 1.0 : 0.0);
+    }
+    if (tc == 0) {
+      if (ti > 0) uvec[ti] = reg[0];
+      else { uvec[0] = 1.0; uvec[kNB] = fast_rcp(reg[0]); piv[0] = reg[0]; }
+    }
+    __syncthreads();
+    for (int k = 0; k < kNB; ++k) {
+      const double* u = uvec + (k & 1) * (kNB + 4);
+      if (ti > k) {
+        const double m = -u[ti] * u[kNB];
+        const double2 ua = *reinterpret_cast<const double2*>(u + tc);
+        const double2 ub = *reinterpret_cast<const double2*>(u + tc + 2);
+        const unsigned kq = (unsigned)(k - tc);
+        if (kq < 4u) {  // the register of column k switches from D[ti][k] to Lu^-1[ti][k] = 0 - m * 1
+          if (kq == 0) reg[0] = 0.0;
+          if (kq == 1) reg[1] = 0.0;
+          if (kq == 2) reg[2] = 0.0;
+          if (kq == 3) reg[3] = 0.0;
+        }
+        reg[0] = fma(m, ua.x, reg[0]);
+        reg[1] = fma(m, ua.y, reg[1]);
+        reg[2] = fma(m, ub.x, reg[2]);
+        reg[3] = fma(m, ub.y, reg[3]);
+      }
+      const int k1 = k + 1;
+      if (k1 < kNB) {
+        double* un = uvec + (k1 & 1) * (kNB + 4);
+        const unsigned q1 = (unsigned)(k1 - tc);
+        if (ti == k1) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            if (tc + q < k1) un[tc + q] = reg[q];
+        }
+        if (q1 < 4u && ti >= k1) {
+          const double v = q1 == 0 ? reg[0] : q1 == 1 ? reg[1] : q1 == 2 ? reg[2] : reg[3];
+          if (ti > k1) un[ti] = v;
+          else { un[k1] = 1.0; un[kNB] = fast_rcp(v); piv[k1] = v; }
+        }
+      }
+      __syncthreads();
+    }
+    {
+      const double sc = 1.0 / sqrt(piv[ti]);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int c = tc + q;
+        Lg[ti * kNB + c] = (c == ti) ? sc : (c < ti ? reg[q] * sc : 0.0);
+      }
+    }
+    if (tid < 32) {
+      // log det and the positive-definiteness check are off the critical path: L^-1 is already on its way
+      const double d = piv[tid];
+      const bool bad = !(d > 0.0);
+      if (__any_sync(0xffffffffu, bad) && tid == 0) *info = 1;
+      logdet_part += log(d);
+    }
+  };
+
+  if (I == 0) factor_block(0);
+  arrivals += nblk;
+  slab_barrier(counter, arrivals);
+
   for (int b = 0; b < nblk; ++b) {
     const int c0 = b * kNB;
     const int nb = min(kNB, N - c0);
     const int par = b & 1;
     double* Vg = Vbuf + par * sPall + z * sPz;
     double* Pg = Pbuf + par * sPall + z * sPz;
-    double* Lg = Lbuf + ((size_t)par * gridDim.y + z) * kNB * kNB;
-
-    // ---- phase 1: CTA b factors its diagonal block ----------------------------------------------------
-    SLAB_T(0);
-    SLAB_TP(4);
-    if (I == b) {
-      // One register per (row ti, column c): it holds D[ti][c] until pivot c has been eliminated and
-      // Lu^-1[ti][c] afterwards. Per pivot k a single shared vector u travels: u[c < k] = Lu^-1[k][c],
-      // u[k] = 1, u[c > k] = D[c][k], u[32] = 1 / pivot; every thread below the pivot row does 4 branch-free FMAs.
-      double reg[4];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int c = tc + q;
-        // identity padding keeps a partial last block a no-op for the extra pivots
-        reg[q] = (ti < nb && c < nb) ? slab[(size_t)ti * lds + c0 + c] : (ti == c ? 1.0 : 0.0);
-      }
-      if (tc == 0) {
-        if (ti > 0) uvec[ti] = reg[0];
-        else { uvec[0] = 1.0; uvec[kNB] = fast_rcp(reg[0]); piv[0] = reg[0]; }
-      }
-      __syncthreads();
-      SLAB_TP(8);
-      for (int k = 0; k < kNB; ++k) {
-        const double* u = uvec + (k & 1) * (kNB + 4);
-        if (ti > k) {
-          const double m = u[ti] * u[kNB];
-          const double2 ua = *reinterpret_cast<const double2*>(u + tc);
-          const double2 ub = *reinterpret_cast<const double2*>(u + tc + 2);
-          const int kq = k - tc;
-          reg[0] = fma(-m, ua.x, kq == 0 ? 0.0 : reg[0]);
-          reg[1] = fma(-m, ua.y, kq == 1 ? 0.0 : reg[1]);
-          reg[2] = fma(-m, ub.x, kq == 2 ? 0.0 : reg[2]);
-          reg[3] = fma(-m, ub.y, kq == 3 ? 0.0 : reg[3]);
-        }
-        const int k1 = k + 1;
-        if (k1 < kNB) {
-          double* un = uvec + (k1 & 1) * (kNB + 4);
-          const int q1 = k1 - tc;
-          if (ti == k1) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-              if (tc + q < k1) un[tc + q] = reg[q];
-          }
-          if (q1 >= 0 && q1 < 4) {
-            const double v = q1 == 0 ? reg[0] : q1 == 1 ? reg[1] : q1 == 2 ? reg[2] : reg[3];
-            if (ti > k1) un[ti] = v;
-            else if (ti == k1) { un[k1] = 1.0; un[kNB] = fast_rcp(v); piv[k1] = v; }
-          }
-        }
-        __syncthreads();
-      }
-      SLAB_TP(9);
-      {
-        const double sc = 1.0 / sqrt(piv[ti]);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int c = tc + q;
-          Lg[ti * kNB + c] = (c == ti) ? sc : (c < ti ? reg[q] * sc : 0.0);
-        }
-      }
-      SLAB_TP(10);
-      if (tid < 32) {
-        // log det and the positive-definiteness check are off the critical path: L^-1 is already on its way
-        const double d = piv[tid];
-        const bool bad = !(d > 0.0);
-        if (__any_sync(0xffffffffu, bad) && tid == 0) *info = 1;
-        logdet_part += log(d);
-      }
-    }
-    SLAB_TP(5);
-    arrivals += nblk;
-    slab_barrier(counter, arrivals);
-    SLAB_T(1);
+    const double* Lg = Lbuf + ((size_t)par * gridDim.y + z) * kNB * kNB;
 
     // ---- phase 2: V_I = R L^-T, P_I = V L^-1 -------------------------------------------------------------
+    SLAB_T(1);
     for (int e = tid; e < kNB * kNB; e += kSlabThreads) {
       const int r = e >> 5, c = e & 31;
       Ls[r * kLp + c] = __ldcg(Lg + e);
@@ -208,7 +213,7 @@ spd_inverse_slab_kernel(double* __restrict__ Aall, int N, int ld, long long stri
     __syncthreads();
     mm32_nt(Rs, Ls, Vs, warp, lane);     // V[r][c] = sum_b R[r][b] Linv[c][b]
     __syncthreads();
-    // P[r][c] = sum_b V[r][b] Linv[b][c] = (V * (Linv')')[r][c]: B operand rows = columns of Linv
+    // P[r][c] = sum_b V[r][b] Linv[b][c]: B operand rows = columns of Linv
     {
 #pragma unroll
       for (int t = 0; t < 2; ++t) {
@@ -235,13 +240,33 @@ spd_inverse_slab_kernel(double* __restrict__ Aall, int N, int ld, long long stri
     arrivals += nblk;
     slab_barrier(counter, arrivals);
     SLAB_T(3);
-    SLAB_TP(6);
 
-    // ---- phase 3: trailing update of the slab ------------------------------------------------------------
-    if (I != b) {
-      // Each warp owns the 8-column tiles tj = warp, warp + 8, ...; ALL its B fragments (rows of V_J, straight
-      // from L2) are requested up front so that one L2 latency covers the whole phase; A fragments (V_I) are
-      // re-read from shared memory per tile.
+    // ---- phase 3 --------------------------------------------------------------------------------------
+    if (I == b + 1) {
+      // Lookahead: the next pivot CTA only needs its diagonal block up to date (everything else in its slab is
+      // dead: its rows are replaced by P_J' at the next step), so it updates those 32 columns with its own V and
+      // factors the block while the other CTAs do their trailing updates.
+      const int c1 = (b + 1) * kNB;
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        const int tile = warp * 2 + t;
+        const int tI = tile >> 2, tJ = tile & 3;
+        double n0 = 0.0, n1 = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          dmma884_s(n0, n1, Vs[(8 * tI + gr) * kLp + 4 * k + gc], Vs[(8 * tJ + gr) * kLp + 4 * k + gc]);
+        double* cp = slab + (size_t)(8 * tI + gr) * lds + c1 + 8 * tJ + 2 * gc;
+        cp[0] -= n0;
+        cp[1] -= n1;
+      }
+      __syncthreads();
+      SLAB_TP(4);
+      factor_block(b + 1);
+      SLAB_TP(5);
+    } else if (I != b) {
+      // trailing update of the slab. Each warp owns the 8-column tiles tj = warp, warp + 8, ...; ALL its B
+      // fragments (rows of V_J, straight from L2) are requested up front so that one L2 latency covers the whole
+      // phase; A fragments (V_I) are re-read from shared memory per tile.
       constexpr int kMaxT = 12;              // tiles per warp: ld / 8 / 8 <= 12 for N <= 768
       const int ntile = ld / 8;              // ld <= Npad; columns >= N only see zero V rows
       double bf[kMaxT][8];
@@ -296,6 +321,10 @@ spd_inverse_slab_kernel(double* __restrict__ Aall, int N, int ld, long long stri
     }
     __syncthreads();
     SLAB_TP(7);
+    if (b + 1 < nblk) {
+      arrivals += nblk;
+      slab_barrier(counter, arrivals);
+    }
   }
 
   if (tid < 32) {
