@@ -71,6 +71,21 @@ __device__ double sweep_p(double* A, int n, int ntot, int ld, int* bad) {
   return logdet;
 }
 
+// KC[k][i][j] = k_theta*(g_i, g_j) + C_k[i][j] on the prediction grid (diagonal exp(th1), no noise): the SE kernel of
+// the new individuals depends only on the pair of grid points, so it is evaluated T^2 times here instead of
+// B * K * T * n* times inside predict_kernel (MC.R:261-264 evaluates it per new individual and cluster).
+__global__ void kc_build_kernel(int K, int T, int ldT, const double* __restrict__ pgrid, const double* __restrict__ pcov,
+                                const double* __restrict__ theta, double* __restrict__ KC) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = blockIdx.y * blockDim.y + threadIdx.y;
+  if (i >= T || j >= T) return;
+  const double th1 = theta[0], th2 = theta[1];
+  const double d = pgrid[i] - pgrid[j];
+  const double e = (i == j) ? exp(th1) : exp(th1 - exp(-th2) / 2.0 * (d * d));
+  const size_t sT = (size_t)T * ldT;
+  for (int k = 0; k < K; ++k) KC[k * sT + (size_t)i * ldT + j] = e + pcov[k * sT + (size_t)i * ldT + j];
+}
+
 __global__ void __launch_bounds__(kTP) predict_kernel(int K, int T, int ldT, const double* __restrict__ pgrid,
                                                       const double* __restrict__ pmean,
                                                       const double* __restrict__ pcov, const int* __restrict__ off,
@@ -87,9 +102,7 @@ __global__ void __launch_bounds__(kTP) predict_kernel(int K, int T, int ldT, con
   double* ts = A + (size_t)(nmax + 1) * ((nmax + 1) | 1);
   double* lk = ts + nmax;                       // K
   int* idx = (int*)(lk + K);
-  const double th1 = theta[0], th2 = theta[1], sg = theta[2];
-  const double hl = exp(-th2) / 2.0;
-  const double dg = exp(th1) + sg * sg;
+  const double sg = theta[2];
   for (int a = threadIdx.x; a < n; a += kTP) {
     idx[a] = oidx[o0 + a];
     ts[a] = pgrid[idx[a]];
@@ -99,13 +112,12 @@ __global__ void __launch_bounds__(kTP) predict_kernel(int K, int T, int ldT, con
   for (int k = 0; k < K; ++k) {
     const double* Ck = pcov + k * sC;
     const double* mk = pmean + (size_t)k * ldT;
-    // S = Psi* + C_k[t*,t*], bordered with z = y* - m_k[t*]   (CF.R:776-777)
+    // S = Psi* + C_k[t*,t*], bordered with z = y* - m_k[t*]   (CF.R:776-777); Ck here is k_theta*(.,.) + C_k
     for (int e = threadIdx.x; e < ntot * ntot; e += kTP) {
       const int a = e / ntot, c = e - a * ntot;
       double v;
       if (a < n && c < n) {
-        const double d = ts[a] - ts[c];
-        v = ((a == c) ? dg : exp(th1 - hl * (d * d))) + Ck[(size_t)idx[a] * ldT + idx[c]];
+        v = Ck[(size_t)idx[a] * ldT + idx[c]] + ((a == c) ? sg * sg : 0.0);
       } else if (a < n) {
         v = yv[o0 + a] - mk[idx[a]];
       } else if (c < n) {
@@ -121,12 +133,10 @@ __global__ void __launch_bounds__(kTP) predict_kernel(int K, int T, int ldT, con
       // Mean_k = m_k[tp] + Gamma' S^-1 z ; Var_k = diag(Sigma(tp) + C_k[tp,tp] - Gamma' S^-1 Gamma)  (MC.R:261-268)
       for (int j = threadIdx.x; j < Tp; j += kTP) {
         const int gj = pidx[j];
-        const double tj = pgrid[gj];
         double gcol[kMaxObs];  // Gamma[:, j] = k(t*, tp_j) + C_k[t*, tp_j]   (MC.R:263)
         double mean = mk[gj];
         for (int a = 0; a < n; ++a) {
-          const double da = ts[a] - tj;
-          const double ga = exp(th1 - hl * (da * da)) + Ck[(size_t)idx[a] * ldT + gj];
+          const double ga = Ck[(size_t)idx[a] * ldT + gj];
           gcol[a] = ga;
           mean += ga * A[a * ld + n];
         }
@@ -138,7 +148,7 @@ __global__ void __launch_bounds__(kTP) predict_kernel(int K, int T, int ldT, con
         }
         const size_t o = ((size_t)b * K + k) * Tp + j;
         out_mean[o] = mean;
-        out_var[o] = dg + Ck[(size_t)gj * ldT + gj] - quad;
+        out_var[o] = sg * sg + Ck[(size_t)gj * ldT + gj] - quad;
       }
     }
     __syncthreads();
@@ -316,7 +326,10 @@ extern "C" int mcb_predict(mcb_handle* h, int B, const int* offsets, const int* 
     cudaEventCreate(&a); cudaEventCreate(&b2);
     h->evpool.push_back(a); h->evpool.push_back(b2);
     cudaEventRecord(a, h->st);
-    predict_kernel<<<B, kTP, smem, h->st>>>(K, T, h->ldT, h->pgrid.p, h->pmean.p, h->pcov.p, d_off.p, d_idx.p, d_y.p,
+    kc_build_kernel<<<dim3((T + 31) / 32, (T + 7) / 8), dim3(32, 8), 0, h->st>>>(K, T, h->ldT, h->pgrid.p, h->pcov.p,
+                                                                                 d_small.p, h->pKinv.p);
+    ++h->launches;
+    predict_kernel<<<B, kTP, smem, h->st>>>(K, T, h->ldT, h->pgrid.p, h->pmean.p, h->pKinv.p, d_off.p, d_idx.p, d_y.p,
                                             d_small.p, d_small.p + 3, Tp, d_pidx.p, nmax, d_tau.p,
                                             out_mean ? d_mean.p : nullptr, out_mean ? d_var.p : nullptr, h->info.p);
     cudaEventRecord(b2, h->st);
