@@ -247,8 +247,8 @@ size_t eval_smem_bytes(int nmax) { return sizeof(double) * eval_smem_doubles(nma
 
 // theta: [M][3] when theta_stride == 3, one shared [3] when theta_stride == 0.
 // f[M], g[M][3] per individual; if sum4 != NULL also atomically accumulates (f, g) into sum4[0..3].
-template <int E>
-__global__ void __launch_bounds__(kT) indiv_eval_kernel(IndivData dd, IndivWork w, int nmax,
+template <int E, int TT>
+__global__ void __launch_bounds__(TT) indiv_eval_kernel(IndivData dd, IndivWork w, int nmax,
                                                         const double* __restrict__ theta, int theta_stride,
                                                         int want_grad, double* __restrict__ f,
                                                         double* __restrict__ g, double* __restrict__ sum4,
@@ -258,9 +258,9 @@ __global__ void __launch_bounds__(kT) indiv_eval_kernel(IndivData dd, IndivWork 
   const int i = blockIdx.x;
   const int o0 = dd.off[i], n = dd.off[i + 1] - o0;
   EvalSm s = eval_carve(sm, nmax);
-  eval_load(s, n, dd.t + o0, dd.y + o0, w.c1 + o0, w.c2 + dd.woff[i]);
+  eval_load<TT>(s, n, dd.t + o0, dd.y + o0, w.c1 + o0, w.c2 + dd.woff[i]);
   const double* th = theta + (size_t)i * theta_stride;
-  indiv_eval_v1<E>(s, n, th[0], th[1], th[2], want_grad != 0, out, info);
+  indiv_eval_v1<E, TT>(s, n, th[0], th[1], th[2], want_grad != 0, out, info);
   if (threadIdx.x == 0) {
     if (f) f[i] = out[0];
     if (g && want_grad) { g[3 * i] = out[1]; g[3 * i + 1] = out[2]; g[3 * i + 2] = out[3]; }
@@ -280,8 +280,8 @@ __global__ void __launch_bounds__(kT) indiv_eval_kernel(IndivData dd, IndivWork 
 // CTA), which this kernel would otherwise keep occupied for milliseconds; so the first `reserve` SMs that report in
 // are left alone: CTAs that land on them exit immediately and their work flows to the others through the queue.
 // ctl[0] = work queue, ctl[1] = number of SMs decided so far, ctl[2 + smid] = 0 undecided / 3 deciding / 1 work / 2 reserved.
-template <int E>
-__global__ void __launch_bounds__(kT) indiv_mstep_kernel(IndivData dd, IndivWork w, int nmax, int M,
+template <int E, int TT>
+__global__ void __launch_bounds__(TT) indiv_mstep_kernel(IndivData dd, IndivWork w, int nmax, int M,
                                                          const double* __restrict__ theta0,
                                                          double* __restrict__ theta_out, int maxit,
                                                          int* __restrict__ nfev, int* __restrict__ niter,
@@ -309,28 +309,28 @@ __global__ void __launch_bounds__(kT) indiv_mstep_kernel(IndivData dd, IndivWork
     }
     cur = (role == 2) ? -1 : 0;
   }
-  __syncthreads();
+  tsync<TT>();
   if (cur < 0) return;
   EvalSm s = eval_carve(sm, nmax);
   int bad = 0;
   for (;;) {
-    __syncthreads();
+    tsync<TT>();
     if (threadIdx.x == 0) cur = atomicAdd(ctl, 1);
-    __syncthreads();
+    tsync<TT>();
     const int i = cur;
     if (i >= M) break;
     const int o0 = dd.off[i], n = dd.off[i + 1] - o0;
-    eval_load(s, n, dd.t + o0, dd.y + o0, w.c1 + o0, w.c2 + dd.woff[i]);
+    eval_load<TT>(s, n, dd.t + o0, dd.y + o0, w.c1 + o0, w.c2 + dd.woff[i]);
     if (threadIdx.x == 0) {
       lb_init(opt, 3, theta0 + 3 * (size_t)i, maxit);
       st = LB_EVAL;
     }
-    __syncthreads();
+    tsync<TT>();
     while (true) {
       const double a = opt.x[0], b = opt.x[1], c = opt.x[2];
-      indiv_eval_v1<E>(s, n, a, b, c, true, out, &bad);
+      indiv_eval_v1<E, TT>(s, n, a, b, c, true, out, &bad);
       if (threadIdx.x == 0) st = lb_advance(opt, out[0], out + 1);
-      __syncthreads();
+      tsync<TT>();
       if (st != LB_EVAL) break;
     }
     if (threadIdx.x == 0) {
@@ -386,21 +386,53 @@ static cudaError_t set_smem_t(K fn, size_t bytes) {
   return cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
 
+// Threads per individual: 64 while the lower block triangle has at most 64 blocks (n <= 41), otherwise 128
+// (measured: n = 30 -> 3.6 ms per 1e5 evaluations with 64 threads vs 4.0 with 128 and 5.5 with 32; n = 50 -> 5.4 ms per
+// M-step with 128 vs 8.1 with 64). MCB_EVAL_THREADS=32|64|128 overrides (experiments).
+static void eval_shape(int nmax, int* TT, int* E) {
+  const int nblk = eval_num_blocks(nmax);
+  int tt = (nblk <= 64) ? 64 : 128;
+  static const char* ov = getenv("MCB_EVAL_THREADS");
+  if (ov) tt = atoi(ov);
+  if (tt != 32 && tt != 64 && tt != 128) tt = 128;
+  while (tt < 128 && (nblk + tt - 1) / tt > 4) tt *= 2;
+  *TT = tt;
+  *E = (nblk + tt - 1) / tt;
+}
+
+#define MCB_DISPATCH_EVAL(MACRO)                       \
+  do {                                                 \
+    if (TT == 32) {                                    \
+      if (E <= 1) MACRO(1, 32);                        \
+      else if (E == 2) MACRO(2, 32);                   \
+      else if (E <= 4) MACRO(4, 32);                   \
+      else return cudaErrorInvalidValue;               \
+    } else if (TT == 64) {                             \
+      if (E <= 1) MACRO(1, 64);                        \
+      else if (E == 2) MACRO(2, 64);                   \
+      else if (E <= 4) MACRO(4, 64);                   \
+      else return cudaErrorInvalidValue;               \
+    } else {                                           \
+      if (E <= 1) MACRO(1, 128);                       \
+      else if (E == 2) MACRO(2, 128);                  \
+      else if (E <= 4) MACRO(4, 128);                  \
+      else return cudaErrorInvalidValue;               \
+    }                                                  \
+  } while (0)
+
 cudaError_t launch_indiv_eval(cudaStream_t s, const IndivData& dd, int M, int nmax, const IndivWork& w,
                               const double* theta, int theta_stride, int want_grad, double* f, double* g,
                               double* sum4, int* info) {
   const size_t sm = eval_smem_bytes(nmax);
-  const int E = eval_blocks_per_thread(nmax);
+  int TT, E;
+  eval_shape(nmax, &TT, &E);
   cudaError_t e;
-#define MCB_LAUNCH_EVAL(EE)                                                                                   \
-  do {                                                                                                        \
-    if ((e = set_smem_t(indiv_eval_kernel<EE>, sm)) != cudaSuccess) return e;                                 \
-    indiv_eval_kernel<EE><<<M, kT, sm, s>>>(dd, w, nmax, theta, theta_stride, want_grad, f, g, sum4, info);   \
+#define MCB_LAUNCH_EVAL(EE, T_)                                                                                  \
+  do {                                                                                                           \
+    if ((e = set_smem_t(indiv_eval_kernel<EE, T_>, sm)) != cudaSuccess) return e;                                \
+    indiv_eval_kernel<EE, T_><<<M, T_, sm, s>>>(dd, w, nmax, theta, theta_stride, want_grad, f, g, sum4, info);  \
   } while (0)
-  if (E <= 1) MCB_LAUNCH_EVAL(1);
-  else if (E == 2) MCB_LAUNCH_EVAL(2);
-  else if (E <= 4) MCB_LAUNCH_EVAL(4);
-  else return cudaErrorInvalidValue;
+  MCB_DISPATCH_EVAL(MCB_LAUNCH_EVAL);
 #undef MCB_LAUNCH_EVAL
   return cudaGetLastError();
 }
@@ -409,27 +441,25 @@ cudaError_t launch_indiv_mstep(cudaStream_t s, const IndivData& dd, int M, int n
                                const double* theta0, double* theta_out, int maxit, int* nfev, int* niter,
                                int* status, int* ctl, int reserve_sms) {
   const size_t sm = eval_smem_bytes(nmax);
-  const int E = eval_blocks_per_thread(nmax);
+  int TT, E;
+  eval_shape(nmax, &TT, &E);
   cudaError_t e;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   if ((e = cudaMemsetAsync(ctl, 0, sizeof(int) * (2 + 1024), s)) != cudaSuccess) return e;
-#define MCB_LAUNCH_MSTEP(EE)                                                                                  \
-  do {                                                                                                        \
-    if ((e = set_smem_t(indiv_mstep_kernel<EE>, sm)) != cudaSuccess) return e;                                \
-    int per_sm = 1;                                                                                           \
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, indiv_mstep_kernel<EE>, kT, sm);                   \
-    if (per_sm < 1) per_sm = 1;                                                                               \
-    int grid = per_sm * sms;                                                                                  \
-    if (grid > M && reserve_sms == 0) grid = M;                                                               \
-    indiv_mstep_kernel<EE><<<grid, kT, sm, s>>>(dd, w, nmax, M, theta0, theta_out, maxit, nfev, niter, status, \
-                                                ctl, reserve_sms);                                            \
+#define MCB_LAUNCH_MSTEP(EE, T_)                                                                                  \
+  do {                                                                                                            \
+    if ((e = set_smem_t(indiv_mstep_kernel<EE, T_>, sm)) != cudaSuccess) return e;                                \
+    int per_sm = 1;                                                                                               \
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, indiv_mstep_kernel<EE, T_>, T_, sm);                   \
+    if (per_sm < 1) per_sm = 1;                                                                                   \
+    int grid = per_sm * sms;                                                                                      \
+    if (grid > M && reserve_sms == 0) grid = M;                                                                   \
+    indiv_mstep_kernel<EE, T_><<<grid, T_, sm, s>>>(dd, w, nmax, M, theta0, theta_out, maxit, nfev, niter, status, \
+                                                    ctl, reserve_sms);                                            \
   } while (0)
-  if (E <= 1) MCB_LAUNCH_MSTEP(1);
-  else if (E == 2) MCB_LAUNCH_MSTEP(2);
-  else if (E <= 4) MCB_LAUNCH_MSTEP(4);
-  else return cudaErrorInvalidValue;
+  MCB_DISPATCH_EVAL(MCB_LAUNCH_MSTEP);
 #undef MCB_LAUNCH_MSTEP
   return cudaGetLastError();
 }

@@ -19,7 +19,14 @@
 
 namespace mcb {
 
-constexpr int kT = 128;  // threads per CTA = per individual
+constexpr int kT = 128;  // threads per CTA of the E-step kernels (indiv.cu)
+
+// barrier over the TT threads that share one individual: a single warp needs no CTA barrier
+template <int TT>
+__device__ __forceinline__ void tsync() {
+  if (TT == 32) __syncwarp();
+  else __syncthreads();
+}
 
 __device__ __forceinline__ void dmma884_i(double& c0, double& c1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
@@ -65,54 +72,62 @@ __device__ __forceinline__ EvalSm eval_carve(double* sm, int nmax) {
   return s;
 }
 
-// number of 4 x 4 blocks per thread needed for n observations
-inline int eval_blocks_per_thread(int nmax) {
+// number of 4 x 4 blocks of the lower block triangle for n observations (+ 2 border rows)
+inline int eval_num_blocks(int nmax) {
   const int nbk = eval_ntot4(nmax) / 4;
-  const int nblk = nbk * (nbk + 1) / 2;
-  return (nblk + kT - 1) / kT;
+  return nbk * (nbk + 1) / 2;
 }
 
-template <int NV>
+template <int NV, int TT>
 __device__ __forceinline__ void cta_sum_v(double (&v)[NV], double* red) {
+  constexpr int NW = TT / 32;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
   for (int q = 0; q < NV; ++q) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v[q] += __shfl_xor_sync(0xffffffffu, v[q], o);
   }
+  if (NW == 1) return;
   __syncthreads();
   if (lane == 0) {
 #pragma unroll
-    for (int q = 0; q < NV; ++q) red[q * 4 + warp] = v[q];
+    for (int q = 0; q < NV; ++q) red[q * NW + warp] = v[q];
   }
   __syncthreads();
 #pragma unroll
-  for (int q = 0; q < NV; ++q) v[q] = red[q * 4] + red[q * 4 + 1] + red[q * 4 + 2] + red[q * 4 + 3];
+  for (int q = 0; q < NV; ++q) {
+    double t = 0.0;
+#pragma unroll
+    for (int w2 = 0; w2 < NW; ++w2) t += red[q * NW + w2];
+    v[q] = t;
+  }
 }
 
 // One-time per individual: zero the matrix buffers, load t / y / c1 and S = corr2 (n x n, row-major in global).
+template <int TT>
 __device__ __forceinline__ void eval_load(const EvalSm& s, int n, const double* __restrict__ tg,
                                           const double* __restrict__ yg, const double* __restrict__ c1g,
                                           const double* __restrict__ c2g) {
   const size_t mat = (size_t)s.np8 * s.ldm;
-  for (size_t e = threadIdx.x; e < 4 * mat; e += kT) s.W[e] = 0.0;
-  for (int a = threadIdx.x; a < n; a += kT) {
+  for (size_t e = threadIdx.x; e < 4 * mat; e += TT) s.W[e] = 0.0;
+  for (int a = threadIdx.x; a < n; a += TT) {
     s.t[a] = tg[a];
     s.y[a] = yg[a];
     s.c1[a] = c1g[a];
   }
-  __syncthreads();
-  for (int e = threadIdx.x; e < n * n; e += kT) {
+  tsync<TT>();
+  for (int e = threadIdx.x; e < n * n; e += TT) {
     const int a = e / n, b = e - a * n;
     s.S[a * s.ldm + b] = c2g[e];
   }
-  __syncthreads();
+  tsync<TT>();
 }
 
 // out[0] = f, out[1..3] = g (shared memory, written by thread 0). All 128 threads must call.
-template <int E>
+template <int E, int TT>
 __device__ void indiv_eval_v1(const EvalSm& s, int n, double th1, double th2, double sg, bool want_grad,
                               double* out, int* bad) {
+  constexpr int NW = TT / 32;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int ntot = n + 2;
   const int nbk = (ntot + 3) >> 2;
@@ -126,7 +141,7 @@ __device__ void indiv_eval_v1(const EvalSm& s, int n, double th1, double th2, do
   double blk[E][4][4], k0[E][4][4];
 #pragma unroll
   for (int e = 0; e < E; ++e) {
-    const int q = tid + kT * e;
+    const int q = tid + TT * e;
     if (q < nblk) {
       int I = (int)((sqrt(8.0 * q + 1.0) - 1.0) * 0.5);
       while ((I + 1) * (I + 2) / 2 <= q) ++I;
@@ -207,9 +222,9 @@ __device__ void indiv_eval_v1(const EvalSm& s, int n, double th1, double th2, do
     }
   };
 
-  __syncthreads();  // Kd / previous call's readers
+  tsync<TT>();  // Kd / previous call's readers
   publish(0, 0, s.col[0]);
-  __syncthreads();
+  tsync<TT>();
   const int npb = (n + 3) >> 2;  // pivot blocks
   for (int kb = 0; kb < npb; ++kb) {
 #pragma unroll
@@ -241,7 +256,7 @@ __device__ void indiv_eval_v1(const EvalSm& s, int n, double th1, double th2, do
         }
       }
       if (k + 1 < n) publish(kk == 3 ? kb + 1 : kb, (kk + 1) & 3, s.col[(k + 1) & 1]);
-      __syncthreads();
+      tsync<TT>();
     }
   }
 
@@ -275,9 +290,9 @@ __device__ void indiv_eval_v1(const EvalSm& s, int n, double th1, double th2, do
       }
     }
   }
-  __syncthreads();
-  for (int a = tid; a < n; a += kT) uv[a] = pv[a] - 2.0 * s.X[a];
-  __syncthreads();
+  tsync<TT>();
+  for (int a = tid; a < n; a += TT) uv[a] = pv[a] - 2.0 * s.X[a];
+  tsync<TT>();
   double v13[13];
 #pragma unroll
   for (int q = 0; q < 13; ++q) v13[q] = 0.0;
@@ -314,7 +329,7 @@ __device__ void indiv_eval_v1(const EvalSm& s, int n, double th1, double th2, do
       }
     }
   }
-  for (int k = tid; k < n; k += kT) {
+  for (int k = tid; k < n; k += TT) {
     const double d = s.piv[k];
     v13[7] += log(d);
     if (!(d > 0.0)) *bad = 1;
@@ -327,7 +342,7 @@ __device__ void indiv_eval_v1(const EvalSm& s, int n, double th1, double th2, do
     const int gr = lane >> 2, gc = lane & 3;
     {
       const int ncu = (nt + 3) >> 2;             // column chunks of <= 4 tiles
-      for (int u = warp; u < nt * ncu; u += 4) {
+      for (int u = warp; u < nt * ncu; u += NW) {
         const int ti = u / ncu, cj = (u - ti * ncu) * 4;
         double acc[4][2];
 #pragma unroll
@@ -353,13 +368,13 @@ __device__ void indiv_eval_v1(const EvalSm& s, int n, double th1, double th2, do
         }
       }
     }
-    __syncthreads();
+    tsync<TT>();
     // ---- D: H = X W on the lower tile triangle, reduced on the fly -----------------------------------
     {
       int u = 0;
       for (int ti = 0; ti < nt; ++ti) {
         for (int cj = 0; cj <= ti; cj += 4, ++u) {
-          if ((u & 3) != warp) continue;
+          if ((u % NW) != warp) continue;
           double acc[4][2];
 #pragma unroll
           for (int j = 0; j < 4; ++j) acc[j][0] = acc[j][1] = 0.0;
@@ -397,7 +412,7 @@ __device__ void indiv_eval_v1(const EvalSm& s, int n, double th1, double th2, do
       }
     }
   }
-  cta_sum_v<13>(v13, s.red);
+  cta_sum_v<13, TT>(v13, s.red);
   if (tid == 0) {
     const double yWy = corner[0], yWc = corner[1];
     out[0] = 0.5 * ((double)n * kLog2Pi + v13[7] + yWy) - yWc + 0.5 * v13[0];
@@ -407,7 +422,7 @@ __device__ void indiv_eval_v1(const EvalSm& s, int n, double th1, double th2, do
       out[3] = -sg * (v13[6] + v13[8] - v13[3]);
     }
   }
-  __syncthreads();
+  tsync<TT>();
 }
 
 }  // namespace mcb
