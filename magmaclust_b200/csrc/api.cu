@@ -343,15 +343,35 @@ static int e_step_impl(mcb_handle* h) {
     ++h->launches;
     MCB_TRY(dbg_stage(h, "e_step: solve(Psi_i)"));
   }
+  // Small grids: all-reduce A_k, w_k and replicate the K solves on every rank (latency bound, cheaper than a
+  // second exchange). Large grids (N > 768): cluster k is OWNED by rank k % nranks: its A_k is reduced onto the
+  // owner, inverted there only, and C_k / log|A_k| are broadcast back (one cluster per GPU at K = nranks).
+  const bool owned = h->nranks > 1 && !spd_inverse_slab_ok(N, ld);
   if (h->nranks > 1) {
     PhaseScope ps(h, PH_COMM);
-    MCB_TRY(comm_allreduce_sum(h, h->cov.p, (size_t)K * sN));
+    if (owned) MCB_TRY(comm_reduce_to_owners(h, h->cov.p, (size_t)sN, sN, K));
+    else MCB_TRY(comm_allreduce_sum(h, h->cov.p, (size_t)K * sN));
     MCB_TRY(comm_allreduce_sum(h, h->wk.p, (size_t)K * ld));
   }
   {
     PhaseScope ps(h, PH_DENSE);
     // C_k = A_k^-1 (CF.R:612), m_k = C_k w_k (CF.R:620)
-    H_CUDA(spd_inverse(h->st, h->cov.p, N, ld, sN, K, h->logdetA.p, h->info.p, h->ws, &h->launches));
+    if (owned) {
+      H_CUDA(cudaMemsetAsync(h->logdetA.p, 0, sizeof(double) * K, h->st));
+      for (int k = h->rank; k < K; k += h->nranks)
+        H_CUDA(spd_inverse(h->st, h->cov.p + (size_t)k * sN, N, ld, sN, 1, h->logdetA.p + k, h->info.p, h->ws,
+                           &h->launches));
+    } else {
+      H_CUDA(spd_inverse(h->st, h->cov.p, N, ld, sN, K, h->logdetA.p, h->info.p, h->ws, &h->launches));
+    }
+  }
+  if (owned) {
+    PhaseScope ps(h, PH_COMM);
+    MCB_TRY(comm_bcast_from_owners(h, h->cov.p, (size_t)sN, sN, K));
+    MCB_TRY(comm_bcast_from_owners(h, h->logdetA.p, 1, 1, K));
+  }
+  {
+    PhaseScope ps(h, PH_DENSE);
     symv(h->st, N, h->cov.p, ld, sN, h->wk.p, ld, h->mean.p, ld, K, &h->launches);
     vec_sub(h->st, K * ld, h->mean.p, h->mk.p, h->rvec.p, &h->launches);
   }

@@ -19,6 +19,10 @@ struct NcclApi {
   ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
   ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
   ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Reduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
 };
@@ -40,9 +44,14 @@ static bool nccl_load(std::string* why) {
   g_nccl.GetUniqueId = (decltype(g_nccl.GetUniqueId))dlsym(lib, "ncclGetUniqueId");
   g_nccl.CommInitRank = (decltype(g_nccl.CommInitRank))dlsym(lib, "ncclCommInitRank");
   g_nccl.AllReduce = (decltype(g_nccl.AllReduce))dlsym(lib, "ncclAllReduce");
+  g_nccl.Reduce = (decltype(g_nccl.Reduce))dlsym(lib, "ncclReduce");
+  g_nccl.Broadcast = (decltype(g_nccl.Broadcast))dlsym(lib, "ncclBroadcast");
+  g_nccl.GroupStart = (decltype(g_nccl.GroupStart))dlsym(lib, "ncclGroupStart");
+  g_nccl.GroupEnd = (decltype(g_nccl.GroupEnd))dlsym(lib, "ncclGroupEnd");
   g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))dlsym(lib, "ncclCommDestroy");
   g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))dlsym(lib, "ncclGetErrorString");
-  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy) {
+  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy || !g_nccl.Reduce ||
+      !g_nccl.Broadcast || !g_nccl.GroupStart || !g_nccl.GroupEnd) {
     if (why) *why = "libnccl is missing required symbols";
     return false;
   }
@@ -55,6 +64,34 @@ int comm_allreduce_sum(mcb_handle* h, double* buf, size_t count) {
   ncclResult_t r = g_nccl.AllReduce(buf, buf, count, ncclDouble, ncclSum, (ncclComm_t)h->comm, h->st);
   if (r != ncclSuccess) {
     h->err = std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error");
+    return MCB_ENCCL;
+  }
+  return MCB_OK;
+}
+
+// Z blocks of `count` doubles at buf + z * stride: block z is summed onto rank owner(z) = z % nranks (in place)
+int comm_reduce_to_owners(mcb_handle* h, double* buf, size_t count, long long stride, int Z) {
+  if (h->nranks <= 1) return MCB_OK;
+  ncclResult_t r = g_nccl.GroupStart();
+  for (int z = 0; z < Z && r == ncclSuccess; ++z)
+    r = g_nccl.Reduce(buf + z * stride, buf + z * stride, count, ncclDouble, ncclSum, z % h->nranks, (ncclComm_t)h->comm, h->st);
+  if (r == ncclSuccess) r = g_nccl.GroupEnd();
+  if (r != ncclSuccess) {
+    h->err = std::string("ncclReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error");
+    return MCB_ENCCL;
+  }
+  return MCB_OK;
+}
+
+// block z is broadcast from rank owner(z) = z % nranks to every rank (in place)
+int comm_bcast_from_owners(mcb_handle* h, double* buf, size_t count, long long stride, int Z) {
+  if (h->nranks <= 1) return MCB_OK;
+  ncclResult_t r = g_nccl.GroupStart();
+  for (int z = 0; z < Z && r == ncclSuccess; ++z)
+    r = g_nccl.Broadcast(buf + z * stride, buf + z * stride, count, ncclDouble, z % h->nranks, (ncclComm_t)h->comm, h->st);
+  if (r == ncclSuccess) r = g_nccl.GroupEnd();
+  if (r != ncclSuccess) {
+    h->err = std::string("ncclBroadcast: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error");
     return MCB_ENCCL;
   }
   return MCB_OK;

@@ -89,5 +89,8 @@ enum Phase { PH_INDIV = 0, PH_DENSE = 1, PH_TAU = 2, PH_MSTEP_I = 3, PH_MSTEP_K 
 
 // NCCL shim (comm.cu): no-ops when the handle is single-rank
 int comm_allreduce_sum(mcb_handle* h, double* buf, size_t count);
+// cluster ownership for large grids: block z lives on rank z % nranks
+int comm_reduce_to_owners(mcb_handle* h, double* buf, size_t count, long long stride, int Z);
+int comm_bcast_from_owners(mcb_handle* h, double* buf, size_t count, long long stride, int Z);
 void comm_destroy(mcb_handle* h);
 }  // namespace mcb
