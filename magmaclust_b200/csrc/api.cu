@@ -134,6 +134,7 @@ extern "C" void mcb_destroy(mcb_handle* h) {
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev_join) cudaEventDestroy(h->ev_join);
   h->mstep_ctl.release();
+  h->order_i.release();
   if (h->st) cudaStreamDestroy(h->st);
   delete h;
 }
@@ -184,6 +185,7 @@ extern "C" int mcb_set_data(mcb_handle* h, int M, int N, long long P, const int*
   H_CUDA(h->theta_i.ensure(3 * (size_t)M)); H_CUDA(h->theta_i_new.ensure(3 * (size_t)M));
   H_CUDA(cudaStreamSynchronize(h->st));  // host vectors go out of scope
   h->has_data = true; h->has_state = false; h->has_post = false; h->has_cand = false; h->has_pred = false;
+  h->nfev_valid = false;
   return MCB_OK;
 }
 
@@ -789,6 +791,18 @@ static int m_step_impl(mcb_handle* h, int common_hp_k, int common_hp_i, int* sta
   // replaces the third entry of theta_k afterwards, CF.R:666-668): run them concurrently.
   static const bool no_overlap = getenv("MCB_NO_OVERLAP") != nullptr;
   const bool overlap = !no_overlap && !common_hp_i && common_hp_k && spd_inverse_slab_ok(h->N, h->ld);
+  // Work-queue order of the per-individual optimisations: longest first, predicted by the evaluation counts of
+  // the previous M-step on the same individuals (shortens the tail of the persistent kernel).
+  const int* order = nullptr;
+  if (!common_hp_i && h->nfev_valid && M <= 65536) {
+    std::vector<int> cnt(M), ord(M);
+    H_CUDA(sync_copy(h, cnt.data(), h->nfev_i.p, sizeof(int) * M, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < M; ++i) ord[i] = i;
+    std::stable_sort(ord.begin(), ord.end(), [&](int x, int y) { return cnt[x] > cnt[y]; });
+    H_CUDA(h->order_i.ensure(M));
+    H_CUDA(sync_copy(h, h->order_i.p, ord.data(), sizeof(int) * M, cudaMemcpyHostToDevice));
+    order = h->order_i.p;
+  }
   // --- individuals (CF.R:645-660)
   {
     PhaseScope ps(h, PH_MSTEP_I);
@@ -822,7 +836,8 @@ static int m_step_impl(mcb_handle* h, int common_hp_k, int common_hp_i, int* sta
       H_CUDA(cudaStreamSynchronize(h->st));
     } else if (!overlap) {
       H_CUDA(launch_indiv_mstep(h->st, h->idata(), M, h->nmax, h->iwork(), h->theta_i.p, h->theta_i_new.p, 100,
-                                h->nfev_i.p, h->niter_i.p, h->status_i.p, h->mstep_ctl.p, 0));
+                                h->nfev_i.p, h->niter_i.p, h->status_i.p, h->mstep_ctl.p, 0, order));
+      h->nfev_valid = true;
       ++h->launches;
     }
   }
@@ -834,7 +849,8 @@ static int m_step_impl(mcb_handle* h, int common_hp_k, int common_hp_i, int* sta
       PhaseScope ps(h, PH_MSTEP_I, h->st2);
       const int nblk = (h->N + kNB - 1) / kNB;
       H_CUDA(launch_indiv_mstep(h->st2, h->idata(), M, h->nmax, h->iwork(), h->theta_i.p, h->theta_i_new.p, 100,
-                                h->nfev_i.p, h->niter_i.p, h->status_i.p, h->mstep_ctl.p, nblk));
+                                h->nfev_i.p, h->niter_i.p, h->status_i.p, h->mstep_ctl.p, nblk, order));
+      h->nfev_valid = true;
       ++h->launches;
     }
     H_CUDA(cudaEventRecord(h->ev_join, h->st2));

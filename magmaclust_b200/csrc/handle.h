@@ -36,7 +36,8 @@ struct mcb_handle {
 
   // ---- per-individual work ----
   mcb::DevBuf<double> Winv, pvec, yWy, logdet_i, c1, c2, Fi, fi_tmp, gi_tmp;
-  mcb::DevBuf<int> nfev_i, niter_i, status_i;
+  mcb::DevBuf<int> nfev_i, niter_i, status_i, order_i;
+  bool nfev_valid = false;   // nfev_i holds the counts of a previous per-individual M-step on this data set
 
   // ---- dense side ----
   int G = 0;                       // distinct theta_k at the last E-step

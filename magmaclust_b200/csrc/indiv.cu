@@ -253,7 +253,7 @@ __global__ void __launch_bounds__(TT) indiv_eval_kernel(IndivData dd, IndivWork 
                                                         int want_grad, double* __restrict__ f,
                                                         double* __restrict__ g, double* __restrict__ sum4,
                                                         int* __restrict__ info) {
-  extern __shared__ double sm[];
+  extern __shared__ __align__(16) double sm[];
   __shared__ double out[4];
   const int i = blockIdx.x;
   const int o0 = dd.off[i], n = dd.off[i + 1] - o0;
@@ -286,8 +286,8 @@ __global__ void __launch_bounds__(TT) indiv_mstep_kernel(IndivData dd, IndivWork
                                                          double* __restrict__ theta_out, int maxit,
                                                          int* __restrict__ nfev, int* __restrict__ niter,
                                                          int* __restrict__ status, int* __restrict__ ctl,
-                                                         int reserve) {
-  extern __shared__ double sm[];
+                                                         int reserve, const int* __restrict__ order) {
+  extern __shared__ __align__(16) double sm[];
   __shared__ double out[4];
   __shared__ Lbfgs opt;
   __shared__ int st, cur;
@@ -317,8 +317,8 @@ __global__ void __launch_bounds__(TT) indiv_mstep_kernel(IndivData dd, IndivWork
     tsync<TT>();
     if (threadIdx.x == 0) cur = atomicAdd(ctl, 1);
     tsync<TT>();
-    const int i = cur;
-    if (i >= M) break;
+    if (cur >= M) break;
+    const int i = order ? order[cur] : cur;  // longest-expected-first order when the previous M-step's counts exist
     const int o0 = dd.off[i], n = dd.off[i + 1] - o0;
     eval_load<TT>(s, n, dd.t + o0, dd.y + o0, w.c1 + o0, w.c2 + dd.woff[i]);
     if (threadIdx.x == 0) {
@@ -439,7 +439,7 @@ cudaError_t launch_indiv_eval(cudaStream_t s, const IndivData& dd, int M, int nm
 
 cudaError_t launch_indiv_mstep(cudaStream_t s, const IndivData& dd, int M, int nmax, const IndivWork& w,
                                const double* theta0, double* theta_out, int maxit, int* nfev, int* niter,
-                               int* status, int* ctl, int reserve_sms) {
+                               int* status, int* ctl, int reserve_sms, const int* order) {
   const size_t sm = eval_smem_bytes(nmax);
   int TT, E;
   eval_shape(nmax, &TT, &E);
@@ -457,7 +457,7 @@ cudaError_t launch_indiv_mstep(cudaStream_t s, const IndivData& dd, int M, int n
     int grid = per_sm * sms;                                                                                      \
     if (grid > M && reserve_sms == 0) grid = M;                                                                   \
     indiv_mstep_kernel<EE, T_><<<grid, T_, sm, s>>>(dd, w, nmax, M, theta0, theta_out, maxit, nfev, niter, status, \
-                                                    ctl, reserve_sms);                                            \
+                                                    ctl, reserve_sms, order);                                     \
   } while (0)
   MCB_DISPATCH_EVAL(MCB_LAUNCH_MSTEP);
 #undef MCB_LAUNCH_MSTEP

@@ -39,6 +39,7 @@ cudaError_t launch_indiv_eval(cudaStream_t s, const IndivData& dd, int M, int nm
                               double* sum4, int* info);
 cudaError_t launch_indiv_mstep(cudaStream_t s, const IndivData& dd, int M, int nmax, const IndivWork& w,
                                const double* theta0, double* theta_out, int maxit, int* nfev, int* niter,
-                               int* status, int* ctl /* [2 + 1024] ints */, int reserve_sms);
+                               int* status, int* ctl /* [2 + 1024] ints */, int reserve_sms,
+                               const int* order /* [M] processing order or NULL */);
 
 }  // namespace mcb

@@ -193,14 +193,17 @@ __device__ void indiv_eval_v1(const EvalSm& s, int n, double th1, double th2, do
 #pragma unroll
     for (int e = 0; e < E; ++e) {
       if (bJ[e] == kb) {
+        double v[4];
 #pragma unroll
         for (int a = 0; a < 4; ++a) {
-          double v = blk[e][a][0];
-          if (kk == 1) v = blk[e][a][1];
-          if (kk == 2) v = blk[e][a][2];
-          if (kk == 3) v = blk[e][a][3];
-          buf[4 * bI[e] + a] = v;
+          v[a] = blk[e][a][0];
+          if (kk == 1) v[a] = blk[e][a][1];
+          if (kk == 2) v[a] = blk[e][a][2];
+          if (kk == 3) v[a] = blk[e][a][3];
         }
+        // two 16-byte stores instead of four 8-byte ones (4 I is a multiple of 4 doubles)
+        *reinterpret_cast<double2*>(buf + 4 * bI[e]) = make_double2(v[0], v[1]);
+        *reinterpret_cast<double2*>(buf + 4 * bI[e] + 2) = make_double2(v[2], v[3]);
         if (bI[e] == kb) {
           double d = blk[e][0][0];
           if (kk == 1) d = blk[e][1][1];
@@ -210,14 +213,16 @@ __device__ void indiv_eval_v1(const EvalSm& s, int n, double th1, double th2, do
           s.piv[4 * kb + kk] = d;
         }
       } else if (bI[e] == kb) {
+        double v[4];
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
-          double v = blk[e][0][b];
-          if (kk == 1) v = blk[e][1][b];
-          if (kk == 2) v = blk[e][2][b];
-          if (kk == 3) v = blk[e][3][b];
-          buf[4 * bJ[e] + b] = v;
+          v[b] = blk[e][0][b];
+          if (kk == 1) v[b] = blk[e][1][b];
+          if (kk == 2) v[b] = blk[e][2][b];
+          if (kk == 3) v[b] = blk[e][3][b];
         }
+        *reinterpret_cast<double2*>(buf + 4 * bJ[e]) = make_double2(v[0], v[1]);
+        *reinterpret_cast<double2*>(buf + 4 * bJ[e] + 2) = make_double2(v[2], v[3]);
       }
     }
   };
@@ -237,10 +242,14 @@ __device__ void indiv_eval_v1(const EvalSm& s, int n, double th1, double th2, do
       for (int e = 0; e < E; ++e) {
         if (bI[e] < 0) continue;
         double ci[4], tj[4];
-#pragma unroll
-        for (int a = 0; a < 4; ++a) ci[a] = buf[4 * bI[e] + a];
-#pragma unroll
-        for (int b = 0; b < 4; ++b) tj[b] = buf[4 * bJ[e] + b] * inv_d;
+        {
+          const double2 c01 = *reinterpret_cast<const double2*>(buf + 4 * bI[e]);
+          const double2 c23 = *reinterpret_cast<const double2*>(buf + 4 * bI[e] + 2);
+          const double2 t01 = *reinterpret_cast<const double2*>(buf + 4 * bJ[e]);
+          const double2 t23 = *reinterpret_cast<const double2*>(buf + 4 * bJ[e] + 2);
+          ci[0] = c01.x; ci[1] = c01.y; ci[2] = c23.x; ci[3] = c23.y;
+          tj[0] = t01.x * inv_d; tj[1] = t01.y * inv_d; tj[2] = t23.x * inv_d; tj[3] = t23.y * inv_d;
+        }
 #pragma unroll
         for (int a = 0; a < 4; ++a)
 #pragma unroll
