@@ -1,0 +1,136 @@
+"""GPU edge cases: tiny and large individuals (all template instantiations of the evaluation kernel), K = 1, grids
+smaller than one pivot block, error paths, batched prediction, full_algo_clust end to end."""
+import numpy as np
+import pytest
+
+from oracle import magma_oracle as O
+from helpers import RTOL_LL, RTOL_POST, assert_param_close, rel_err, small_problem
+
+pytestmark = pytest.mark.gpu
+
+
+def _check_eval(session, db, hp, tau, m_k, seed=0):
+    from magmaclust_b200 import magma
+    ref = O.e_step_VEM(db, m_k, O.kernel_mu, O.kernel, hp, tau)
+    got = magma.e_step_VEM(db, m_k, magma.kernel_mu, magma.kernel, hp, tau, session=session)
+    assert_param_close(got, ref, list(m_k.keys()))
+    per = O.split_db(db)
+    rng = np.random.default_rng(seed)
+    th = np.array([np.asarray(hp["theta_i"][i]) + 0.1 * rng.standard_normal(3) for i in per])
+    f, g = session.eng.eval_indiv(th)
+    for r, (i, d) in enumerate(per.items()):
+        fr = O.logL_clust_multi_GP(th[r], d, ref, O.kernel)
+        gr = O.gr_clust_multi_GP(th[r], d, ref, O.kernel)
+        assert abs(f[r] - fr) <= RTOL_LL * max(1.0, abs(fr)), (i, f[r], fr)
+        assert np.max(np.abs(g[r] - gr)) <= RTOL_LL * max(1.0, np.max(np.abs(gr))), (i, g[r], gr)
+    return ref, got
+
+
+@pytest.mark.parametrize("nrange,n_grid", [((1, 3), 12), ((38, 44), 90), ((60, 75), 120), ((78, 80), 120)])
+def test_individual_sizes_cover_all_kernel_shapes(session, nrange, n_grid):
+    """n_i from 1 (scalar branch, CF.R:167-170) to 80 (the shared-memory limit): 64-thread and 128-thread shapes with
+    1, 2 and 4 register blocks per thread"""
+    db, hp, tau, m_k = small_problem(M=6, K=2, n=nrange, n_grid=n_grid, seed=11)
+    _check_eval(session, db, hp, tau, m_k)
+
+
+def test_more_than_80_observations_is_rejected(session):
+    from magmaclust_b200._lib import McbError
+    from magmaclust_b200 import magma
+    db, hp, tau, m_k = small_problem(M=3, K=2, n=(81, 81), n_grid=100, seed=1, ragged=False)
+    with pytest.raises(McbError):
+        magma.e_step_VEM(db, m_k, magma.kernel_mu, magma.kernel, hp, tau, session=session)
+
+
+def test_single_cluster_and_tiny_grid(session):
+    db, hp, tau, m_k = small_problem(M=5, K=1, n=(3, 6), n_grid=9, seed=2)
+    ref, got = _check_eval(session, db, hp, tau, m_k)
+    A = O.tau_to_array(got["tau_i_k"])
+    assert np.allclose(A, 1.0)
+
+
+def test_grid_sizes_around_pivot_block_boundaries(session):
+    from magmaclust_b200 import magma
+    for n_grid in (31, 32, 33, 64, 65):
+        db, hp, tau, m_k = small_problem(M=14, K=2, n=(5, 9), n_grid=n_grid, seed=n_grid)
+        ref = O.e_step_VEM(db, m_k, O.kernel_mu, O.kernel, hp, tau)
+        got = magma.e_step_VEM(db, m_k, magma.kernel_mu, magma.kernel, hp, tau, session=session)
+        assert_param_close(got, ref, list(m_k.keys()))
+
+
+def test_not_positive_definite_is_reported_not_hidden(session):
+    """the reference silently falls back to MASS::ginv (CF.R:142); the library reports MCB_ENOTPD"""
+    from magmaclust_b200._lib import McbError
+    from magmaclust_b200 import magma
+    db, hp, tau, m_k = small_problem(M=8, K=2, n=(6, 9), n_grid=60, seed=3)
+    hp["theta_k"] = {k: np.array([9.0, 6.0, 0.0]) for k in hp["theta_k"]}  # smooth kernel, zero jitter: singular
+    with pytest.raises(McbError) as ei:
+        magma.e_step_VEM(db, m_k, magma.kernel_mu, magma.kernel, hp, tau, session=session)
+    assert ei.value.code == 2
+    # the handle stays usable afterwards
+    db, hp, tau, m_k = small_problem(M=8, K=2, n=(6, 9), n_grid=60, seed=3)
+    ref = O.e_step_VEM(db, m_k, O.kernel_mu, O.kernel, hp, tau)
+    got = magma.e_step_VEM(db, m_k, magma.kernel_mu, magma.kernel, hp, tau, session=session)
+    assert_param_close(got, ref, list(m_k.keys()))
+
+
+def test_negative_noise_sd_is_not_clamped(session):
+    """theta[3] may be negative: only its square enters Psi, the gradient keeps the sign"""
+    db, hp, tau, m_k = small_problem(M=6, K=2, n=(5, 8), n_grid=30, seed=4)
+    hp["theta_i"] = {i: np.array([v[0], v[1], -abs(v[2])]) for i, v in hp["theta_i"].items()}
+    _check_eval(session, db, hp, tau, m_k)
+
+
+def test_batched_prediction_matches_per_individual_oracle(session):
+    from magmaclust_b200 import magma
+    db, hp, tau, m_k = small_problem(M=10, K=3, seed=12, common_hp_i=True)
+    names = list(m_k.keys())
+    ref_param = O.e_step_VEM(db, m_k, O.kernel_mu, O.kernel, hp, tau)
+    list_hp = {"hp": hp, "param": ref_param}
+    grid = np.unique(np.r_[db["Timestamp"], np.round(np.linspace(0.05, 9.95, 37), 3)])
+    mu_ref = O.posterior_mu_k(db, grid, m_k, O.kernel_mu, O.kernel, list_hp)
+    magma.posterior_mu_k(db, grid, m_k, magma.kernel_mu, magma.kernel, list_hp, session=session)
+    rng = np.random.default_rng(0)
+    B = 7
+    offs, idx, ys, news = [0], [], [], []
+    for b in range(B):
+        nb = int(rng.integers(1, 9))
+        sel = np.sort(rng.choice(grid.shape[0], nb, replace=False))
+        y = rng.standard_normal(nb)
+        idx += list(sel)
+        ys += list(y)
+        offs.append(offs[-1] + nb)
+        news.append({"ID": np.array([100 + b] * nb), "Timestamp": grid[sel], "Output": y})
+    theta_new = np.asarray(next(iter(hp["theta_i"].values())))
+    pred_idx = np.arange(0, grid.shape[0], 3)
+    pi_k = np.array([np.mean(list(tau[k].values())) for k in names])
+    tau_b, mean_b, var_b = session.eng.predict(offs, idx, ys, theta_new, pred_idx, pi_k)
+    for b in range(B):
+        t_ref = O.update_tau_star_k_EM(news[b], mu_ref["mean"], mu_ref["cov"], O.kernel, theta_new,
+                                       {k: pi_k[c] for c, k in enumerate(names)})
+        p_ref = O.pred_gp_clust(news[b], grid[pred_idx], mu_ref, O.kernel, {"theta_new": theta_new, "tau_k": t_ref})
+        for c, k in enumerate(names):
+            assert abs(tau_b[b, c] - t_ref[k]) < RTOL_LL
+            assert rel_err(mean_b[b, c], p_ref[k]["Mean"]) < RTOL_POST
+            assert np.max(np.abs(var_b[b, c] - p_ref[k]["Var"])) < 1e-8 * max(1.0, np.max(np.abs(p_ref[k]["Var"])))
+
+
+def test_full_algo_clust_end_to_end(session):
+    """MC.R:301-347 with list_hp = NULL: training, hyper-posterior on the prediction grid, tau*, prediction"""
+    from magmaclust_b200 import magma
+    db, hp, tau, m_k = small_problem(M=12, K=2, n=(8, 12), n_grid=40, seed=21, common_hp_i=True)
+    ids = list(O.split_db(db).keys())
+    names = list(m_k.keys())
+    A = O.tau_to_array(tau)
+    tau0 = {k: {i: 1.0 if A[r].argmax() == c else 0.0 for r, i in enumerate(ids)} for c, k in enumerate(names)}
+    ini = {"theta_k": np.array([1.0, 1.0, 0.2]), "theta_i": np.array([1.0, 1.0, 0.2])}
+    new_db = {"ID": np.array([99] * 4), "Timestamp": np.array([0.513, 3.077, 5.128, 8.205]), "Output": np.array([0.1, 0.8, -0.3, 0.5])}
+    targets = np.round(np.linspace(0.2, 9.8, 11), 3)
+    ref = O.full_algo_clust(db, new_db, targets, O.kernel, tau0, True, True, prior_mean=m_k, kern_0=O.kernel_mu, ini_hp=ini)
+    got = magma.full_algo_clust(db, new_db, targets, magma.kernel, tau0, True, True, prior_mean=m_k,
+                                kern_0=magma.kernel_mu, ini_hp=ini, session=session)
+    assert len(got["logL_iterations"]) == len(ref["logL_iterations"])
+    for k in names:
+        assert abs(got["Hyperparameters"]["new_i"]["tau_k"][k] - ref["Hyperparameters"]["new_i"]["tau_k"][k]) < 1e-3
+        assert np.allclose(got["Prediction"][k]["Mean"], ref["Prediction"][k]["Mean"], rtol=2e-3, atol=2e-3)
+        assert np.allclose(got["Prediction"][k]["Var"], ref["Prediction"][k]["Var"], rtol=5e-3, atol=1e-4)
