@@ -43,6 +43,7 @@ def parse():
     ap.add_argument("--no-flush", action="store_true", help="do not evict L2 between timed steps")
     ap.add_argument("--cpu-sample", type=int, default=48, help="individuals in the CPU baseline sample")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--individuals", type=int, default=0, help="override the individuals per GPU of the workload")
     return ap.parse_args()
 
 
@@ -91,9 +92,11 @@ class Clocks:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def workload_data(name, nranks):
+def workload_data(name, nranks, individuals=0):
     from magmaclust_b200 import synth
     c = dict(synth.CONFIGS[name])
+    if individuals:
+        c["M"] = individuals
     ds = synth.make_dataset(c["M"] * nranks, c["K"], c["n"], c["n_grid"], c["common_hp_i"], c["seed"])
     return ds, c
 
@@ -164,7 +167,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    ds, cfg = workload_data(args.workload, 1)
+    ds, cfg = workload_data(args.workload, 1, args.individuals)
     cores = os.cpu_count() or 1
     base = cpu_baseline(ds, cfg, args.cpu_sample, steps=args.steps, warmup=args.warmup)
     M = cfg["M"] * args.gpus
@@ -207,7 +210,7 @@ def run_ours(args):
     from magmaclust_b200 import synth
     from magmaclust_b200.engine import Engine
 
-    ds, cfg = workload_data(args.workload, world)
+    ds, cfg = workload_data(args.workload, world, args.individuals)
     sh = synth.shard(ds, rank, world)
     M, K, N = sh["M"], sh["K"], sh["N"]
     eng = Engine(local)

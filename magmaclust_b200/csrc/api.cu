@@ -826,7 +826,11 @@ static int m_step_impl(mcb_handle* h, int common_hp_k, int common_hp_i, int* sta
       int st = LB_EVAL;
       double out[4];
       while (st == LB_EVAL) {
-        MCB_TRY(eval_indiv_common(h, opt.x, true, out));
+        // a trial point where some Psi_i is not positive definite is an infinite objective for the line search
+        // (the reference's solve() would fail over to ginv and carry on, CF.R:142)
+        const int rc = eval_indiv_common(h, opt.x, true, out);
+        if (rc == MCB_ENOTPD) { out[0] = INFINITY; out[1] = out[2] = out[3] = 0.0; }
+        else if (rc != MCB_OK) return rc;
         st = lb_advance(opt, out[0], out + 1);
       }
       nfev_i = opt.nfev; nit_i = opt.iter;
@@ -870,7 +874,9 @@ static int m_step_impl(mcb_handle* h, int common_hp_k, int common_hp_i, int* sta
       int st = LB_EVAL;
       double f, g[3];
       while (st == LB_EVAL) {
-        MCB_TRY(eval_mean_groups(h, 1, opt.x, gm.data(), true, false, &f, g));
+        const int rc = eval_mean_groups(h, 1, opt.x, gm.data(), true, false, &f, g);
+        if (rc == MCB_ENOTPD) { f = INFINITY; g[0] = g[1] = g[2] = 0.0; }  // line search backs off (see above)
+        else if (rc != MCB_OK) return rc;
         st = lb_advance(opt, f, g);
       }
       nfev_k = opt.nfev; nit_k = opt.iter;
@@ -903,7 +909,14 @@ static int m_step_impl(mcb_handle* h, int common_hp_k, int common_hp_i, int* sta
             active.push_back(k);
           }
         if (active.empty()) break;
-        MCB_TRY(eval_mean_groups(h, (int)active.size(), th.data(), gm.data(), true, false, f.data(), g.data()));
+        const int rc = eval_mean_groups(h, (int)active.size(), th.data(), gm.data(), true, false, f.data(), g.data());
+        if (rc == MCB_ENOTPD) {
+          // the flag is shared by the batch: every active line search backs off this round
+          std::fill(f.begin(), f.end(), INFINITY);
+          std::fill(g.begin(), g.end(), 0.0);
+        } else if (rc != MCB_OK) {
+          return rc;
+        }
         for (size_t a = 0; a < active.size(); ++a) {
           const int k = active[a];
           st[k] = lb_advance(opt[k], f[a], g.data() + 3 * a);
@@ -986,8 +999,15 @@ extern "C" int mcb_vem_iteration(mcb_handle* h, int common_hp_k, int common_hp_i
   double e_old[2], e_new[2];
   MCB_TRY(elbo_impl(h, nullptr, nullptr, e_old));           // MC.R:51-53; also the second term of MC.R:71
   MCB_TRY(m_step_impl(h, common_hp_k, common_hp_i, nullptr));
-  MCB_TRY(elbo_impl(h, h->h_theta_k_new.data(), h->theta_i_new.p, e_new));  // MC.R:70
-  const double eps = (e_new[0] - e_old[0]) / fabs(e_new[0]);
+  {
+    // MC.R:70. If the candidate hp make a covariance numerically singular (e.g. pen_diag = mean_i theta_i[3] ~ 0,
+    // SURVEY Q12) the candidate is treated like the reference treats an M-step failure (MC.R:62-67): training
+    // stops and the last valid hp are kept.
+    const int rc = elbo_impl(h, h->h_theta_k_new.data(), h->theta_i_new.p, e_new);
+    if (rc == MCB_ENOTPD) { e_new[0] = -INFINITY; e_new[1] = -INFINITY; }
+    else if (rc != MCB_OK) return rc;
+  }
+  const double eps = std::isfinite(e_new[0]) ? (e_new[0] - e_old[0]) / fabs(e_new[0]) : -INFINITY;
   out[0] = e_old[1];
   out[1] = eps;
   if (eps < 1e-2) {
