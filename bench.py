@@ -41,7 +41,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C2", choices=["C1", "C2", "C3"])
     ap.add_argument("--no-flush", action="store_true", help="do not evict L2 between timed steps")
-    ap.add_argument("--cpu-sample", type=int, default=48, help="individuals in the CPU baseline sample")
+    ap.add_argument("--cpu-sample", type=int, default=200, help="individuals in the CPU baseline sample")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--individuals", type=int, default=0, help="override the individuals per GPU of the workload")
     return ap.parse_args()

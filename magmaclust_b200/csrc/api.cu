@@ -524,7 +524,7 @@ extern "C" int mcb_set_posterior(mcb_handle* h, const double* mean, const double
 // 510-537). use_resident: take K^-1 and log|K| from the last E-step instead of building them.
 // Stream work of one evaluation (no host synchronisation): reads theta / gmap from the pinned staging area,
 // leaves the reductions, log|K| and the not-PD flag in the pinned result area. Captured into a CUDA graph.
-static int eval_mean_enqueue(mcb_handle* h, int G, bool want_grad, bool use_resident) {
+static int eval_mean_enqueue(mcb_handle* h, int G, bool want_grad, bool use_resident, bool refresh_csum) {
   const int N = h->N, ld = h->ld, K = h->K;
   const long long sN = (long long)N * ld;
   double* stage = h->hbuf + 1024;
@@ -543,8 +543,9 @@ static int eval_mean_enqueue(mcb_handle* h, int G, bool want_grad, bool use_resi
     Kinv = h->eK.p;
     logdetK = h->elogdet.p;
   }
-  // sum of the hyper-posterior covariances of each group
-  sum_groups(h->st, N, ld, sN, h->cov.p, h->egmap.p, K, h->eCsum.p, G, &h->launches);
+  // sum of the hyper-posterior covariances of each group: theta independent, refreshed only when the hyper-posterior
+  // or the grouping changed since the last evaluation
+  if (refresh_csum) sum_groups(h->st, N, ld, sN, h->cov.p, h->egmap.p, K, h->eCsum.p, G, &h->launches);
   symv_mapped(h->st, N, ld, sN, Kinv, h->egmap.p, h->rvec.p, h->pz.p, K, &h->launches);
   double* redg = h->ered.p;          // [G][4]
   double* redz = redg + 4 * K;       // [K][4]
@@ -580,17 +581,21 @@ static int eval_mean_groups(mcb_handle* h, int G, const double* theta_h, const i
   memcpy(stage, theta_h, sizeof(double) * 3 * G);
   memcpy(stage_i, gmap_h, sizeof(int) * K);
   static const bool no_graph = getenv("MCB_NO_GRAPH") != nullptr;
+  const std::vector<int> gm(gmap_h, gmap_h + K);
+  const bool refresh_csum = !h->csum_valid || gm != h->csum_gmap;
+  h->csum_gmap = gm;
+  h->csum_valid = true;
   if (no_graph) {
-    MCB_TRY(eval_mean_enqueue(h, G, want_grad, use_resident));
+    MCB_TRY(eval_mean_enqueue(h, G, want_grad, use_resident, refresh_csum));
   } else {
-    const int key = ((G * 2 + (want_grad ? 1 : 0)) * 2 + (use_resident ? 1 : 0));
+    const int key = (((G * 2 + (want_grad ? 1 : 0)) * 2 + (use_resident ? 1 : 0)) * 2 + (refresh_csum ? 1 : 0));
     auto it = h->eval_graphs.find(key);
     if (it == h->eval_graphs.end()) {
       cudaGraph_t graph = nullptr;
       cudaGraphExec_t exec = nullptr;
       const long long before = h->launches;
       H_CUDA(cudaStreamBeginCapture(h->st, cudaStreamCaptureModeThreadLocal));
-      const int rc = eval_mean_enqueue(h, G, want_grad, use_resident);
+      const int rc = eval_mean_enqueue(h, G, want_grad, use_resident, refresh_csum);
       cudaError_t ce = cudaStreamEndCapture(h->st, &graph);
       if (rc != MCB_OK || ce != cudaSuccess) {
         if (graph) cudaGraphDestroy(graph);

@@ -80,6 +80,6 @@ int main() {
   cudaMemcpy(&cy, c, 8, cudaMemcpyDeviceToHost); cudaMemcpy(out, o, sizeof out, cudaMemcpyDeviceToHost); \
   { double err = 0; for (int i = 0; i < kNB * kNB; ++i) err = fmax(err, fabs(out[i] - Li[i])); \
   printf("threads %3d: %6lld cycles (%.0f per pivot), max |Linv - host| = %.3e\n", 32 * TPR, cy, cy / 32.0, err); }
-  RUN(8) RUN(4) RUN(2) RUN(1)
+  RUN(16) RUN(8) RUN(4)
   return 0;
 }
