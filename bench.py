@@ -169,7 +169,9 @@ def run_reference(args):
         return 0
     ds, cfg = workload_data(args.workload, 1, args.individuals)
     cores = os.cpu_count() or 1
-    base = cpu_baseline(ds, cfg, args.cpu_sample, steps=args.steps, warmup=args.warmup)
+    # bounded sample: the whole --steps/--warmup run should end within a few minutes (~0.07 s per individual)
+    sample = int(min(args.cpu_sample, max(40, 1600 // max(1, args.steps + args.warmup))))
+    base = cpu_baseline(ds, cfg, sample, steps=args.steps, warmup=args.warmup)
     M = cfg["M"] * args.gpus
     sec = extrapolate(base, M)
     value = M / sec  # individual-VEM-iterations per second
