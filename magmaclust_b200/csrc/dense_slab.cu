@@ -51,11 +51,13 @@ __device__ __forceinline__ double fast_rcp(double d) {
 __device__ __forceinline__ void slab_barrier(unsigned* counter, unsigned target) {
   __syncthreads();
   if (threadIdx.x == 0) {
-    __threadfence();
-    atomicAdd(counter, 1u);
-    while (*((volatile unsigned*)counter) < target) {
-    }
-    __threadfence();
+    // release: everything this CTA wrote (bar.sync above orders the other threads' writes before this point) becomes
+    // visible before the arrival; acquire: nothing after the barrier is read before the last arrival is seen
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
+    unsigned seen;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+    } while (seen < target);
   }
   __syncthreads();
 }
