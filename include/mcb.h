@@ -114,6 +114,13 @@ int mcb_eval_mean_common(mcb_handle* h, const double* theta, int nhp, double pen
  * out[1] = the MC.R:51-53 total (finite log-determinants). theta_* NULL -> use the resident hp. */
 int mcb_elbo(mcb_handle* h, const double* theta_k, const double* theta_i, double out[2]);
 
+/* ---- BIC (CF.R:354-432, clust = TRUE; "next" row of SURVEY 8f) --------------------------------------- */
+/* Terms of the reference's BIC at the resident hp against the resident hyper-posterior (mcb_set_state +
+ * mcb_set_posterior install both): out[0] = sum_i sum_k tau_ik (l_ik + log(pi_k / tau_ik)) (CF.R:366-399),
+ * out[1] = sum_k [dmvnorm(mean_k; m_1, K_k) - 0.5 sum(K_k^-1 o C_k)] (CF.R:409-414), out[2] = sum_k log det C_k
+ * (CF.R:415). The host adds 0.5 K (N + N log 2 pi) and the penalty (counts of distinct hp values). */
+int mcb_bic_terms(mcb_handle* h, double out[3]);
+
 /* ---- built-in M-step: m_step_VEM (CF.R:631-687) with the L-BFGS of csrc/lbfgs.h -------------------- */
 /* Optimises theta_i (one batched on-device L-BFGS per individual, or one shared), then theta_k, then
  * pi_k = mean_i tau_ik. Writes the NEW hp to new_* (host, may be NULL) and keeps them as "candidate" on the

@@ -49,6 +49,7 @@ SIGNATURES = {
     "mcb_eval_mean": (C.c_int, [H, C.c_int, c_double_p, C.c_int, C.c_double, c_double_p, c_double_p]),
     "mcb_eval_mean_common": (C.c_int, [H, c_double_p, C.c_int, C.c_double, c_double_p, c_double_p]),
     "mcb_elbo": (C.c_int, [H, c_double_p, c_double_p, c_double_p]),
+    "mcb_bic_terms": (C.c_int, [H, c_double_p]),
     "mcb_m_step": (C.c_int, [H, C.c_int, C.c_int, c_double_p, c_double_p, c_double_p, c_int_p]),
     "mcb_accept_hp": (C.c_int, [H]),
     "mcb_get_new_hp": (C.c_int, [H, c_double_p, c_double_p, c_double_p]),

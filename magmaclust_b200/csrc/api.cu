@@ -777,6 +777,46 @@ extern "C" int mcb_elbo(mcb_handle* h, const double* theta_k, const double* thet
   return elbo_impl(h, theta_k, ti, out);
 }
 
+// ---- BIC (CF.R:354-432, clust = TRUE) -----------------------------------------------------------------
+// Terms of BIC at the resident hp against the resident hyper-posterior (install both with mcb_set_state +
+// mcb_set_posterior, which also evaluates mat_logL at those hp):
+//   out[0] = sum_i sum_k tau_ik (l_ik + log(pi_k / tau_ik))                         (LL_i, CF.R:366-399)
+//   out[1] = sum_k [ dmvnorm(mean_k; m_1, K_k) - 0.5 sum(K_k^-1 o C_k) ]            (CF.R:414; every cluster is centred
+//            on the FIRST prior mean m_k[[1]], CF.R:409)
+//   out[2] = sum_k log det C_k          (maotai::pdeterminant of a full-rank SPD matrix, CF.R:415)
+// The caller adds 0.5 K (N + N log 2 pi) and subtracts the penalty, which only counts distinct hp values.
+extern "C" int mcb_bic_terms(mcb_handle* h, double out[3]) {
+  if (!h || !out) return MCB_EINVAL;
+  H_CHECK(h->has_post, MCB_ESTATE, "mcb_bic_terms: no hyper-posterior (run the E-step or mcb_set_posterior)");
+  H_CUDA(cudaSetDevice(h->device));
+  spans_reset(h);
+  const int K = h->K, ld = h->ld;
+  double* d = h->scal.p + 48;
+  H_CUDA(cudaMemsetAsync(d, 0, sizeof(double), h->st));
+  bic_indiv(h->st, h->M, K, h->tau_new.p, h->logL.p, h->pi.p, d, &h->launches);
+  MCB_TRY(comm_allreduce_sum(h, d, 1));
+  H_CUDA(cudaMemcpyAsync(h->hbuf + 760, d, sizeof(double), cudaMemcpyDeviceToHost, h->st));
+  // cluster part with r_k = mean_k - m_1 (first prior mean for every cluster)
+  for (int k = 0; k < K; ++k)
+    H_CUDA(cudaMemcpyAsync(h->pz.p + (size_t)k * ld, h->mk.p, sizeof(double) * ld, cudaMemcpyDeviceToDevice, h->st));
+  vec_sub(h->st, K * ld, h->mean.p, h->pz.p, h->rvec.p, &h->launches);
+  std::vector<int> gmap;
+  std::vector<double> groups;
+  const int G = group_theta(h->h_theta_k.data(), K, gmap, groups);
+  std::vector<double> f(G);
+  const int rc = eval_mean_groups(h, G, groups.data(), gmap.data(), false, true, f.data(), nullptr);
+  // restore r_k = mean_k - m_k for the other entry points
+  vec_sub(h->st, K * ld, h->mean.p, h->mk.p, h->rvec.p, &h->launches);
+  H_CUDA(cudaStreamSynchronize(h->st));
+  if (rc != MCB_OK) return rc;
+  out[0] = h->hbuf[760];
+  out[1] = 0.0;
+  for (int g = 0; g < G; ++g) out[1] -= f[g];
+  out[2] = 0.0;
+  for (int k = 0; k < K; ++k) out[2] += -h->h_logdetA[k];
+  return MCB_OK;
+}
+
 // pen_diag = mean_i theta_i[3] over all ranks (CF.R:662)
 static int compute_pen_diag(mcb_handle* h, double* pen_diag) {
   double* d = h->scal.p + 40;

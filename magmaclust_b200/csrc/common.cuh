@@ -124,6 +124,9 @@ void vec_sub(cudaStream_t s, int n, const double* a, const double* b, double* ou
 void tau_colsum(cudaStream_t s, int M, int K, const double* tau, double* out, long long* launches);
 // out[0] = sum_i theta[i][2]
 void theta3_sum(cudaStream_t s, int M, const double* theta, double* out, long long* launches);
+// out[0] += sum_i sum_k tau_ik (logL_ik + log(pi_k / tau_ik))   (BIC, CF.R:384-385)
+void bic_indiv(cudaStream_t s, int M, int K, const double* tau, const double* logL, const double* pi, double* out,
+               long long* launches);
 // out[0] += sum_i v[i]
 void vec_sum(cudaStream_t s, int M, const double* v, double* out, long long* launches);
 // symmetrise/mirror helpers are not needed: every producer writes both triangles.

@@ -186,6 +186,30 @@ void theta3_sum(cudaStream_t s, int M, const double* theta, double* out, long lo
   if (launches) ++*launches;
 }
 
+// out[0] += sum_i sum_k tau_ik (l_ik + log(pi_k / tau_ik)), the log term skipped when tau_ik == 0 or pi_k == 0
+// (BIC's per-individual part, CF.R:384-385, with l_ik = mat_logL[i][k])
+__global__ void bic_indiv_kernel(int M, int K, const double* __restrict__ tau, const double* __restrict__ logL,
+                                 const double* __restrict__ pi, double* __restrict__ out) {
+  double s = 0;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < M * K; e += gridDim.x * blockDim.x) {
+    const int k = e % K;
+    const double t = tau[e], p = pi[k];
+    double v = t * logL[e];
+    if (t != 0.0 && p != 0.0) v += t * log(p / t);
+    s += v;
+  }
+  s = wsum(s);
+  if ((threadIdx.x & 31) == 0) atomicAdd(out, s);
+}
+
+void bic_indiv(cudaStream_t s, int M, int K, const double* tau, const double* logL, const double* pi, double* out,
+               long long* launches) {
+  int blocks = (M * K + 255) / 256;
+  if (blocks > 148 * 4) blocks = 148 * 4;
+  bic_indiv_kernel<<<blocks, 256, 0, s>>>(M, K, tau, logL, pi, out);
+  if (launches) ++*launches;
+}
+
 void vec_sum(cudaStream_t s, int M, const double* v, double* out, long long* launches) {
   int blocks = (M + 255) / 256;
   if (blocks > 148 * 4) blocks = 148 * 4;

@@ -177,6 +177,11 @@ class Engine:
         self._ck(self.lib.mcb_elbo(self.h, dptr(tk), dptr(ti), dptr(out)))
         return float(out[0]), float(out[1])
 
+    def bic_terms(self):
+        out = np.empty(3)
+        self._ck(self.lib.mcb_bic_terms(self.h, dptr(out)))
+        return float(out[0]), float(out[1]), float(out[2])
+
     def m_step(self, common_hp_k=True, common_hp_i=True):
         tk, ti, pi = np.empty((self.K, 3)), np.empty((self.M, 3)), np.empty(self.K)
         stats = np.zeros(4, dtype=np.int32)

@@ -306,6 +306,52 @@ def logL_monitoring_VEM(hp, db, kern_i, kern_0, mu_k_param, m_k, session=None):
     return s.eng.elbo(theta_k, theta_i)[0]
 
 
+def BIC(hp, db, kern_0, kern_i, m_k, mu_k_param, clust=True, session=None):
+    """CF.R:354-432 (clust = TRUE). The sums run on the device; the penalty counts distinct hp VALUES like the
+    reference's `n_distinct(unlist(.))` (CF.R:359-361)."""
+    if not clust:
+        raise NotImplementedError("clust = FALSE needs the single-cluster MAGMA model of the sibling repository")
+    _check_kernels(kern_0, kern_i)
+    s = session or default_session()
+    c = s.ensure_data(db)
+    names_k = list(mu_k_param["mean"].keys())
+    # evaluate at (hp, mu_k_param): install both (mat_logL is recomputed at these hp with tau frozen)
+    theta_k, theta_i = s.pack_hp(hp, names_k)
+    tau = s.pack_tau(mu_k_param["tau_i_k"], names_k)
+    s.eng.set_state(theta_k, theta_i, np.asarray(hp["pi_k"], dtype=np.float64), s.pack_mk(m_k, names_k), tau)
+    mean = np.array([np.asarray(mu_k_param["mean"][k]["Output"], dtype=np.float64) for k in names_k])
+    cov = np.array([mu_k_param["cov"][k].m for k in names_k])
+    s.eng.set_posterior(mean, cov, tau)
+    s._post_token = None
+    ll_i, ll_k, logdet = s.eng.bic_terms()
+    K, N = len(names_k), c.N
+    nb_hp_i = len(np.unique(theta_i))
+    nb_hp_k = len(np.unique(theta_k))
+    nb_clust = len(np.unique(np.asarray(hp["pi_k"], dtype=np.float64)))
+    pen = 0.5 * (nb_hp_i + nb_hp_k + nb_clust - 1) * np.log(c.M)
+    return ll_i + ll_k + 0.5 * (K * (N + N * np.log(2 * np.pi)) + logdet) - pen
+
+
+def model_selection(db, k_grid, ini_tau_by_k, ini_hp=None, kern_0=kernel_mu, kern_i=kernel, common_hp_k=True,
+                    common_hp_i=True, session=None):
+    """MC.R:101-135 for K >= 2: train one model per K, score it with BIC, keep the arg max. `ini_tau_by_k[K]` supplies
+    the initial responsibilities (the reference's default is an unseeded k-means); K = 1 would need `training` from
+    the sibling MAGMA repository, which the reference does not ship."""
+    s = session or default_session()
+    res = {}
+    for K in k_grid:
+        if K < 2:
+            raise NotImplementedError("K = 1 needs the sibling repository's training()")
+        prior_mean_k = {f"K{k + 1}": 0.0 for k in range(K)}
+        model = training_VEM(db, prior_mean_k, ini_hp, kern_0, kern_i, ini_tau_by_k[K], common_hp_k, common_hp_i,
+                             session=s)
+        model["BIC"] = BIC(model["hp"], db, kern_0, kern_i, prior_mean_k, model["param"], True, session=s)
+        res[f"K = {K}"] = model
+    bics = {K: res[f"K = {K}"]["BIC"] for K in k_grid}
+    res["K_max_BIC"] = max(bics, key=bics.get)
+    return res
+
+
 # ---------------------------------------------------------------------------------------------
 # drivers (MC.R)
 # ---------------------------------------------------------------------------------------------

@@ -284,6 +284,69 @@ def logL_monitoring_VEM(hp, db, kern_i, kern_0, mu_k_param, m_k):
     return -sum_ll_k - sum_ll_i
 
 
+def BIC(hp, db, kern_0, kern_i, m_k, mu_k_param, clust=True):
+    """CF.R:354-432 (clust = TRUE branch). `maotai::pdeterminant(x)$modulus` (third-party, unpinned) is taken as the
+    log-determinant: the pseudo-determinant of a full-rank SPD matrix. Quirks kept: the numbers of hyper-parameters
+    are counts of DISTINCT VALUES (`n_distinct(unlist(.))`, CF.R:359-361) and every cluster is centred on the FIRST
+    prior mean `m_k[[1]]` (CF.R:409)."""
+    if not clust:
+        raise NotImplementedError("clust = FALSE needs the single-cluster MAGMA model of the sibling repository")
+    list_clust = list(mu_k_param["mean"].keys())
+    per_id = split_db(db)
+    nb_indiv = len(per_id)
+    nb_hp_i = len(np.unique(np.concatenate([np.asarray(v, dtype=np.float64).ravel() for v in hp["theta_i"].values()])))
+    nb_hp_k = len(np.unique(np.concatenate([np.asarray(v, dtype=np.float64).ravel() for v in hp["theta_k"].values()])))
+    nb_clust = len(np.unique(np.asarray(hp["pi_k"], dtype=np.float64)))
+    pen = 0.5 * (nb_hp_i + nb_hp_k + nb_clust - 1) * np.log(nb_indiv)
+    pi = np.asarray(hp["pi_k"], dtype=np.float64)
+    LL_i = 0.0
+    for i, d in per_id.items():
+        t_i, y_i = d["Timestamp"], d["Output"]
+        th = np.asarray(hp["theta_i"][i], dtype=np.float64).ravel()
+        inv_i = kern_to_inv(t_i, kern_i, th[:2], th[2]).m
+        sum_LL = 0.0
+        LL_Z = 0.0
+        for c, k in enumerate(list_clust):
+            mk = mu_k_param["mean"][k]
+            mu_k_ti = np.asarray(mk["Output"])[np.isin(mk["Timestamp"], t_i)]
+            tau = mu_k_param["tau_i_k"][k][i]
+            cov_k_hat = mu_k_param["cov"][k].sub(t_i)
+            sum_LL += tau * (dmvnorm(y_i, mu_k_ti, inv_i, log=True) - 0.5 * np.sum(inv_i * cov_k_hat))
+            LL_Z += tau * (0.0 if (tau == 0 or pi[c] == 0) else np.log(pi[c] / tau))
+        LL_i += sum_LL + LL_Z
+    t = unique_stable(np.asarray(db["Timestamp"], dtype=np.float64))
+    size_mu = t.shape[0]
+    first = np.atleast_1d(np.asarray(next(iter(m_k.values())), dtype=np.float64))
+    LL_k = 0.0
+    for k in list_clust:
+        mk = mu_k_param["mean"][k]
+        mu_k_t = np.asarray(mk["Output"])[np.isin(mk["Timestamp"], t)]
+        mean_k = np.repeat(first[0], size_mu)
+        thk = np.asarray(hp["theta_k"][k], dtype=np.float64)
+        inv_k = kern_to_inv(t, kern_0, thk[:2], thk[2])
+        cov_k_hat = mu_k_param["cov"][k].sub(inv_k.t)
+        LL_k += dmvnorm(mu_k_t, mean_k, inv_k.m, log=True) - 0.5 * np.sum(inv_k.m * cov_k_hat) + \
+            0.5 * (size_mu + size_mu * LOG_2PI + np.linalg.slogdet(cov_k_hat)[1])
+    return LL_i + LL_k - pen
+
+
+def model_selection(db, k_grid, ini_tau_by_k, ini_hp=None, kern_0=kernel_mu, kern_i=kernel, common_hp_k=True,
+                    common_hp_i=True):
+    """MC.R:101-135 for K >= 2 (K = 1 calls `training` of the sibling MAGMA repository, which is not in the reference).
+    `ini_tau_by_k[K]` supplies the initial responsibilities (the reference's default is an unseeded k-means)."""
+    res = {}
+    for K in k_grid:
+        if K < 2:
+            raise NotImplementedError("K = 1 needs the sibling repository's training()")
+        prior_mean_k = {f"K{k + 1}": 0.0 for k in range(K)}
+        model = training_VEM(db, prior_mean_k, ini_hp, kern_0, kern_i, ini_tau_by_k[K], common_hp_k, common_hp_i)
+        model["BIC"] = BIC(model["hp"], db, kern_0, kern_i, prior_mean_k, model["param"], True)
+        res[f"K = {K}"] = model
+    bics = {K: res[f"K = {K}"]["BIC"] for K in k_grid}
+    res["K_max_BIC"] = max(bics, key=bics.get)
+    return res
+
+
 # --------------------------------------------------------------------------------------------
 # CF.R:448-586 — gradients
 # --------------------------------------------------------------------------------------------

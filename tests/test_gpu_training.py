@@ -62,3 +62,41 @@ def test_prediction_chain(session):
     for k in names:
         assert rel_err(p_got[k]["Mean"], p_ref[k]["Mean"]) < RTOL_POST
         assert np.max(np.abs(p_got[k]["Var"] - p_ref[k]["Var"])) < 1e-8 * max(1.0, np.max(np.abs(p_ref[k]["Var"])))
+
+
+@pytest.mark.parametrize("case", ["gold0", "small_indiv_hp"])
+def test_bic(session, case):
+    """BIC (CF.R:354-432), the first 'next' row of SURVEY 8f: same value as the oracle at (hp, param)"""
+    from magmaclust_b200 import magma
+    if case == "gold0":
+        db, hp, tau, m_k = gold_dataset(load_gold(), 0)
+    else:
+        db, hp, tau, m_k = small_problem(M=9, K=3, seed=15)
+        m_k = {k: 0.3 for k in m_k}
+    ref_param = O.e_step_VEM(db, m_k, O.kernel_mu, O.kernel, hp, tau)
+    got_param = magma.e_step_VEM(db, m_k, magma.kernel_mu, magma.kernel, hp, tau, session=session)
+    # score at DIFFERENT hp than the E-step's (training_VEM returns new_hp with the previous param, MC.R:95)
+    hp2 = {"theta_k": {k: np.asarray(v) + 0.05 for k, v in hp["theta_k"].items()},
+           "theta_i": {i: np.asarray(v) * 1.02 for i, v in hp["theta_i"].items()}, "pi_k": hp["pi_k"]}
+    b_ref = O.BIC(hp2, db, O.kernel_mu, O.kernel, m_k, ref_param)
+    b_got = magma.BIC(hp2, db, magma.kernel_mu, magma.kernel, m_k, got_param, session=session)
+    assert abs(b_got - b_ref) <= RTOL_LL * abs(b_ref)
+
+
+def test_model_selection_picks_the_same_k(session):
+    from magmaclust_b200 import magma
+    db, hp, tau, m_k = small_problem(M=14, K=3, n=(8, 12), n_grid=40, seed=31, common_hp_i=True)
+    ids = list(O.split_db(db).keys())
+    rng = np.random.default_rng(1)
+    ini = {}
+    for K in (2, 3):
+        lab = rng.integers(0, K, len(ids))
+        lab[:K] = np.arange(K)
+        ini[K] = {f"K{c + 1}": {i: 1.0 if lab[r] == c else 0.0 for r, i in enumerate(ids)} for c in range(K)}
+    ini_hp = {"theta_k": np.array([1.0, 1.0, 0.2]), "theta_i": np.array([1.0, 1.0, 0.2])}
+    ref = O.model_selection(db, [2, 3], ini, ini_hp)
+    got = magma.model_selection(db, [2, 3], ini, ini_hp, session=session)
+    assert got["K_max_BIC"] == ref["K_max_BIC"]
+    for K in (2, 3):
+        b_ref, b_got = ref[f"K = {K}"]["BIC"], got[f"K = {K}"]["BIC"]
+        assert abs(b_got - b_ref) <= 1e-3 * abs(b_ref), (K, b_got, b_ref)
