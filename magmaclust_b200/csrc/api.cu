@@ -18,11 +18,6 @@ static inline cudaError_t sync_copy(mcb_handle* h, void* dst, const void* src, s
   cudaError_t e = cudaMemcpyAsync(dst, src, bytes, kind, h->st);
   return e != cudaSuccess ? e : cudaStreamSynchronize(h->st);
 }
-static inline cudaError_t sync_copy2d(mcb_handle* h, void* dst, size_t dpitch, const void* src, size_t spitch,
-                                      size_t width, size_t height, cudaMemcpyKind kind) {
-  cudaError_t e = cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, height, kind, h->st);
-  return e != cudaSuccess ? e : cudaStreamSynchronize(h->st);
-}
 #define H_CHECK(cond, code, text) \
   do {                            \
     if (!(cond)) {                \

@@ -15,6 +15,7 @@
 #include <cooperative_groups.h>
 
 #include "common.cuh"
+#include "factor32.cuh"
 
 namespace mcb {
 
@@ -98,15 +99,13 @@ spd_inverse_slab_kernel(double* __restrict__ Aall, int N, int ld, long long stri
   double* Rs = Ls + kNB * kLp;             // A[I,b] rows     (32 x kLp)
   double* Vs = Rs + kNB * kLp;             // V_I
   double* Ps = Vs + kNB * kLp;             // P_I
-  double* uvec = Ps + kNB * kLp;           // [2][kNB + 4] travelling pivot vector (double-buffered)
-  double* piv = uvec + 2 * (kNB + 4);      // [kNB]
+  double* uvec = Ps + kNB * kLp;           // scratch of factor32
   double* A = Aall + z * stride;
   unsigned* counter = bar + z;
   unsigned arrivals = 0;
-  double logdet_part = 0.0;  // lanes of warp 0: sum of log pivots of the blocks this CTA factored
+  double logdet_part = 0.0;  // lanes of warp 7: sum of log pivots of the blocks this CTA factored
   const long long sPz = (long long)Npad * kNB;          // per-matrix panel size
   const long long sPall = sPz * gridDim.y;              // per-parity size
-  const int ti = tid >> 3, tc = (tid & 7) * 4;          // factorisation ownership: row ti, columns tc..tc+3
 
   // ---- load the slab (rows r0..r0+31, all ld columns incl. zero pads) ----------------------------------
   for (int e = tid; e < kNB * (ld / 2); e += kSlabThreads) {
@@ -118,79 +117,26 @@ spd_inverse_slab_kernel(double* __restrict__ Aall, int N, int ld, long long stri
   }
   __syncthreads();
 
-  // Factor this CTA's diagonal block (pivot block bb): D = Lu Delta Lu', publish L^-1 = Delta^-1/2 Lu^-1.
-  // One register per (row ti, column c): it holds D[ti][c] until pivot c has been eliminated and Lu^-1[ti][c]
-  // afterwards. Per pivot k a single shared vector u travels: u[c < k] = Lu^-1[k][c], u[k] = 1, u[c > k] = D[c][k],
-  // u[32] = 1 / pivot; every thread below the pivot row does 4 FMAs, one barrier per pivot.
-  auto factor_block = [&](int bb) {
+  // Factor this CTA's diagonal block (pivot block bb): D = L L', publish L^-1 (factor32.cuh: register-resident 8 x 8
+  // diagonal tiles + DMMA tile products; the N sequential pivots are the critical path of the whole inverse).
+  // The block is expected in Rs (identity-padded) unless from_slab; Ps receives L^-1.
+  auto factor_block = [&](int bb, bool from_slab) {
     const int c0 = bb * kNB;
     const int nb = min(kNB, N - c0);
     double* Lg = Lbuf + ((size_t)(bb & 1) * gridDim.y + z) * kNB * kNB;
-    double reg[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int c = tc + q;
-      // identity padding keeps a partial last block a no-op for the extra pivots
-      reg[q] = (ti < nb && c < nb) ? slab[(size_t)ti * lds + c0 + c] : (ti == c ? 1.0 : 0.0);
-    }
-    if (tc == 0) {
-      if (ti > 0) uvec[ti] = reg[0];
-      else { uvec[0] = 1.0; uvec[kNB] = fast_rcp(reg[0]); piv[0] = reg[0]; }
-    }
-    __syncthreads();
-    for (int k = 0; k < kNB; ++k) {
-      const double* u = uvec + (k & 1) * (kNB + 4);
-      if (ti > k) {
-        const double m = -u[ti] * u[kNB];
-        const double2 ua = *reinterpret_cast<const double2*>(u + tc);
-        const double2 ub = *reinterpret_cast<const double2*>(u + tc + 2);
-        const unsigned kq = (unsigned)(k - tc);
-        if (kq < 4u) {  // the register of column k switches from D[ti][k] to Lu^-1[ti][k] = 0 - m * 1
-          if (kq == 0) reg[0] = 0.0;
-          if (kq == 1) reg[1] = 0.0;
-          if (kq == 2) reg[2] = 0.0;
-          if (kq == 3) reg[3] = 0.0;
-        }
-        reg[0] = fma(m, ua.x, reg[0]);
-        reg[1] = fma(m, ua.y, reg[1]);
-        reg[2] = fma(m, ub.x, reg[2]);
-        reg[3] = fma(m, ub.y, reg[3]);
-      }
-      const int k1 = k + 1;
-      if (k1 < kNB) {
-        double* un = uvec + (k1 & 1) * (kNB + 4);
-        const unsigned q1 = (unsigned)(k1 - tc);
-        if (ti == k1) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q)
-            if (tc + q < k1) un[tc + q] = reg[q];
-        }
-        if (q1 < 4u && ti >= k1) {
-          const double v = q1 == 0 ? reg[0] : q1 == 1 ? reg[1] : q1 == 2 ? reg[2] : reg[3];
-          if (ti > k1) un[ti] = v;
-          else { un[k1] = 1.0; un[kNB] = fast_rcp(v); piv[k1] = v; }
-        }
+    if (from_slab) {
+      for (int e = tid; e < kNB * kNB; e += kSlabThreads) {
+        const int r = e >> 5, c = e & 31;
+        // identity padding keeps a partial last block a no-op for the extra pivots
+        Rs[r * kLp + c] = (r < nb && c < nb) ? slab[(size_t)r * lds + c0 + c] : (r == c ? 1.0 : 0.0);
       }
       __syncthreads();
     }
-    {
-      const double sc = 1.0 / sqrt(piv[ti]);
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int c = tc + q;
-        Lg[ti * kNB + c] = (c == ti) ? sc : (c < ti ? reg[q] * sc : 0.0);
-      }
-    }
-    if (tid < 32) {
-      // log det and the positive-definiteness check are off the critical path: L^-1 is already on its way
-      const double d = piv[tid];
-      const bool bad = !(d > 0.0);
-      if (__any_sync(0xffffffffu, bad) && tid == 0) *info = 1;
-      logdet_part += log(d);
-    }
+    factor32(Rs, Ps, uvec, &logdet_part, info);
+    for (int e = tid; e < kNB * kNB; e += kSlabThreads) Lg[e] = Ps[(e >> 5) * kLp + (e & 31)];
   };
 
-  if (I == 0) factor_block(0);
+  if (I == 0) factor_block(0, true);
   arrivals += nblk;
   slab_barrier(counter, arrivals);
 
@@ -257,13 +203,15 @@ spd_inverse_slab_kernel(double* __restrict__ Aall, int N, int ld, long long stri
 #pragma unroll
         for (int k = 0; k < 8; ++k)
           dmma884_s(n0, n1, Vs[(8 * tI + gr) * kLp + 4 * k + gc], Vs[(8 * tJ + gr) * kLp + 4 * k + gc]);
-        double* cp = slab + (size_t)(8 * tI + gr) * lds + c1 + 8 * tJ + 2 * gc;
-        cp[0] -= n0;
-        cp[1] -= n1;
+        const double* cp = slab + (size_t)(8 * tI + gr) * lds + c1 + 8 * tJ + 2 * gc;
+        const int r = 8 * tI + gr, c = 8 * tJ + 2 * gc;
+        const int nb1 = min(kNB, N - c1);
+        Rs[r * kLp + c] = (r < nb1 && c < nb1) ? cp[0] - n0 : (r == c ? 1.0 : 0.0);
+        Rs[r * kLp + c + 1] = (r < nb1 && c + 1 < nb1) ? cp[1] - n1 : (r == c + 1 ? 1.0 : 0.0);
       }
       __syncthreads();
       SLAB_TP(4);
-      factor_block(b + 1);
+      factor_block(b + 1, false);
       SLAB_TP(5);
     } else if (I != b) {
       // trailing update of the slab. Each warp owns the 8-column tiles tj = warp, warp + 8, ...; ALL its B
@@ -329,10 +277,10 @@ spd_inverse_slab_kernel(double* __restrict__ Aall, int N, int ld, long long stri
     }
   }
 
-  if (tid < 32) {
+  if (warp == 7) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) logdet_part += __shfl_xor_sync(0xffffffffu, logdet_part, o);
-    if (tid == 0) atomicAdd(logdet + z, logdet_part);
+    if (lane == 0) atomicAdd(logdet + z, logdet_part);
   }
   // ---- write back, flipping the sign (-A^-1 -> A^-1) -------------------------------------------------------
   for (int e = tid; e < kNB * (ld / 2); e += kSlabThreads) {
