@@ -108,6 +108,9 @@ extern "C" void mcb_destroy(mcb_handle* h) {
   cudaStreamSynchronize(h->st);
   comm_destroy(h);
   for (auto& kv : h->eval_graphs) cudaGraphExecDestroy(kv.second.exec);
+  if (h->mopt_exec) cudaGraphExecDestroy(h->mopt_exec);
+  if (h->st_cap) cudaStreamDestroy(h->st_cap);
+  h->mopt_state.release();
   for (auto e : h->evpool) cudaEventDestroy(e);
   mcb::DevBuf<double>* dbl[] = {&h->t, &h->y, &h->grid, &h->theta_i, &h->theta_k, &h->pi, &h->mk, &h->tau,
                                 &h->theta_i_new, &h->theta_k_new, &h->pi_new, &h->tau_new, &h->logL, &h->Winv,
@@ -188,6 +191,8 @@ extern "C" int mcb_set_data(mcb_handle* h, int M, int N, long long P, const int*
 static void drop_graphs(mcb_handle* h) {
   for (auto& kv : h->eval_graphs) cudaGraphExecDestroy(kv.second.exec);
   h->eval_graphs.clear();
+  if (h->mopt_exec) cudaGraphExecDestroy(h->mopt_exec);
+  h->mopt_exec = nullptr;
 }
 
 static int alloc_state(mcb_handle* h, int K) {
@@ -812,6 +817,156 @@ extern "C" int mcb_bic_terms(mcb_handle* h, double out[3]) {
   return MCB_OK;
 }
 
+// ---- device-driven optimisation of a shared theta_k -------------------------------------------------------
+// The optimiser loop of CF.R:666-668 evaluates the objective ~25 times in sequence; driven from the host every
+// evaluation pays a graph launch, a stream synchronisation and two small copies (~50 us against ~220 us of kernels).
+// Here the loop itself lives on the device: a WHILE conditional graph node whose body is one evaluation followed by
+// a one-warp kernel that forms f and the gradient from the reductions, advances the same L-BFGS state machine the
+// host path uses (lbfgs.h) and decides whether to iterate again. The host launches one graph and waits once.
+constexpr int kMoptWords = (int)((sizeof(Lbfgs) + 7) / 8);
+
+__global__ void mean_opt_init_kernel(const double* __restrict__ theta_k, double* state, double* etheta, int* egmap,
+                                     int K) {
+  if (threadIdx.x == 0) {
+    Lbfgs* o = reinterpret_cast<Lbfgs*>(state);
+    lb_init(*o, 3, theta_k);
+    etheta[0] = theta_k[0]; etheta[1] = theta_k[1]; etheta[2] = theta_k[2];
+  }
+  for (int k = threadIdx.x; k < K; k += blockDim.x) egmap[k] = 0;
+}
+
+// result: [0..2] theta, [3] nfev, [4] iterations, [5] evaluations that met a non-positive pivot
+__global__ void mean_opt_advance_kernel(double* state, const double* __restrict__ ered, const double* __restrict__ logdet,
+                                        int* info, double* etheta, int N, int K, cudaGraphConditionalHandle handle,
+                                        double* result) {
+  __shared__ double words[kMoptWords];
+  for (int w = threadIdx.x; w < kMoptWords; w += blockDim.x) words[w] = state[w];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    Lbfgs& o = *reinterpret_cast<Lbfgs*>(words);
+    const double* rg = ered;            // [G = 1][4]: sum Kinv.Csum, tr(Kinv D1), tr(Kinv D2), tr(Kinv)
+    const double* rz = ered + 4 * K;    // [K][4]:     r'p, p'p, p'D1 p, p'D2 p
+    const double* rt = ered + 8 * K;    // [1][4]:     tr(G D1), tr(G D2), tr(G)
+    double q = 0, pp = 0, d1 = 0, d2 = 0;
+    for (int z = 0; z < K; ++z) { q += rz[4 * z]; pp += rz[4 * z + 1]; d1 += rz[4 * z + 2]; d2 += rz[4 * z + 3]; }
+    double f = 0.5 * K * ((double)N * kLog2Pi + logdet[0]) + 0.5 * q + 0.5 * rg[0];
+    double g[3];
+    const double sg = o.x[2];
+    g[0] = -0.5 * (d1 + rt[0] - K * rg[1]);
+    g[1] = -0.5 * (d2 + rt[1] - K * rg[2]);
+    g[2] = -sg * (pp + rt[2] - K * rg[3]);
+    if (*info) {  // trial point with a non-PD covariance: infinite objective, the line search backs off
+      f = INFINITY; g[0] = g[1] = g[2] = 0.0;
+      *info = 0;
+      result[5] += 1.0;
+    }
+    const int st = lb_advance(o, f, g);
+    etheta[0] = o.x[0]; etheta[1] = o.x[1]; etheta[2] = o.x[2];
+    result[0] = o.x[0]; result[1] = o.x[1]; result[2] = o.x[2];
+    result[3] = (double)o.nfev; result[4] = (double)o.iter;
+    cudaGraphSetConditional(handle, st == LB_EVAL ? 1u : 0u);
+  }
+  __syncthreads();
+  for (int w = threadIdx.x; w < kMoptWords; w += blockDim.x) state[w] = words[w];
+}
+
+static int build_mean_opt_graph(mcb_handle* h) {
+  const int N = h->N, ld = h->ld, K = h->K;
+  const long long sN = (long long)N * ld;
+  H_CUDA(h->mopt_state.ensure(kMoptWords + 16));
+  if (!h->st_cap) H_CUDA(cudaStreamCreateWithFlags(&h->st_cap, cudaStreamNonBlocking));
+  double* state = h->mopt_state.p;
+  double* result = state + kMoptWords;
+  cudaGraph_t graph = nullptr;
+  const long long before = h->launches;
+  H_CUDA(cudaStreamBeginCapture(h->st, cudaStreamCaptureModeThreadLocal));
+  auto fail = [&](const char* what, cudaError_t ce) {
+    cudaGraph_t g2 = nullptr;
+    cudaStreamEndCapture(h->st, &g2);
+    if (g2) cudaGraphDestroy(g2);
+    h->launches = before;
+    h->err = std::string("theta_k loop graph: ") + what + ": " + cudaGetErrorString(ce);
+    return MCB_ECUDA;
+  };
+  cudaError_t ce;
+  if ((ce = cudaMemsetAsync(result, 0, sizeof(double) * 16, h->st)) != cudaSuccess) return fail("memset", ce);
+  mean_opt_init_kernel<<<1, 32, 0, h->st>>>(h->theta_k.p, state, h->etheta.p, h->egmap.p, K);
+  ++h->launches;
+  sum_groups(h->st, N, ld, sN, h->cov.p, h->egmap.p, K, h->eCsum.p, 1, &h->launches);
+  h->mopt_pre = h->launches - before;
+  // the WHILE node, inserted at the current capture frontier
+  cudaStreamCaptureStatus cst;
+  const cudaGraphNode_t* deps = nullptr;
+  size_t ndeps = 0;
+  if ((ce = cudaStreamGetCaptureInfo(h->st, &cst, nullptr, &graph, &deps, &ndeps)) != cudaSuccess) return fail("capture info", ce);
+  cudaGraphConditionalHandle handle;
+  if ((ce = cudaGraphConditionalHandleCreate(&handle, graph, 1, cudaGraphCondAssignDefault)) != cudaSuccess) return fail("handle", ce);
+  cudaGraphNodeParams np = {};
+  np.type = cudaGraphNodeTypeConditional;
+  np.conditional.handle = handle;
+  np.conditional.type = cudaGraphCondTypeWhile;
+  np.conditional.size = 1;
+  cudaGraphNode_t loop;
+  if ((ce = cudaGraphAddNode(&loop, graph, deps, ndeps, &np)) != cudaSuccess) return fail("conditional node", ce);
+  cudaGraph_t body = np.conditional.phGraph_out[0];
+  // body: one evaluation with gradient (same enqueue order as eval_mean_enqueue, theta from device memory)
+  {
+    const long long b0 = h->launches;
+    if ((ce = cudaStreamBeginCaptureToGraph(h->st_cap, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal)) != cudaSuccess)
+      return fail("body capture", ce);
+    cudaStream_t s = h->st_cap;
+    se_build(s, h->eK.p, h->eD1.p, h->eD2.p, N, ld, sN, h->grid.p, h->etheta.p, 3, 1, &h->launches);
+    cudaError_t ie = spd_inverse(s, h->eK.p, N, ld, sN, 1, h->elogdet.p, h->info.p, h->ws, &h->launches);
+    symv_mapped(s, N, ld, sN, h->eK.p, h->egmap.p, h->rvec.p, h->pz.p, K, &h->launches);
+    double* redg = h->ered.p;
+    double* redz = redg + 4 * K;
+    double* redt = redz + 4 * K;
+    cudaMemsetAsync(h->ered.p, 0, sizeof(double) * 12 * K, s);
+    group_reduce(s, N, ld, sN, h->eK.p, h->eCsum.p, sN, h->eD1.p, h->eD2.p, redg, 1, &h->launches);
+    cluster_reduce(s, N, ld, sN, h->rvec.p, h->pz.p, h->eD1.p, h->eD2.p, h->egmap.p, redz, K, &h->launches);
+    gemm_nt(s, N, N, N, h->eK.p, ld, sN, h->eCsum.p, ld, sN, h->eX.p, ld, sN, 1.0, 0.0, 1, &h->launches);
+    gemm_nt_trace(s, N, h->eX.p, ld, sN, h->eK.p, ld, sN, h->eD1.p, h->eD2.p, ld, sN, redt, 4, 1, &h->launches);
+    mean_opt_advance_kernel<<<1, 32, 0, s>>>(state, h->ered.p, h->elogdet.p, h->info.p, h->etheta.p, N, K, handle, result);
+    ++h->launches;
+    cudaError_t ee = cudaStreamEndCapture(s, nullptr);
+    h->mopt_body = h->launches - b0;
+    if (ie != cudaSuccess) return fail("inverse in body", ie);
+    if (ee != cudaSuccess) return fail("body end capture", ee);
+  }
+  if ((ce = cudaStreamUpdateCaptureDependencies(h->st, &loop, 1, cudaStreamSetCaptureDependencies)) != cudaSuccess)
+    return fail("dependencies", ce);
+  if ((ce = cudaMemcpyAsync(h->hbuf + 4096, result, sizeof(double) * 8, cudaMemcpyDeviceToHost, h->st)) != cudaSuccess)
+    return fail("result copy", ce);
+  h->launches = before;
+  H_CUDA(cudaStreamEndCapture(h->st, &graph));
+  cudaError_t inst = cudaGraphInstantiate(&h->mopt_exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (inst != cudaSuccess) {
+    h->mopt_exec = nullptr;
+    h->err = std::string("theta_k loop graph: instantiate: ") + cudaGetErrorString(inst);
+    return MCB_ECUDA;
+  }
+  return MCB_OK;
+}
+
+// Runs the whole optimisation; out[0..2] = theta, nfev / iterations returned through the pointers. Enqueue only when
+// !wait (the caller synchronises h->st later and then calls with collect = true).
+static int mean_opt_launch(mcb_handle* h) {
+  if (!h->mopt_exec) MCB_TRY(build_mean_opt_graph(h));
+  H_CUDA(cudaGraphLaunch(h->mopt_exec, h->st));
+  h->csum_valid = true;
+  h->csum_gmap.assign(h->K, 0);
+  return MCB_OK;
+}
+
+static void mean_opt_collect(mcb_handle* h, double theta[3], int* nfev, int* iters) {
+  const double* r = h->hbuf + 4096;
+  theta[0] = r[0]; theta[1] = r[1]; theta[2] = r[2];
+  *nfev = (int)r[3];
+  *iters = (int)r[4];
+  h->launches += h->mopt_pre + (long long)*nfev * h->mopt_body;
+}
+
 // pen_diag = mean_i theta_i[3] over all ranks (CF.R:662)
 static int compute_pen_diag(mcb_handle* h, double* pen_diag) {
   double* d = h->scal.p + 40;
@@ -909,17 +1064,25 @@ static int m_step_impl(mcb_handle* h, int common_hp_k, int common_hp_i, int* sta
       // NB reference behaviour: the start vector theta_k[[1]] has 3 entries, so sigma is optimised too and
       // then discarded: opm(...)[1, 1:2] keeps (a, b) and pen_diag becomes the third entry (CF.R:666-668)
       Lbfgs opt;
-      lb_init(opt, 3, h->h_theta_k.data());
-      std::vector<int> gm(K, 0);
-      int st = LB_EVAL;
-      double f, g[3];
-      while (st == LB_EVAL) {
-        const int rc = eval_mean_groups(h, 1, opt.x, gm.data(), true, false, &f, g);
-        if (rc == MCB_ENOTPD) { f = INFINITY; g[0] = g[1] = g[2] = 0.0; }  // line search backs off (see above)
-        else if (rc != MCB_OK) return rc;
-        st = lb_advance(opt, f, g);
+      static const bool host_loop = getenv("MCB_HOST_THETA_K") != nullptr || getenv("MCB_NO_GRAPH") != nullptr;
+      if (!host_loop) {
+        // the loop runs on the device (WHILE graph node); one launch, one wait
+        MCB_TRY(mean_opt_launch(h));
+        H_CUDA(cudaStreamSynchronize(h->st));
+        mean_opt_collect(h, opt.x, &nfev_k, &nit_k);
+      } else {
+        lb_init(opt, 3, h->h_theta_k.data());
+        std::vector<int> gm(K, 0);
+        int st = LB_EVAL;
+        double f, g[3];
+        while (st == LB_EVAL) {
+          const int rc = eval_mean_groups(h, 1, opt.x, gm.data(), true, false, &f, g);
+          if (rc == MCB_ENOTPD) { f = INFINITY; g[0] = g[1] = g[2] = 0.0; }  // line search backs off (see above)
+          else if (rc != MCB_OK) return rc;
+          st = lb_advance(opt, f, g);
+        }
+        nfev_k = opt.nfev; nit_k = opt.iter;
       }
-      nfev_k = opt.nfev; nit_k = opt.iter;
       if (overlap) {
         // join the theta_i stream, then pen_diag = mean_i theta_i[3]
         H_CUDA(cudaStreamWaitEvent(h->st, h->ev_join, 0));

@@ -70,6 +70,12 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
   const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem));
 }
+// 16-byte copy that writes zeros instead when !valid (the source address is not dereferenced)
+__device__ __forceinline__ void cp_async16_zfill(void* smem, const void* gmem, bool valid) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  const int n = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sa), "l"(gmem), "r"(n));
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
@@ -88,25 +94,33 @@ struct GemmParams {
   const double* D1; const double* D2; int ldd; long long sD; double* out; int out_stride;
 };
 
-constexpr int kBK = 16;
+constexpr int kBK = 32;
 constexpr int kPad = 4;  // row stride kBK+kPad doubles: (4r + c) mod 16 distinct over a DMMA fragment
 
 // C tile BM x BN per CTA, 4 warps as 2 x 2, each warp (BM/2) x (BN/2) in m8n8k4 tiles; the K loop streams
-// 16-wide slabs of A and B rows through a 2-stage cp.async pipeline.
+// 32-wide slabs of A and B rows through an ST-stage cp.async pipeline. The matrices of this path are small
+// (N = 401 at the headline configuration), so a CTA's K loop is a chain of L2 round trips unless ST - 1 tiles
+// (~100 k-columns) are in flight.
 // Contract: rows of A and B are zero-padded up to a multiple of 16 columns (every dense buffer of this
-// library has ld % 16 == 0 and zero pads), so the K loop needs no column guards; row indices past M / N are
-// clamped (their results are discarded by the epilogue).
-template <int BM, int BN, int MODE>
+// library has ld % 16 == 0 and zero pads), so the K loop needs no column guards below roundup16(K) (the last
+// half tile is zero-filled); row indices past M / N are clamped (their results are discarded by the epilogue).
+template <int BM, int BN, int ST>
+constexpr size_t gemm_smem_bytes() { return sizeof(double) * ST * (BM + BN) * (kBK + kPad); }
+
+template <int BM, int BN, int MODE, int ST>
 __global__ void __launch_bounds__(128) gemm_nt_kernel(GemmParams p) {
   constexpr int FM = BM / 16, FN = BN / 16;  // fragments per warp per dimension
-  __shared__ __align__(16) double As[2][BM][kBK + kPad];
-  __shared__ __align__(16) double Bs[2][BN][kBK + kPad];
+  constexpr int LDT = kBK + kPad;
+  extern __shared__ __align__(16) double gsm[];
+  double* As = gsm;                       // [ST][BM][LDT]
+  double* Bs = gsm + ST * BM * LDT;       // [ST][BN][LDT]
   const int z = blockIdx.z;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wm = (warp >> 1) * (BM / 2), wn = (warp & 1) * (BN / 2);
   const double* A = p.A + z * p.sA;
   const double* B = p.B + z * p.sB;
+  const int K16 = (p.K + 15) & ~15;
 
   double acc[FM][FN][2];
 #pragma unroll
@@ -119,41 +133,46 @@ __global__ void __launch_bounds__(128) gemm_nt_kernel(GemmParams p) {
     for (int c = tid; c < BM * (kBK / 2); c += 128) {
       const int r = c / (kBK / 2), c2 = (c % (kBK / 2)) * 2;
       const int gr = min(m0 + r, p.M - 1);
-      cp_async16(&As[st][r][c2], A + (size_t)gr * p.lda + k0 + c2);
+      const bool ok = k0 + c2 < K16;
+      cp_async16_zfill(As + (st * BM + r) * LDT + c2, A + (size_t)gr * p.lda + (ok ? k0 + c2 : 0), ok);
     }
 #pragma unroll
     for (int c = tid; c < BN * (kBK / 2); c += 128) {
       const int r = c / (kBK / 2), c2 = (c % (kBK / 2)) * 2;
       const int gr = min(n0 + r, p.N - 1);
-      cp_async16(&Bs[st][r][c2], B + (size_t)gr * p.ldb + k0 + c2);
+      const bool ok = k0 + c2 < K16;
+      cp_async16_zfill(Bs + (st * BN + r) * LDT + c2, B + (size_t)gr * p.ldb + (ok ? k0 + c2 : 0), ok);
     }
-    cp_async_commit();
   };
 
   const int nk = (p.K + kBK - 1) / kBK;
-  load_tile(0, 0);
+#pragma unroll
+  for (int s = 0; s < ST - 1; ++s) {
+    if (s < nk) load_tile(s, s * kBK);
+    cp_async_commit();
+  }
   for (int kt = 0; kt < nk; ++kt) {
-    const int st = kt & 1;
-    if (kt + 1 < nk) {
-      load_tile(st ^ 1, (kt + 1) * kBK);
-      cp_async_wait<1>();
-    } else {
-      cp_async_wait<0>();
+    cp_async_wait<ST - 2>();   // tile kt has landed
+    __syncthreads();           // ... for everyone, and everyone is done with tile kt - 1 (its stage is refilled now)
+    {
+      const int nx = kt + ST - 1;
+      if (nx < nk) load_tile(nx % ST, nx * kBK);
+      cp_async_commit();
     }
-    __syncthreads();
+    const double* at = As + (kt % ST) * BM * LDT;
+    const double* bt = Bs + (kt % ST) * BN * LDT;
 #pragma unroll
     for (int kk = 0; kk < kBK; kk += 4) {
       double af[FM], bf[FN];
 #pragma unroll
-      for (int i = 0; i < FM; ++i) af[i] = As[st][wm + 8 * i + (lane >> 2)][kk + (lane & 3)];
+      for (int i = 0; i < FM; ++i) af[i] = at[(wm + 8 * i + (lane >> 2)) * LDT + kk + (lane & 3)];
 #pragma unroll
-      for (int j = 0; j < FN; ++j) bf[j] = Bs[st][wn + 8 * j + (lane >> 2)][kk + (lane & 3)];
+      for (int j = 0; j < FN; ++j) bf[j] = bt[(wn + 8 * j + (lane >> 2)) * LDT + kk + (lane & 3)];
 #pragma unroll
       for (int i = 0; i < FM; ++i)
 #pragma unroll
         for (int j = 0; j < FN; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
     }
-    __syncthreads();
   }
 
   double t1 = 0, t2 = 0, t0 = 0;
@@ -218,16 +237,29 @@ __global__ void __launch_bounds__(128) gemm_nt_kernel(GemmParams p) {
   }
 }
 
+template <int BM, int BN, int MODE, int ST>
+static void launch_gemm_cfg(cudaStream_t s, const GemmParams& p, dim3 grd) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(gemm_nt_kernel<BM, BN, MODE, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)gemm_smem_bytes<BM, BN, ST>());
+    attr_set = true;
+  }
+  gemm_nt_kernel<BM, BN, MODE, ST><<<grd, 128, gemm_smem_bytes<BM, BN, ST>(), s>>>(p);
+}
+
 template <int MODE>
 static void launch_gemm(cudaStream_t s, const GemmParams& p, int Z, long long* launches) {
-  // small problems: 32 x 64 CTA tiles so that more SMs take part
+  // The DMMA pipe of one SM sustains ~250 GFLOP/s, so a CTA tile is a fixed amount of serial time (BM * BN * K * 2 flop
+  // at that rate): small problems get small tiles so that the work spreads over all 148 SMs in near-equal shares.
   const long long ctas64 = (long long)((p.M + 63) / 64) * ((p.N + 63) / 64) * Z;
+  const long long ctas32 = (long long)((p.M + 31) / 32) * ((p.N + 63) / 64) * Z;
   if (ctas64 >= 2 * 148) {
-    dim3 grd((p.N + 63) / 64, (p.M + 63) / 64, Z);
-    gemm_nt_kernel<64, 64, MODE><<<grd, 128, 0, s>>>(p);
+    launch_gemm_cfg<64, 64, MODE, 3>(s, p, dim3((p.N + 63) / 64, (p.M + 63) / 64, Z));   // 108 KB: 2 CTAs / SM
+  } else if (ctas32 >= 2 * 148) {
+    launch_gemm_cfg<32, 64, MODE, 4>(s, p, dim3((p.N + 63) / 64, (p.M + 31) / 32, Z));   // 108 KB
   } else {
-    dim3 grd((p.N + 63) / 64, (p.M + 31) / 32, Z);
-    gemm_nt_kernel<32, 64, MODE><<<grd, 128, 0, s>>>(p);
+    launch_gemm_cfg<16, 32, MODE, 4>(s, p, dim3((p.N + 31) / 32, (p.M + 15) / 16, Z));   // 54 KB: 4 CTAs / SM
   }
   if (launches) ++*launches;
 }

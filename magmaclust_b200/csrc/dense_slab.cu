@@ -23,7 +23,10 @@ namespace mcb {
 __device__ long long g_slab_prof[64][12];
 #define SLAB_T(slot) do { if (tid == 0 && z == 0 && b < 64 && I == (b + 1) % nblk) g_slab_prof[b][slot] = clock64(); } while (0)
 #define SLAB_TP(slot) do { if (tid == 0 && z == 0 && b < 64 && I == b) g_slab_prof[b][slot] = clock64(); } while (0)
+__device__ long long g_slab_prof2[64][12];  // a trailing-update CTA (I = b + 2)
+#define SLAB_TO(slot) do { if (tid == 0 && z == 0 && b < 64 && I == (b + 2) % nblk) g_slab_prof2[b][slot] = clock64(); } while (0)
 #else
+#define SLAB_TO(slot)
 #define SLAB_T(slot)
 #define SLAB_TP(slot)
 #endif
@@ -150,6 +153,7 @@ spd_inverse_slab_kernel(double* __restrict__ Aall, int N, int ld, long long stri
 
     // ---- phase 2: V_I = R L^-T, P_I = V L^-1 -------------------------------------------------------------
     SLAB_T(1);
+    SLAB_TO(1);
     for (int e = tid; e < kNB * kNB; e += kSlabThreads) {
       const int r = e >> 5, c = e & 31;
       Ls[r * kLp + c] = __ldcg(Lg + e);
@@ -185,9 +189,11 @@ spd_inverse_slab_kernel(double* __restrict__ Aall, int N, int ld, long long stri
       Pg[(size_t)(r0 + r) * kNB + c] = Ps[r * kLp + c];
     }
     SLAB_T(2);
+    SLAB_TO(2);
     arrivals += nblk;
     slab_barrier(counter, arrivals);
     SLAB_T(3);
+    SLAB_TO(3);
 
     // ---- phase 3 --------------------------------------------------------------------------------------
     if (I == b + 1) {
@@ -210,9 +216,9 @@ spd_inverse_slab_kernel(double* __restrict__ Aall, int N, int ld, long long stri
         Rs[r * kLp + c + 1] = (r < nb1 && c + 1 < nb1) ? cp[1] - n1 : (r == c + 1 ? 1.0 : 0.0);
       }
       __syncthreads();
-      SLAB_TP(4);
+      SLAB_T(4);
       factor_block(b + 1, false);
-      SLAB_TP(5);
+      SLAB_T(5);
     } else if (I != b) {
       // trailing update of the slab. Each warp owns the 8-column tiles tj = warp, warp + 8, ...; ALL its B
       // fragments (rows of V_J, straight from L2) are requested up front so that one L2 latency covers the whole
@@ -270,7 +276,8 @@ spd_inverse_slab_kernel(double* __restrict__ Aall, int N, int ld, long long stri
       }
     }
     __syncthreads();
-    SLAB_TP(7);
+    SLAB_T(7);
+    SLAB_TO(7);
     if (b + 1 < nblk) {
       arrivals += nblk;
       slab_barrier(counter, arrivals);

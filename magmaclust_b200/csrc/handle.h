@@ -53,6 +53,11 @@ struct mcb_handle {
   std::vector<int> csum_gmap;
   struct EvalGraph { cudaGraphExec_t exec; long long kernels; };
   std::map<int, EvalGraph> eval_graphs;   // captured evaluation sequences, keyed by (G, want_grad, resident)
+  // device-driven theta_k optimisation (common theta_k): a WHILE graph whose body is one objective evaluation
+  cudaGraphExec_t mopt_exec = nullptr;
+  long long mopt_pre = 0, mopt_body = 0;  // kernels before the loop / per evaluation
+  mcb::DevBuf<double> mopt_state;         // the L-BFGS state (Lbfgs struct) + result slots
+  cudaStream_t st_cap = nullptr;          // capture-only stream for conditional-node bodies
   mcb::DenseWs ws;
   mcb::DevBuf<int> info;
   mcb::DevBuf<double> scal;        // small device scalars

@@ -19,11 +19,15 @@ int main() {
   }
   long long prof[64][12];
   cudaMemcpyFromSymbol(prof, g_slab_prof, sizeof prof);
-  printf("step: other-CTA [ph1wait bar | ph2 | bar | ph3+..]   pivot-CTA [ph1 | ... | ph3]\n");
-  for (int b = 0; b < 13; ++b)
-    printf("b=%2d  wait+barA %6lld  ph2 %6lld  barB %6lld | pivot: ph1 %6lld  to_barB_done %6lld  ph3 %6lld\n", b,
-           prof[b][1] - prof[b][0], prof[b][2] - prof[b][1], prof[b][3] - prof[b][2], prof[b][5] - prof[b][4],
-           prof[b][6] - prof[b][5], prof[b][7] - prof[b][6]);
-  for (int b = 0; b < 3; ++b) printf("b=%d ph1 detail: init %lld loop %lld log %lld tail %lld\n", b, prof[b][8]-prof[b][4], prof[b][9]-prof[b][8], prof[b][10]-prof[b][9], prof[b][5]-prof[b][10]);
+  printf("lookahead CTA (I = b + 1) timeline, cycles: ph2 | barrier B | diag update | factor32 | rest of ph3 | barrier A (to next ph2)\n");
+  for (int b = 0; b < 12; ++b)
+    printf("b=%2d  ph2 %6lld  barB %6lld  upd %6lld  factor %6lld  rest %6lld  barA %6lld | step %6lld\n", b,
+           prof[b][2] - prof[b][1], prof[b][3] - prof[b][2], prof[b][4] - prof[b][3], prof[b][5] - prof[b][4],
+           prof[b][7] - prof[b][5], prof[b + 1][1] - prof[b][7], prof[b + 1][1] - prof[b][1]);
+  long long prof2[64][12];
+  cudaMemcpyFromSymbol(prof2, g_slab_prof2, sizeof prof2);
+  printf("trailing-update CTA (I = b + 2): ph2 | barrier B | ph3\n");
+  for (int b = 0; b < 11; ++b)
+    printf("b=%2d  ph2 %6lld  barB %6lld  ph3 %6lld\n", b, prof2[b][2] - prof2[b][1], prof2[b][3] - prof2[b][2], prof2[b][7] - prof2[b][3]);
   return 0;
 }
