@@ -588,7 +588,7 @@ static int eval_mean_groups(mcb_handle* h, int G, const double* theta_h, const i
   if (no_graph) {
     MCB_TRY(eval_mean_enqueue(h, G, want_grad, use_resident, refresh_csum));
   } else {
-    const int key = (((G * 2 + (want_grad ? 1 : 0)) * 2 + (use_resident ? 1 : 0)) * 2 + (refresh_csum ? 1 : 0));
+    const int key = ((((h->ws.max_ctas * 64 + G) * 2 + (want_grad ? 1 : 0)) * 2 + (use_resident ? 1 : 0)) * 2 + (refresh_csum ? 1 : 0));
     auto it = h->eval_graphs.find(key);
     if (it == h->eval_graphs.end()) {
       cudaGraph_t graph = nullptr;
@@ -952,7 +952,12 @@ static int build_mean_opt_graph(mcb_handle* h) {
 // Runs the whole optimisation; out[0..2] = theta, nfev / iterations returned through the pointers. Enqueue only when
 // !wait (the caller synchronises h->st later and then calls with collect = true).
 static int mean_opt_launch(mcb_handle* h) {
+  if (h->mopt_exec && h->mopt_budget != h->ws.max_ctas) {  // captured with another SM budget
+    cudaGraphExecDestroy(h->mopt_exec);
+    h->mopt_exec = nullptr;
+  }
   if (!h->mopt_exec) MCB_TRY(build_mean_opt_graph(h));
+  h->mopt_budget = h->ws.max_ctas;
   H_CUDA(cudaGraphLaunch(h->mopt_exec, h->st));
   h->csum_valid = true;
   h->csum_gmap.assign(h->K, 0);
@@ -1046,9 +1051,15 @@ static int m_step_impl(mcb_handle* h, int common_hp_k, int common_hp_i, int* sta
     H_CUDA(cudaStreamWaitEvent(h->st2, h->ev_fork, 0));
     {
       PhaseScope ps(h, PH_MSTEP_I, h->st2);
+      // SMs left to the theta_k chain: one per CTA of the slab inverse (they must be co-resident), i.e. two column
+      // parts per 32-row slab when that stays below ~a quarter of the GPU; the GEMMs / reductions between two
+      // inverses share the same SMs
       const int nblk = (h->N + kNB - 1) / kNB;
+      static const int extra = getenv("MCB_RESERVE_EXTRA") ? atoi(getenv("MCB_RESERVE_EXTRA")) : -1;
+      const int reserve = extra >= 0 ? std::min(nblk + extra, 96) : (2 * nblk <= 40 ? 2 * nblk : nblk);
       H_CUDA(launch_indiv_mstep(h->st2, h->idata(), M, h->nmax, h->iwork(), h->theta_i.p, h->theta_i_new.p, 100,
-                                h->nfev_i.p, h->niter_i.p, h->status_i.p, h->mstep_ctl.p, nblk, order));
+                                h->nfev_i.p, h->niter_i.p, h->status_i.p, h->mstep_ctl.p, reserve, order));
+      h->ws.max_ctas = reserve;   // what the slab inverse may count on while that kernel runs
       h->nfev_valid = true;
       ++h->launches;
     }
@@ -1086,6 +1097,7 @@ static int m_step_impl(mcb_handle* h, int common_hp_k, int common_hp_i, int* sta
       if (overlap) {
         // join the theta_i stream, then pen_diag = mean_i theta_i[3]
         H_CUDA(cudaStreamWaitEvent(h->st, h->ev_join, 0));
+        h->ws.max_ctas = 0;
         MCB_TRY(compute_pen_diag(h, &pen_diag));
       }
       for (int k = 0; k < K; ++k) {

@@ -65,8 +65,9 @@ constexpr int kNB = 32;  // pivot block of the blocked symmetric sweep
 struct DenseWs {
   DevBuf<double> Pbuf, Cold;  // [Z][Npad][kNB] panels of the blocked sweep
   DevBuf<double> red;         // scratch for reductions
-  DevBuf<double> slabV, slabP, slabL;  // panel exchange buffers of the persistent slab inverse (double-buffered)
-  DevBuf<unsigned> bar;                // its per-matrix barrier counters
+  DevBuf<double> slabV, slabP, slabL;  // panel exchange buffers of the persistent slab inverse (V, P triple-buffered)
+  DevBuf<unsigned> bar;                // its per-matrix arrival counter and published-block flag
+  int max_ctas = 0;                    // SMs the slab inverse may count on (0: all); see spd_inverse_slab
 };
 
 // K[z] = SE covariance on `grid` with theta[z] = (a, b, sigma): exp(a - exp(-b)/2 d^2) off-diagonal,

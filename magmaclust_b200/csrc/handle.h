@@ -55,6 +55,7 @@ struct mcb_handle {
   std::map<int, EvalGraph> eval_graphs;   // captured evaluation sequences, keyed by (G, want_grad, resident)
   // device-driven theta_k optimisation (common theta_k): a WHILE graph whose body is one objective evaluation
   cudaGraphExec_t mopt_exec = nullptr;
+  int mopt_budget = 0;                    // ws.max_ctas it was captured with
   long long mopt_pre = 0, mopt_body = 0;  // kernels before the loop / per evaluation
   mcb::DevBuf<double> mopt_state;         // the L-BFGS state (Lbfgs struct) + result slots
   cudaStream_t st_cap = nullptr;          // capture-only stream for conditional-node bodies
