@@ -17,6 +17,7 @@
 #include "indiv.cuh"
 #include "lbfgs.h"
 #include "indiv_eval.cuh"
+#include "indiv_eval2.cuh"
 
 namespace mcb {
 
@@ -344,6 +345,100 @@ __global__ void __launch_bounds__(TT) indiv_mstep_kernel(IndivData dd, IndivWork
   }
 }
 
+// ---- second design of the evaluator (indiv_eval2.cuh): same contracts as the two kernels above -------------------
+template <int E, int TT, int NT>
+__global__ void __launch_bounds__(TT, (E > 1 ? 256 : 512) / TT) indiv_eval2_kernel(IndivData dd, IndivWork w, int nmax,
+                                                                   const double* __restrict__ theta, int theta_stride,
+                                                                   int want_grad, double* __restrict__ f,
+                                                                   double* __restrict__ g, double* __restrict__ sum4,
+                                                                   int* __restrict__ info) {
+  extern __shared__ __align__(16) double sm[];
+  __shared__ double out[4];
+  const int i = blockIdx.x;
+  const int o0 = dd.off[i], n = dd.off[i + 1] - o0;
+  EvalSm2<NT> s = eval2_carve<NT>(sm);
+  eval2_load<TT, NT>(s, n, dd.t + o0, dd.y + o0, w.c1 + o0, w.c2 + dd.woff[i]);
+  int bI[E], bJ[E];
+  eval2_decode<E, TT>(n, bI, bJ);
+  const double* th = theta + (size_t)i * theta_stride;
+  indiv_eval_v2<E, TT, NT>(s, n, bI, bJ, th[0], th[1], th[2], want_grad != 0, out, info, i);
+  if (threadIdx.x == 0) {
+    if (f) f[i] = out[0];
+    if (g && want_grad) { g[3 * i] = out[1]; g[3 * i + 1] = out[2]; g[3 * i + 2] = out[3]; }
+    if (sum4) {
+      atomicAdd(sum4, out[0]);
+      if (want_grad) { atomicAdd(sum4 + 1, out[1]); atomicAdd(sum4 + 2, out[2]); atomicAdd(sum4 + 3, out[3]); }
+    }
+  }
+}
+
+template <int E, int TT, int NT>
+__global__ void __launch_bounds__(TT, (E > 1 ? 256 : 512) / TT) indiv_mstep2_kernel(IndivData dd, IndivWork w, int nmax, int M,
+                                                                    const double* __restrict__ theta0,
+                                                                    double* __restrict__ theta_out, int maxit,
+                                                                    int* __restrict__ nfev, int* __restrict__ niter,
+                                                                    int* __restrict__ status, int* __restrict__ ctl,
+                                                                    int reserve, const int* __restrict__ order) {
+  extern __shared__ __align__(16) double sm[];
+  __shared__ double out[4];
+  __shared__ Lbfgs opt;
+  __shared__ int st, cur;
+  if (threadIdx.x == 0) {
+    int role = 1;
+    if (reserve > 0) {
+      unsigned smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      int* flag = ctl + 2 + (smid & 1023);
+      const int old = atomicCAS(flag, 0, 3);
+      if (old == 0) {
+        role = (atomicAdd(ctl + 1, 1) < reserve) ? 2 : 1;
+        __threadfence();
+        atomicExch(flag, role);
+      } else {
+        role = old;
+        while (role == 3) role = *((volatile int*)flag);
+      }
+    }
+    cur = (role == 2) ? -1 : 0;
+  }
+  tsync<TT>();
+  if (cur < 0) return;
+  EvalSm2<NT> s = eval2_carve<NT>(sm);
+  int bad = 0;
+  for (;;) {
+    tsync<TT>();
+    if (threadIdx.x == 0) cur = atomicAdd(ctl, 1);
+    tsync<TT>();
+    if (cur >= M) break;
+    const int slot = cur;
+    const int i = order ? order[slot] : slot;  // longest-expected-first order when the previous M-step's counts exist
+    const int o0 = dd.off[i], n = dd.off[i + 1] - o0;
+    eval2_load<TT, NT>(s, n, dd.t + o0, dd.y + o0, w.c1 + o0, w.c2 + dd.woff[i]);
+    int bI[E], bJ[E];
+    eval2_decode<E, TT>(n, bI, bJ);
+    if (threadIdx.x == 0) {
+      lb_init(opt, 3, theta0 + 3 * (size_t)i, maxit);
+      st = LB_EVAL;
+    }
+    tsync<TT>();
+    while (true) {
+      const double a = opt.x[0], b = opt.x[1], c = opt.x[2];
+      indiv_eval_v2<E, TT, NT>(s, n, bI, bJ, a, b, c, true, out, &bad, slot);
+      if (threadIdx.x == 0) st = lb_advance(opt, out[0], out + 1);
+      tsync<TT>();
+      if (st != LB_EVAL) break;
+    }
+    if (threadIdx.x == 0) {
+      theta_out[3 * (size_t)i] = opt.x[0];
+      theta_out[3 * (size_t)i + 1] = opt.x[1];
+      theta_out[3 * (size_t)i + 2] = opt.x[2];
+      nfev[i] = opt.nfev;
+      niter[i] = opt.iter;
+      status[i] = st;
+    }
+  }
+}
+
 // -------------------------------------------------------------------------------------------------
 // host launchers
 // -------------------------------------------------------------------------------------------------
@@ -420,9 +515,47 @@ static void eval_shape(int nmax, int* TT, int* E) {
     }                                                  \
   } while (0)
 
+// second design: TT = 64 while the lower block triangle fits 64 threads, else 128 (E = 2 above n = 56); NT = tile bucket
+static bool eval2_shape(int nmax, int* TT, int* E, int* NT) {
+  static const bool v1 = getenv("MCB_EVAL_V1") != nullptr;
+  if (v1 || nmax > 80) return false;
+  const int nbk = (nmax + 2 + 3) / 4, nblk = nbk * (nbk + 1) / 2;
+  *TT = (nblk <= 64) ? 64 : 128;
+  *E = (nblk + *TT - 1) / *TT;
+  *NT = (nmax <= 32) ? 4 : (nmax <= 56 ? 7 : 10);
+  return true;
+}
+static size_t eval2_smem_bytes(int NT) {
+  return sizeof(double) * (size_t)(NT == 4 ? Eval2Geo<4>::DOUBLES : NT == 7 ? Eval2Geo<7>::DOUBLES : Eval2Geo<10>::DOUBLES);
+}
+
+#define MCB_DISPATCH_EVAL2(MACRO)                                   \
+  do {                                                              \
+    if (TT == 64 && E == 1 && NT == 4) MACRO(1, 64, 4);             \
+    else if (TT == 64 && E == 1 && NT == 7) MACRO(1, 64, 7);        \
+    else if (TT == 128 && E == 1 && NT == 7) MACRO(1, 128, 7);      \
+    else if (TT == 128 && E == 2 && NT == 10) MACRO(2, 128, 10);    \
+    else return cudaErrorInvalidValue;                              \
+  } while (0)
+
 cudaError_t launch_indiv_eval(cudaStream_t s, const IndivData& dd, int M, int nmax, const IndivWork& w,
                               const double* theta, int theta_stride, int want_grad, double* f, double* g,
                               double* sum4, int* info) {
+  {
+    int TT, E, NT;
+    if (eval2_shape(nmax, &TT, &E, &NT)) {
+      const size_t sm2 = eval2_smem_bytes(NT);
+      cudaError_t e;
+#define MCB_LAUNCH_EVAL2(EE, T_, N_)                                                                                   \
+  do {                                                                                                                 \
+    if ((e = set_smem_t(indiv_eval2_kernel<EE, T_, N_>, sm2)) != cudaSuccess) return e;                                \
+    indiv_eval2_kernel<EE, T_, N_><<<M, T_, sm2, s>>>(dd, w, nmax, theta, theta_stride, want_grad, f, g, sum4, info);  \
+  } while (0)
+      MCB_DISPATCH_EVAL2(MCB_LAUNCH_EVAL2);
+#undef MCB_LAUNCH_EVAL2
+      return cudaGetLastError();
+    }
+  }
   const size_t sm = eval_smem_bytes(nmax);
   int TT, E;
   eval_shape(nmax, &TT, &E);
@@ -448,6 +581,27 @@ cudaError_t launch_indiv_mstep(cudaStream_t s, const IndivData& dd, int M, int n
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   if ((e = cudaMemsetAsync(ctl, 0, sizeof(int) * (2 + 1024), s)) != cudaSuccess) return e;
+  {
+    int NT;
+    if (eval2_shape(nmax, &TT, &E, &NT)) {
+      const size_t sm2 = eval2_smem_bytes(NT);
+#define MCB_LAUNCH_MSTEP2(EE, T_, N_)                                                                                  \
+  do {                                                                                                                 \
+    if ((e = set_smem_t(indiv_mstep2_kernel<EE, T_, N_>, sm2)) != cudaSuccess) return e;                               \
+    int per_sm = 1;                                                                                                    \
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, indiv_mstep2_kernel<EE, T_, N_>, T_, sm2);                  \
+    if (per_sm < 1) per_sm = 1;                                                                                        \
+    int grid = per_sm * sms;                                                                                           \
+    if (grid > M && reserve_sms == 0) grid = M;                                                                        \
+    indiv_mstep2_kernel<EE, T_, N_><<<grid, T_, sm2, s>>>(dd, w, nmax, M, theta0, theta_out, maxit, nfev, niter,       \
+                                                          status, ctl, reserve_sms, order);                            \
+  } while (0)
+      MCB_DISPATCH_EVAL2(MCB_LAUNCH_MSTEP2);
+#undef MCB_LAUNCH_MSTEP2
+      return cudaGetLastError();
+    }
+    eval_shape(nmax, &TT, &E);
+  }
 #define MCB_LAUNCH_MSTEP(EE, T_)                                                                                  \
   do {                                                                                                            \
     if ((e = set_smem_t(indiv_mstep_kernel<EE, T_>, sm)) != cudaSuccess) return e;                                \

@@ -17,6 +17,21 @@
 #pragma once
 #include "common.cuh"
 
+#ifdef MCB_PROF
+// phase profile of indiv_eval_v1 (tools/dbg/eval_prof.cu): thread 0 accumulates clock64 deltas per phase
+__device__ long long g_eval_prof[16];
+#define MCB_STAMP(k)                                    \
+  do {                                                  \
+    if (threadIdx.x == 0 && blockIdx.x == 0) {          \
+      const long long now_ = clock64();                 \
+      g_eval_prof[k] += now_ - prof_t_;                 \
+      prof_t_ = now_;                                   \
+    }                                                   \
+  } while (0)
+#else
+#define MCB_STAMP(k) do {} while (0)
+#endif
+
 namespace mcb {
 
 constexpr int kT = 128;  // threads per CTA of the E-step kernels (indiv.cu)
@@ -137,6 +152,9 @@ __device__ void indiv_eval_v1(const EvalSm& s, int n, double th1, double th2, do
   const double e1 = exp(th1);
   const double dg = e1 + sg * sg;
 
+#ifdef MCB_PROF
+  long long prof_t_ = clock64();
+#endif
   int bI[E], bJ[E];
   double blk[E][4][4], k0[E][4][4];
 #pragma unroll
@@ -187,6 +205,7 @@ __device__ void indiv_eval_v1(const EvalSm& s, int n, double th1, double th2, do
     }
   }
 
+  MCB_STAMP(0);
   // ---- B: sweep -----------------------------------------------------------------------------------
   auto publish = [&](int kb, int kk, double* buf) {
     // column k = 4 kb + kk of the current symmetric matrix -> buf[0..ntot4), buf[ntot4] = 1 / pivot
@@ -269,6 +288,7 @@ __device__ void indiv_eval_v1(const EvalSm& s, int n, double th1, double th2, do
     }
   }
 
+  MCB_STAMP(1);
   // ---- W, p, q to shared memory; block-layout partial sums ----------------------------------------------
   // borders after the sweep: A[r][n] = p_r = (W y)_r, A[r][n+1] = q_r = (W c1)_r, A[n][n] = -y'Wy, A[n][n+1] = -y'Wc1
   double* pv = s.col[0];            // p
@@ -344,6 +364,7 @@ __device__ void indiv_eval_v1(const EvalSm& s, int n, double th1, double th2, do
     if (!(d > 0.0)) *bad = 1;
   }
 
+  MCB_STAMP(2);
   if (want_grad) {
     // ---- C: X = W S (np8 x np8, DMMA) -------------------------------------------------------------
     const int nt = (n + 7) >> 3;   // 8-wide tiles
@@ -378,6 +399,7 @@ __device__ void indiv_eval_v1(const EvalSm& s, int n, double th1, double th2, do
       }
     }
     tsync<TT>();
+    MCB_STAMP(3);
     // ---- D: H = X W on the lower tile triangle, reduced on the fly -----------------------------------
     {
       int u = 0;
@@ -421,7 +443,9 @@ __device__ void indiv_eval_v1(const EvalSm& s, int n, double th1, double th2, do
       }
     }
   }
+  MCB_STAMP(4);
   cta_sum_v<13, TT>(v13, s.red);
+  MCB_STAMP(5);
   if (tid == 0) {
     const double yWy = corner[0], yWc = corner[1];
     out[0] = 0.5 * ((double)n * kLog2Pi + v13[7] + yWy) - yWc + 0.5 * v13[0];
