@@ -825,6 +825,41 @@ extern "C" int mcb_bic_terms(mcb_handle* h, double out[3]) {
 // host path uses (lbfgs.h) and decides whether to iterate again. The host launches one graph and waits once.
 constexpr int kMoptWords = (int)((sizeof(Lbfgs) + 7) / 8);
 
+// MCB_TRACE_K=1 (debug): globaltimer stamps between the nodes of the loop body, printed per segment after the M-step
+static __device__ unsigned long long g_ktrace[8192];
+static __device__ unsigned g_ktrace_n;
+__global__ void ktrace_stamp_kernel(int tag) {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  const unsigned i = atomicAdd(&g_ktrace_n, 1u);
+  if (i < 4096) { g_ktrace[2 * i] = t; g_ktrace[2 * i + 1] = (unsigned long long)tag; }
+}
+static bool ktrace_on() {
+  static const bool on = getenv("MCB_TRACE_K") != nullptr;
+  return on;
+}
+static void ktrace_dump() {
+  static unsigned long long hostbuf[8192];
+  unsigned n = 0;
+  cudaMemcpyFromSymbol(&n, g_ktrace_n, sizeof n);
+  cudaMemcpyFromSymbol(hostbuf, g_ktrace, sizeof hostbuf);
+  if (n > 4096) n = 4096;
+  double sum[32] = {0};
+  int cnt[32] = {0};
+  for (unsigned i = 0; i + 1 < n; ++i) {
+    const int tag = (int)hostbuf[2 * i + 1];
+    if (tag < 0 || tag >= 32) continue;
+    sum[tag] += (double)(hostbuf[2 * i + 2] - hostbuf[2 * i]) * 1e-3;
+    ++cnt[tag];
+  }
+  fprintf(stderr, "[ktrace] segment after stamp: mean us (count)\n");
+  for (int t = 0; t < 32; ++t)
+    if (cnt[t]) fprintf(stderr, "[ktrace]   %2d: %8.2f (%d)\n", t, sum[t] / cnt[t], cnt[t]);
+  const unsigned zero = 0;
+  cudaMemcpyToSymbol(g_ktrace_n, &zero, sizeof zero);
+}
+#define KTRACE(s, tag) do { if (ktrace_on()) ktrace_stamp_kernel<<<1, 1, 0, s>>>(tag); } while (0)
+
 __global__ void mean_opt_init_kernel(const double* __restrict__ theta_k, double* state, double* etheta, int* egmap,
                                      int K) {
   if (threadIdx.x == 0) {
@@ -837,18 +872,20 @@ __global__ void mean_opt_init_kernel(const double* __restrict__ theta_k, double*
 
 // result: [0..2] theta, [3] nfev, [4] iterations, [5] evaluations that met a non-positive pivot
 __global__ void mean_opt_advance_kernel(double* state, const double* __restrict__ ered, const double* __restrict__ logdet,
-                                        int* info, double* etheta, int N, int K, cudaGraphConditionalHandle handle,
-                                        double* result) {
+                                        int* info, double* etheta, int N, int K, int fused,
+                                        cudaGraphConditionalHandle handle, double* result) {
   __shared__ double words[kMoptWords];
   for (int w = threadIdx.x; w < kMoptWords; w += blockDim.x) words[w] = state[w];
   __syncthreads();
   if (threadIdx.x == 0) {
     Lbfgs& o = *reinterpret_cast<Lbfgs*>(words);
-    const double* rg = ered;            // [G = 1][4]: sum Kinv.Csum, tr(Kinv D1), tr(Kinv D2), tr(Kinv)
-    const double* rz = ered + 4 * K;    // [K][4]:     r'p, p'p, p'D1 p, p'D2 p
-    const double* rt = ered + 8 * K;    // [1][4]:     tr(G D1), tr(G D2), tr(G)
+    // unfused layout: [G = 1][4] group sums, [K][4] per cluster r'p, p'p, p'D1 p, p'D2 p, [1][4] traces of G;
+    // fused layout (MeanFuse): the same three groups of four, the cluster sums already added up
+    const double* rg = ered;            // sum Kinv.Csum, tr(Kinv D1), tr(Kinv D2), tr(Kinv)
+    const double* rz = ered + (fused ? 4 : 4 * K);
+    const double* rt = ered + (fused ? 8 : 8 * K);   // tr(G D1), tr(G D2), tr(G)
     double q = 0, pp = 0, d1 = 0, d2 = 0;
-    for (int z = 0; z < K; ++z) { q += rz[4 * z]; pp += rz[4 * z + 1]; d1 += rz[4 * z + 2]; d2 += rz[4 * z + 3]; }
+    for (int z = 0; z < (fused ? 1 : K); ++z) { q += rz[4 * z]; pp += rz[4 * z + 1]; d1 += rz[4 * z + 2]; d2 += rz[4 * z + 3]; }
     double f = 0.5 * K * ((double)N * kLog2Pi + logdet[0]) + 0.5 * q + 0.5 * rg[0];
     double g[3];
     const double sg = o.x[2];
@@ -915,18 +952,48 @@ static int build_mean_opt_graph(mcb_handle* h) {
     if ((ce = cudaStreamBeginCaptureToGraph(h->st_cap, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal)) != cudaSuccess)
       return fail("body capture", ce);
     cudaStream_t s = h->st_cap;
-    se_build(s, h->eK.p, h->eD1.p, h->eD2.p, N, ld, sN, h->grid.p, h->etheta.p, 3, 1, &h->launches);
-    cudaError_t ie = spd_inverse(s, h->eK.p, N, ld, sN, 1, h->elogdet.p, h->info.p, h->ws, &h->launches);
-    symv_mapped(s, N, ld, sN, h->eK.p, h->egmap.p, h->rvec.p, h->pz.p, K, &h->launches);
-    double* redg = h->ered.p;
-    double* redz = redg + 4 * K;
-    double* redt = redz + 4 * K;
-    cudaMemsetAsync(h->ered.p, 0, sizeof(double) * 12 * K, s);
-    group_reduce(s, N, ld, sN, h->eK.p, h->eCsum.p, sN, h->eD1.p, h->eD2.p, redg, 1, &h->launches);
-    cluster_reduce(s, N, ld, sN, h->rvec.p, h->pz.p, h->eD1.p, h->eD2.p, h->egmap.p, redz, K, &h->launches);
-    gemm_nt(s, N, N, N, h->eK.p, ld, sN, h->eCsum.p, ld, sN, h->eX.p, ld, sN, 1.0, 0.0, 1, &h->launches);
-    gemm_nt_trace(s, N, h->eX.p, ld, sN, h->eK.p, ld, sN, h->eD1.p, h->eD2.p, ld, sN, redt, 4, 1, &h->launches);
-    mean_opt_advance_kernel<<<1, 32, 0, s>>>(state, h->ered.p, h->elogdet.p, h->info.p, h->etheta.p, N, K, handle, result);
+    static const bool unfused = getenv("MCB_MEAN_UNFUSED") != nullptr;
+    const bool fused = !unfused && K <= 8 && spd_inverse_slab_ok(N, ld);
+    cudaError_t ie = cudaSuccess;
+    if (fused) {
+      // four kernels per evaluation: build (+ clears the accumulators), slab inverse, two GEMM stages carrying the
+      // reductions. ered: [0..3] group sums, [4..7] cluster sums (all clusters together), [8..10] traces
+      if ((ie = spd_inverse_slab_reserve(h->ws, N, 1)) == cudaSuccess) {
+        ZeroJob zj{h->ered.p, 12 * K, h->elogdet.p, 1, h->pz.p, K * ld, slab_sync_words(h->ws), 2};
+        KTRACE(s, 0);
+        se_build(s, h->eK.p, h->eD1.p, h->eD2.p, N, ld, sN, h->grid.p, h->etheta.p, 3, 1, &h->launches, &zj);
+        KTRACE(s, 1);
+        ie = spd_inverse_slab(s, h->eK.p, N, ld, sN, 1, h->elogdet.p, h->info.p, h->ws, &h->launches, true);
+        MeanFuse mf{K, ld, h->rvec.p, h->pz.p, h->ered.p};
+        KTRACE(s, 2);
+        mean_stage1(s, N, h->eK.p, h->eCsum.p, h->eX.p, ld, h->eD1.p, h->eD2.p, mf, &h->launches);
+        KTRACE(s, 3);
+        mean_stage2(s, N, h->eX.p, h->eK.p, ld, h->eD1.p, h->eD2.p, mf, &h->launches);
+        KTRACE(s, 7);
+      }
+    } else {
+      KTRACE(s, 0);
+      se_build(s, h->eK.p, h->eD1.p, h->eD2.p, N, ld, sN, h->grid.p, h->etheta.p, 3, 1, &h->launches);
+      KTRACE(s, 1);
+      ie = spd_inverse(s, h->eK.p, N, ld, sN, 1, h->elogdet.p, h->info.p, h->ws, &h->launches);
+      KTRACE(s, 2);
+      symv_mapped(s, N, ld, sN, h->eK.p, h->egmap.p, h->rvec.p, h->pz.p, K, &h->launches);
+      double* redg = h->ered.p;
+      double* redz = redg + 4 * K;
+      double* redt = redz + 4 * K;
+      cudaMemsetAsync(h->ered.p, 0, sizeof(double) * 12 * K, s);
+      KTRACE(s, 3);
+      group_reduce(s, N, ld, sN, h->eK.p, h->eCsum.p, sN, h->eD1.p, h->eD2.p, redg, 1, &h->launches);
+      KTRACE(s, 4);
+      cluster_reduce(s, N, ld, sN, h->rvec.p, h->pz.p, h->eD1.p, h->eD2.p, h->egmap.p, redz, K, &h->launches);
+      KTRACE(s, 5);
+      gemm_nt(s, N, N, N, h->eK.p, ld, sN, h->eCsum.p, ld, sN, h->eX.p, ld, sN, 1.0, 0.0, 1, &h->launches);
+      KTRACE(s, 6);
+      gemm_nt_trace(s, N, h->eX.p, ld, sN, h->eK.p, ld, sN, h->eD1.p, h->eD2.p, ld, sN, redt, 4, 1, &h->launches);
+      KTRACE(s, 7);
+    }
+    mean_opt_advance_kernel<<<1, 32, 0, s>>>(state, h->ered.p, h->elogdet.p, h->info.p, h->etheta.p, N, K, fused ? 1 : 0,
+                                             handle, result);
     ++h->launches;
     cudaError_t ee = cudaStreamEndCapture(s, nullptr);
     h->mopt_body = h->launches - b0;
@@ -965,6 +1032,7 @@ static int mean_opt_launch(mcb_handle* h) {
 }
 
 static void mean_opt_collect(mcb_handle* h, double theta[3], int* nfev, int* iters) {
+  if (ktrace_on()) ktrace_dump();
   const double* r = h->hbuf + 4096;
   theta[0] = r[0]; theta[1] = r[1]; theta[2] = r[2];
   *nfev = (int)r[3];

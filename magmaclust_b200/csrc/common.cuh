@@ -74,8 +74,32 @@ struct DenseWs {
 // exp(a) + sigma^2 on the diagonal (kern_to_cov, CF.R:61-86). Optionally also D2[z] = dK/db (deriv_hp2,
 // CF.R:441-446; zero diagonal). theta is a DEVICE pointer, theta_stride doubles between problems.
 // D1[z] = dK/da (deriv_hp1, CF.R:436-439: the kernel itself, diagonal exp(a) without the noise term).
+// zj (optional): buffers that block 0 clears on the way (accumulators of the kernels that follow in the same graph)
+struct ZeroJob {
+  double* d; int n_d;
+  double* d2; int n_d2;
+  double* d3; int n_d3;
+  unsigned* u; int n_u;
+};
 void se_build(cudaStream_t s, double* Kmat, double* D1, double* D2, int N, int ld, long long stride,
-              const double* grid, const double* theta, int theta_stride, int Z, long long* launches);
+              const double* grid, const double* theta, int theta_stride, int Z, long long* launches,
+              const ZeroJob* zj = nullptr);
+
+// Side jobs of the fused objective / gradient of a theta_k shared by all K clusters (logL_GP_mod_common_hp_k,
+// gr_GP_mod_common_hp_k, CF.R:250-278, 510-537), carried by the two GEMM stages so that one evaluation is four kernels.
+// red[0..3] = sum Kinv o Csum, tr(Kinv dK/da), tr(Kinv dK/db), tr Kinv; red[4..7] = sum_z (r'p, p'p, p'dK/da p,
+// p'dK/db p); red[8..10] = tr(G dK/da), tr(G dK/db), tr G with G = Kinv Csum Kinv. red must be zero on entry.
+struct MeanFuse {
+  int K;            // clusters
+  int ldp;          // stride of r and p
+  const double* r;  // [K][ldp] m_hat_k - m_k
+  double* p;        // [K][ldp] Kinv r_k (accumulated by stage 1: zero on entry; read by stage 2); K <= 8
+  double* red;      // [12]
+};
+void mean_stage1(cudaStream_t s, int N, const double* Kinv, const double* Csum, double* X, int ld, const double* D1,
+                 const double* D2, const MeanFuse& mf, long long* launches);
+void mean_stage2(cudaStream_t s, int N, const double* X, const double* Kinv, int ld, const double* D1, const double* D2,
+                 const MeanFuse& mf, long long* launches);
 
 // In-place inverse of Z symmetric positive definite matrices by a blocked symmetric sweep (block
 // Gauss-Jordan). logdet[z] (device) receives log det of the ORIGINAL matrix; *info (device int) is set
@@ -84,8 +108,10 @@ cudaError_t spd_inverse_reserve(DenseWs& ws, int N, int Z);  // pre-size the wor
 // dense_slab.cu: persistent shared-memory-resident variant for N <= 768 (chosen automatically by spd_inverse)
 bool spd_inverse_slab_ok(int N, int ld);
 cudaError_t spd_inverse_slab_reserve(DenseWs& ws, int N, int Z);
+// pre_zeroed: logdet[0..Z) and the 2 Z sync words (slab_sync_words) were cleared by the caller (no memset nodes)
 cudaError_t spd_inverse_slab(cudaStream_t s, double* A, int N, int ld, long long stride, int Z, double* logdet,
-                             int* info, DenseWs& ws, long long* launches);
+                             int* info, DenseWs& ws, long long* launches, bool pre_zeroed = false);
+unsigned* slab_sync_words(DenseWs& ws);
 cudaError_t spd_inverse(cudaStream_t s, double* A, int N, int ld, long long stride, int Z, double* logdet,
                         int* info, DenseWs& ws, long long* launches);
 

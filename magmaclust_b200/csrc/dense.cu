@@ -23,7 +23,15 @@ namespace mcb {
 // -------------------------------------------------------------------------------------------------
 __global__ void se_build_kernel(double* __restrict__ Kmat, double* __restrict__ D1, double* __restrict__ D2, int N, int ld,
                                 long long stride, const double* __restrict__ grid,
-                                const double* __restrict__ theta, int theta_stride) {
+                                const double* __restrict__ theta, int theta_stride, ZeroJob zj) {
+  if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
+    // side job of the fused theta_k evaluation: clear the accumulators that the following kernels add into
+    const int t = threadIdx.y * blockDim.x + threadIdx.x, nt = blockDim.x * blockDim.y;
+    for (int e = t; e < zj.n_d; e += nt) zj.d[e] = 0.0;
+    for (int e = t; e < zj.n_d2; e += nt) zj.d2[e] = 0.0;
+    for (int e = t; e < zj.n_d3; e += nt) zj.d3[e] = 0.0;
+    for (int e = t; e < zj.n_u; e += nt) zj.u[e] = 0u;
+  }
   const int z = blockIdx.z;
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   const int i = blockIdx.y * blockDim.y + threadIdx.y;
@@ -51,9 +59,10 @@ __global__ void se_build_kernel(double* __restrict__ Kmat, double* __restrict__ 
 }
 
 void se_build(cudaStream_t s, double* Kmat, double* D1, double* D2, int N, int ld, long long stride,
-              const double* grid, const double* theta, int theta_stride, int Z, long long* launches) {
+              const double* grid, const double* theta, int theta_stride, int Z, long long* launches, const ZeroJob* zj) {
   dim3 blk(32, 8), grd((N + 31) / 32, (N + 7) / 8, Z);
-  se_build_kernel<<<grd, blk, 0, s>>>(Kmat, D1, D2, N, ld, stride, grid, theta, theta_stride);
+  ZeroJob none{};
+  se_build_kernel<<<grd, blk, 0, s>>>(Kmat, D1, D2, N, ld, stride, grid, theta, theta_stride, zj ? *zj : none);
   if (launches) ++*launches;
 }
 
@@ -80,7 +89,8 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
 
-enum { EPI_STORE = 0, EPI_SWEEP = 1, EPI_TRACE = 2 };
+// EPI_STORE_F / EPI_TRACE_F: the two stages of the fused shared-theta_k objective (MeanFuse in common.cuh)
+enum { EPI_STORE = 0, EPI_SWEEP = 1, EPI_TRACE = 2, EPI_STORE_F = 3, EPI_TRACE_F = 4 };
 
 struct GemmParams {
   int M, N, K;
@@ -92,6 +102,8 @@ struct GemmParams {
   const double* Pbuf; long long sP; int c0, nb; double sign;
   // trace epilogue
   const double* D1; const double* D2; int ldd; long long sD; double* out; int out_stride;
+  // fused mean-process stages
+  MeanFuse mf;
 };
 
 constexpr int kBK = 32;
@@ -121,6 +133,7 @@ __global__ void __launch_bounds__(128) gemm_nt_kernel(GemmParams p) {
   const double* A = p.A + z * p.sA;
   const double* B = p.B + z * p.sB;
   const int K16 = (p.K + 15) & ~15;
+  if (MODE == EPI_TRACE_F && n0 > m0 + BM - 1) return;   // G = X Kinv is symmetric: strictly upper tiles are not needed
 
   double acc[FM][FN][2];
 #pragma unroll
@@ -175,7 +188,7 @@ __global__ void __launch_bounds__(128) gemm_nt_kernel(GemmParams p) {
     }
   }
 
-  double t1 = 0, t2 = 0, t0 = 0;
+  double t1 = 0, t2 = 0, t0 = 0, u1 = 0, u2 = 0;
 #pragma unroll
   for (int i = 0; i < FM; ++i) {
     const int gi = m0 + wm + 8 * i + (lane >> 2);
@@ -184,7 +197,7 @@ __global__ void __launch_bounds__(128) gemm_nt_kernel(GemmParams p) {
       const int gj = n0 + wn + 8 * j + (lane & 3) * 2;
       if (gi >= p.M || gj >= p.N) continue;
       const bool two = (gj + 1 < p.N);
-      if (MODE == EPI_STORE) {
+      if (MODE == EPI_STORE || MODE == EPI_STORE_F) {
         double* c = p.C + z * p.sC + (size_t)gi * p.ldc + gj;
         if (p.beta == 0.0) {
           c[0] = p.alpha * acc[i][j][0];
@@ -207,7 +220,7 @@ __global__ void __launch_bounds__(128) gemm_nt_kernel(GemmParams p) {
           else r = p.Pbuf[z * p.sP + (size_t)gq * kNB + (gi - p.c0)];
           c[q] = p.sign * r;
         }
-      } else {
+      } else if (MODE == EPI_TRACE) {
         const size_t o = z * p.sD + (size_t)gi * p.ldd + gj;
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
@@ -216,6 +229,25 @@ __global__ void __launch_bounds__(128) gemm_nt_kernel(GemmParams p) {
           if (gi == gj + q) t0 += v;
           t1 += v * p.D1[o + q];
           t2 += v * p.D2[o + q];
+        }
+      } else {
+        // lower triangle with weight 2 (G and dK are symmetric); the quadratic forms sum_z p_z' dK p_z ride along
+        const size_t o = (size_t)gi * p.ldd + gj;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          if (q == 1 && !two) break;
+          const int gq = gj + q;
+          if (gq > gi) continue;
+          const double wgt = (gq == gi) ? 1.0 : 2.0;
+          const double v = acc[i][j][q];
+          const double d1 = p.D1[o + q], d2 = p.D2[o + q];
+          double pp = 0.0;
+          for (int zz = 0; zz < p.mf.K; ++zz) pp += p.mf.p[(size_t)zz * p.mf.ldp + gi] * p.mf.p[(size_t)zz * p.mf.ldp + gq];
+          if (gq == gi) t0 += v;
+          t1 += wgt * v * d1;
+          t2 += wgt * v * d2;
+          u1 += wgt * pp * d1;
+          u2 += wgt * pp * d2;
         }
       }
     }
@@ -233,6 +265,89 @@ __global__ void __launch_bounds__(128) gemm_nt_kernel(GemmParams p) {
     if (tid < 3) {
       double s = red[tid][0] + red[tid][1] + red[tid][2] + red[tid][3];
       atomicAdd(p.out + (size_t)z * p.out_stride + tid, s);
+    }
+  }
+  if (MODE == EPI_TRACE_F) {
+    // red[8..10] += tr(G dK/da), tr(G dK/db), tr G ; red[6..7] += sum_z p_z' dK/da p_z, p_z' dK/db p_z
+    double v5[5] = {t1, t2, t0, u1, u2};
+#pragma unroll
+    for (int q = 0; q < 5; ++q)
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v5[q] += __shfl_xor_sync(0xffffffffu, v5[q], o);
+    if (lane == 0) {
+      atomicAdd(p.mf.red + 8, v5[0]);
+      atomicAdd(p.mf.red + 9, v5[1]);
+      atomicAdd(p.mf.red + 10, v5[2]);
+      atomicAdd(p.mf.red + 6, v5[3]);
+      atomicAdd(p.mf.red + 7, v5[4]);
+    }
+    if (blockIdx.x == 0) {
+      // red[4] += sum_z r_z' p_z, red[5] += sum_z p_z' p_z over this CTA's rows
+      double q1 = 0, q2 = 0;
+      for (int e = tid; e < BM * p.mf.K; e += 128) {
+        const int zz = e / BM, gi = m0 + (e - zz * BM);
+        if (gi < p.M) {
+          const double pv = p.mf.p[(size_t)zz * p.mf.ldp + gi];
+          q1 += p.mf.r[(size_t)zz * p.mf.ldp + gi] * pv;
+          q2 += pv * pv;
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        q1 += __shfl_xor_sync(0xffffffffu, q1, o);
+        q2 += __shfl_xor_sync(0xffffffffu, q2, o);
+      }
+      if (lane == 0) { atomicAdd(p.mf.red + 4, q1); atomicAdd(p.mf.red + 5, q2); }
+    }
+  }
+  if constexpr (MODE == EPI_STORE_F) {
+    // side job, spread over all tiles: over THIS tile's BM x BN patch of Kinv (= A), the element-wise sums against
+    // Csum (= B), dK/da, dK/db and the partial products p_z[row] += Kinv[row, patch] r_z[patch] (p is cleared by the
+    // build kernel). All loads of a thread are independent: one L2 round trip.
+    static_assert(BM * BN == 128 * 4, "one thread per 4 consecutive columns");
+    const int rr = tid / (BN / 4), cc = (tid % (BN / 4)) * 4;
+    const int gi = m0 + rr, gj = n0 + cc;
+    double g4[4] = {0, 0, 0, 0};
+    double pz[8];
+#pragma unroll
+    for (int zz = 0; zz < 8; ++zz) pz[zz] = 0.0;
+    if (gi < p.M && gj < p.N) {   // pads beyond N inside the row are zero in every operand
+      const double2 k01 = *reinterpret_cast<const double2*>(A + (size_t)gi * p.lda + gj);
+      const double2 k23 = *reinterpret_cast<const double2*>(A + (size_t)gi * p.lda + gj + 2);
+      const double2 c01 = *reinterpret_cast<const double2*>(B + (size_t)gi * p.ldb + gj);
+      const double2 c23 = *reinterpret_cast<const double2*>(B + (size_t)gi * p.ldb + gj + 2);
+      const double2 a01 = *reinterpret_cast<const double2*>(p.D1 + (size_t)gi * p.ldd + gj);
+      const double2 a23 = *reinterpret_cast<const double2*>(p.D1 + (size_t)gi * p.ldd + gj + 2);
+      const double2 b01 = *reinterpret_cast<const double2*>(p.D2 + (size_t)gi * p.ldd + gj);
+      const double2 b23 = *reinterpret_cast<const double2*>(p.D2 + (size_t)gi * p.ldd + gj + 2);
+      g4[0] = k01.x * c01.x + k01.y * c01.y + k23.x * c23.x + k23.y * c23.y;
+      g4[1] = k01.x * a01.x + k01.y * a01.y + k23.x * a23.x + k23.y * a23.y;
+      g4[2] = k01.x * b01.x + k01.y * b01.y + k23.x * b23.x + k23.y * b23.y;
+      if (gi >= gj && gi < gj + 4) g4[3] = (gi == gj) ? k01.x : (gi == gj + 1) ? k01.y : (gi == gj + 2) ? k23.x : k23.y;
+#pragma unroll
+      for (int zz = 0; zz < 8; ++zz) {
+        if (zz < p.mf.K) {
+          const double2 r01 = *reinterpret_cast<const double2*>(p.mf.r + (size_t)zz * p.mf.ldp + gj);
+          const double2 r23 = *reinterpret_cast<const double2*>(p.mf.r + (size_t)zz * p.mf.ldp + gj + 2);
+          pz[zz] = k01.x * r01.x + k01.y * r01.y + k23.x * r23.x + k23.y * r23.y;
+        }
+      }
+    }
+    // the BN / 4 = 8 threads of a row are consecutive lanes
+#pragma unroll
+    for (int zz = 0; zz < 8; ++zz) {
+      if (zz < p.mf.K) {
+        double a = pz[zz];
+#pragma unroll
+        for (int o = BN / 8; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+        if ((tid % (BN / 4)) == 0 && gi < p.M) atomicAdd(p.mf.p + (size_t)zz * p.mf.ldp + gi, a);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) g4[q] += __shfl_xor_sync(0xffffffffu, g4[q], o);
+      if (lane == 0 && g4[q] != 0.0) atomicAdd(p.mf.red + q, g4[q]);
     }
   }
 }
@@ -285,6 +400,32 @@ void gemm_nt_trace(cudaStream_t s, int N, const double* A, int lda, long long sA
   p.B = B; p.ldb = ldb; p.sB = sB;
   p.D1 = D1; p.D2 = D2; p.ldd = ldd; p.sD = sD; p.out = out; p.out_stride = out_stride;
   launch_gemm<EPI_TRACE>(s, p, Z, launches);
+}
+
+// Fused stages of the shared-theta_k objective (see MeanFuse). Stage 1: X = Kinv Csum, plus the row-wise group sums
+// and p_z = Kinv r_z. Stage 2: traces of G = X Kinv against dK/da, dK/db, I on the lower triangle, plus the quadratic
+// forms of p_z. Both use the small-tile configuration: they run next to the persistent theta_i kernel on few SMs.
+void mean_stage1(cudaStream_t s, int N, const double* Kinv, const double* Csum, double* X, int ld, const double* D1,
+                 const double* D2, const MeanFuse& mf, long long* launches) {
+  GemmParams p{};
+  p.M = N; p.N = N; p.K = N;
+  p.A = Kinv; p.lda = ld; p.B = Csum; p.ldb = ld; p.C = X; p.ldc = ld;
+  p.alpha = 1.0; p.beta = 0.0;
+  p.D1 = D1; p.D2 = D2; p.ldd = ld;
+  p.mf = mf;
+  launch_gemm_cfg<16, 32, EPI_STORE_F, 4>(s, p, dim3((N + 31) / 32, (N + 15) / 16, 1));
+  if (launches) ++*launches;
+}
+
+void mean_stage2(cudaStream_t s, int N, const double* X, const double* Kinv, int ld, const double* D1, const double* D2,
+                 const MeanFuse& mf, long long* launches) {
+  GemmParams p{};
+  p.M = N; p.N = N; p.K = N;
+  p.A = X; p.lda = ld; p.B = Kinv; p.ldb = ld;
+  p.D1 = D1; p.D2 = D2; p.ldd = ld;
+  p.mf = mf;
+  launch_gemm_cfg<16, 32, EPI_TRACE_F, 4>(s, p, dim3((N + 31) / 32, (N + 15) / 16, 1));
+  if (launches) ++*launches;
 }
 
 // -------------------------------------------------------------------------------------------------

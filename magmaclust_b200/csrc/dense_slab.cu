@@ -336,8 +336,10 @@ cudaError_t spd_inverse_slab_reserve(DenseWs& ws, int N, int Z) {
   return ws.bar.ensure(2 * (size_t)(Z > 64 ? Z : 64));
 }
 
+unsigned* slab_sync_words(DenseWs& ws) { return ws.bar.p; }
+
 cudaError_t spd_inverse_slab(cudaStream_t s, double* A, int N, int ld, long long stride, int Z, double* logdet,
-                             int* info, DenseWs& ws, long long* launches) {
+                             int* info, DenseWs& ws, long long* launches, bool pre_zeroed) {
   cudaError_t e;
   if ((e = spd_inverse_slab_reserve(ws, N, Z)) != cudaSuccess) return e;
   static bool attr_set = false;
@@ -346,7 +348,7 @@ cudaError_t spd_inverse_slab(cudaStream_t s, double* A, int N, int ld, long long
       return e;
     attr_set = true;
   }
-  if ((e = cudaMemsetAsync(logdet, 0, sizeof(double) * Z, s)) != cudaSuccess) return e;
+  if (!pre_zeroed && (e = cudaMemsetAsync(logdet, 0, sizeof(double) * Z, s)) != cudaSuccess) return e;
   // all CTAs of a launch must be co-resident (1 CTA per SM): batch the matrices accordingly. ws.max_ctas is the
   // number of SMs the caller knows to be free (the M-step runs this next to a persistent kernel).
   int dev = 0, sms = 148;
@@ -359,7 +361,7 @@ cudaError_t spd_inverse_slab(cudaStream_t s, double* A, int N, int ld, long long
   const int zmax = budget / (c.nblk * c.Q) > 0 ? budget / (c.nblk * c.Q) : 1;
   for (int z0 = 0; z0 < Z; z0 += zmax) {
     const int zc = (Z - z0 < zmax) ? Z - z0 : zmax;
-    if ((e = cudaMemsetAsync(ws.bar.p, 0, sizeof(unsigned) * 2 * zc, s)) != cudaSuccess) return e;
+    if (!(pre_zeroed && z0 == 0) && (e = cudaMemsetAsync(ws.bar.p, 0, sizeof(unsigned) * 2 * zc, s)) != cudaSuccess) return e;
     double* Az = A + (size_t)z0 * stride;
     double* ldz = logdet + z0;
     double* Vb = ws.slabV.p;

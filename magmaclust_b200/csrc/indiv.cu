@@ -585,12 +585,14 @@ cudaError_t launch_indiv_mstep(cudaStream_t s, const IndivData& dd, int M, int n
     int NT;
     if (eval2_shape(nmax, &TT, &E, &NT)) {
       const size_t sm2 = eval2_smem_bytes(NT);
+      static const int cap_per_sm = getenv("MCB_MSTEP_CTAS") ? atoi(getenv("MCB_MSTEP_CTAS")) : 0;
 #define MCB_LAUNCH_MSTEP2(EE, T_, N_)                                                                                  \
   do {                                                                                                                 \
     if ((e = set_smem_t(indiv_mstep2_kernel<EE, T_, N_>, sm2)) != cudaSuccess) return e;                               \
     int per_sm = 1;                                                                                                    \
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, indiv_mstep2_kernel<EE, T_, N_>, T_, sm2);                  \
     if (per_sm < 1) per_sm = 1;                                                                                        \
+    if (cap_per_sm > 0 && per_sm > cap_per_sm) per_sm = cap_per_sm;                                                    \
     int grid = per_sm * sms;                                                                                           \
     if (grid > M && reserve_sms == 0) grid = M;                                                                        \
     indiv_mstep2_kernel<EE, T_, N_><<<grid, T_, sm2, s>>>(dd, w, nmax, M, theta0, theta_out, maxit, nfev, niter,       \
