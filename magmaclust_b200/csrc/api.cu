@@ -90,7 +90,7 @@ extern "C" int mcb_create(mcb_handle** out, int device) {
       (e = cudaStreamCreateWithFlags(&h->st2, cudaStreamNonBlocking)) != cudaSuccess ||
       (e = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming)) != cudaSuccess ||
       (e = cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming)) != cudaSuccess ||
-      (e = h->mstep_ctl.ensure(2 + 1024)) != cudaSuccess ||
+      (e = h->mstep_ctl.ensure(mcb::kMstepCtlWords)) != cudaSuccess ||
       (e = cudaMallocHost(&h->hbuf, sizeof(double) * mcb_handle::kHbuf)) != cudaSuccess ||
       (e = h->info.ensure(4)) != cudaSuccess || (e = h->scal.ensure(64)) != cudaSuccess) {
     g_create_err = cudaGetErrorString(e);
@@ -114,7 +114,7 @@ extern "C" void mcb_destroy(mcb_handle* h) {
   for (auto e : h->evpool) cudaEventDestroy(e);
   mcb::DevBuf<double>* dbl[] = {&h->t, &h->y, &h->grid, &h->theta_i, &h->theta_k, &h->pi, &h->mk, &h->tau,
                                 &h->theta_i_new, &h->theta_k_new, &h->pi_new, &h->tau_new, &h->logL, &h->Winv,
-                                &h->pvec, &h->yWy, &h->logdet_i, &h->c1, &h->c2, &h->Fi, &h->fi_tmp, &h->gi_tmp,
+                                &h->pvec, &h->yWy, &h->logdet_i, &h->c1, &h->c2, &h->Fi, &h->Fnew, &h->fi_tmp, &h->gi_tmp,
                                 &h->theta_g, &h->Kinv, &h->cov, &h->wk, &h->mean, &h->rvec, &h->pz, &h->logdetK,
                                 &h->logdetA, &h->eK, &h->eD1, &h->eD2, &h->eCsum, &h->eX, &h->etheta, &h->ered,
                                 &h->elogdet, &h->ws.Pbuf, &h->ws.Cold, &h->ws.red, &h->ws.slabV, &h->ws.slabP, &h->ws.slabL, &h->scal, &h->pgrid, &h->pKinv,
@@ -179,7 +179,7 @@ extern "C" int mcb_set_data(mcb_handle* h, int M, int N, long long P, const int*
   H_CUDA(h->pvec.ensure(P)); H_CUDA(h->c1.ensure(P));
   H_CUDA(h->yWy.ensure(M)); H_CUDA(h->logdet_i.ensure(M)); H_CUDA(h->Fi.ensure(M));
   H_CUDA(h->fi_tmp.ensure(M)); H_CUDA(h->gi_tmp.ensure(3 * (size_t)M));
-  H_CUDA(h->nfev_i.ensure(M)); H_CUDA(h->niter_i.ensure(M)); H_CUDA(h->status_i.ensure(M));
+  H_CUDA(h->nfev_i.ensure(M)); H_CUDA(h->niter_i.ensure(M)); H_CUDA(h->status_i.ensure(M)); H_CUDA(h->Fnew.ensure(M));
   H_CUDA(h->theta_i.ensure(3 * (size_t)M)); H_CUDA(h->theta_i_new.ensure(3 * (size_t)M));
   H_CUDA(cudaStreamSynchronize(h->st));  // host vectors go out of scope
   h->has_data = true; h->has_state = false; h->has_post = false; h->has_cand = false; h->has_pred = false;
@@ -747,6 +747,9 @@ static int elbo_impl(mcb_handle* h, const double* theta_k, const double* theta_i
   H_CUDA(cudaMemsetAsync(dsum, 0, sizeof(double), h->st));
   if (theta_i_dev == nullptr) {
     vec_sum(h->st, h->M, h->Fi.p, dsum, &h->launches);
+  } else if (theta_i_dev == h->theta_i_new.p && h->fnew_valid) {
+    // the per-individual optimiser already evaluated F_i at the point it returned
+    vec_sum(h->st, h->M, h->Fnew.p, dsum, &h->launches);
   } else {
     H_CUDA(launch_indiv_eval(h->st, h->idata(), h->M, h->nmax, h->iwork(), theta_i_dev, 3, 0, nullptr, nullptr, dsum,
                              h->info.p));
@@ -756,6 +759,7 @@ static int elbo_impl(mcb_handle* h, const double* theta_k, const double* theta_i
   H_CUDA(cudaMemcpyAsync(h->hbuf + 600, dsum, sizeof(double), cudaMemcpyDeviceToHost, h->st));
   MCB_TRY(check_info(h, "logL_monitoring_VEM"));
   const double sum_i = h->hbuf[600];
+  if (!std::isfinite(sum_i)) { h->err = "logL_monitoring_VEM: covariance not positive definite"; return MCB_ENOTPD; }
   out[0] = -sum_k - sum_i;
   double ld = 0.0;
   for (int k = 0; k < K; ++k) ld += -h->h_logdetA[k];
@@ -1055,6 +1059,8 @@ static int compute_pen_diag(mcb_handle* h, double* pen_diag) {
 static int m_step_impl(mcb_handle* h, int common_hp_k, int common_hp_i, int* stats) {
   const int M = h->M, K = h->K;
   int nfev_i = 0, nit_i = 0, nfev_k = 0, nit_k = 0;
+  int fw = 0;
+  h->fnew_valid = false;
   // With individual-specific theta_i and a shared theta_k the two optimisations are independent (pen_diag only
   // replaces the third entry of theta_k afterwards, CF.R:666-668): run them concurrently.
   static const bool no_overlap = getenv("MCB_NO_OVERLAP") != nullptr;
@@ -1108,7 +1114,8 @@ static int m_step_impl(mcb_handle* h, int common_hp_k, int common_hp_i, int* sta
       H_CUDA(cudaStreamSynchronize(h->st));
     } else if (!overlap) {
       H_CUDA(launch_indiv_mstep(h->st, h->idata(), M, h->nmax, h->iwork(), h->theta_i.p, h->theta_i_new.p, 100,
-                                h->nfev_i.p, h->niter_i.p, h->status_i.p, h->mstep_ctl.p, 0, order));
+                                h->nfev_i.p, h->niter_i.p, h->status_i.p, h->mstep_ctl.p, 0, order, h->Fnew.p, &fw));
+      h->fnew_valid = fw != 0;
       h->nfev_valid = true;
       ++h->launches;
     }
@@ -1126,7 +1133,8 @@ static int m_step_impl(mcb_handle* h, int common_hp_k, int common_hp_i, int* sta
       static const int extra = getenv("MCB_RESERVE_EXTRA") ? atoi(getenv("MCB_RESERVE_EXTRA")) : -1;
       const int reserve = extra >= 0 ? std::min(nblk + extra, 96) : (2 * nblk <= 40 ? 2 * nblk : nblk);
       H_CUDA(launch_indiv_mstep(h->st2, h->idata(), M, h->nmax, h->iwork(), h->theta_i.p, h->theta_i_new.p, 100,
-                                h->nfev_i.p, h->niter_i.p, h->status_i.p, h->mstep_ctl.p, reserve, order));
+                                h->nfev_i.p, h->niter_i.p, h->status_i.p, h->mstep_ctl.p, reserve, order, h->Fnew.p, &fw));
+      h->fnew_valid = fw != 0;
       h->ws.max_ctas = reserve;   // what the slab inverse may count on while that kernel runs
       h->nfev_valid = true;
       ++h->launches;

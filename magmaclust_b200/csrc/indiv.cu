@@ -18,6 +18,7 @@
 #include "lbfgs.h"
 #include "indiv_eval.cuh"
 #include "indiv_eval2.cuh"
+#include "indiv_eval3.cuh"
 
 namespace mcb {
 
@@ -346,8 +347,9 @@ __global__ void __launch_bounds__(TT) indiv_mstep_kernel(IndivData dd, IndivWork
 }
 
 // ---- second design of the evaluator (indiv_eval2.cuh): same contracts as the two kernels above -------------------
-template <int E, int TT, int NT>
-__global__ void __launch_bounds__(TT, (E > 1 ? 256 : 512) / TT) indiv_eval2_kernel(IndivData dd, IndivWork w, int nmax,
+// VER = 2: indiv_eval2.cuh (rank-1 sweep on 4 x 4 register blocks), VER = 3: indiv_eval3.cuh (blocked DMMA sweep)
+template <int E, int TT, int NT, int VER>
+__global__ void __launch_bounds__(TT, ((E > 1 || NT > 8) ? 256 : 512) / TT) indiv_eval2_kernel(IndivData dd, IndivWork w, int nmax,
                                                                    const double* __restrict__ theta, int theta_stride,
                                                                    int want_grad, double* __restrict__ f,
                                                                    double* __restrict__ g, double* __restrict__ sum4,
@@ -358,10 +360,14 @@ __global__ void __launch_bounds__(TT, (E > 1 ? 256 : 512) / TT) indiv_eval2_kern
   const int o0 = dd.off[i], n = dd.off[i + 1] - o0;
   EvalSm2<NT> s = eval2_carve<NT>(sm);
   eval2_load<TT, NT>(s, n, dd.t + o0, dd.y + o0, w.c1 + o0, w.c2 + dd.woff[i]);
-  int bI[E], bJ[E];
-  eval2_decode<E, TT>(n, bI, bJ);
   const double* th = theta + (size_t)i * theta_stride;
-  indiv_eval_v2<E, TT, NT>(s, n, bI, bJ, th[0], th[1], th[2], want_grad != 0, out, info, i);
+  if constexpr (VER == 3) {
+    indiv_eval_v3<TT, NT>(s, n, th[0], th[1], th[2], want_grad != 0, out, info, i);
+  } else {
+    int bI[E], bJ[E];
+    eval2_decode<E, TT>(n, bI, bJ);
+    indiv_eval_v2<E, TT, NT>(s, n, bI, bJ, th[0], th[1], th[2], want_grad != 0, out, info, i);
+  }
   if (threadIdx.x == 0) {
     if (f) f[i] = out[0];
     if (g && want_grad) { g[3 * i] = out[1]; g[3 * i + 1] = out[2]; g[3 * i + 2] = out[3]; }
@@ -372,50 +378,75 @@ __global__ void __launch_bounds__(TT, (E > 1 ? 256 : 512) / TT) indiv_eval2_kern
   }
 }
 
-template <int E, int TT, int NT>
-__global__ void __launch_bounds__(TT, (E > 1 ? 256 : 512) / TT) indiv_mstep2_kernel(IndivData dd, IndivWork w, int nmax, int M,
+// ctl words (kMstepCtlWords ints, cleared before the launch): [0] head of the work queue, [1] SMs that have reported,
+// [2 + smid] role of the SM (0 undecided, 3 deciding, 1 shared, 2 reserved, 4 solo), [1026] tail counter of the queue,
+// [1027 + smid] CTAs of a solo SM that have reported.
+//
+// Scheduling. The M-step of M individuals is bounded below by its longest optimisation (82 sequential evaluations at the
+// C2 benchmark against a mean of 31), and an evaluation is 1.5x slower when four CTAs share an SM than when one has
+// it alone. So the first `solo` SMs (after the `reserve` ones left to the theta_k chain) keep ONE working CTA, and the
+// queue (longest-expected-first order) is popped from both ends: solo CTAs take the head, i.e. the `solo_items` longest
+// optimisations, shared CTAs start behind them; each side moves on to the other's range when its own is exhausted.
+template <int E, int TT, int NT, int VER>
+__global__ void __launch_bounds__(TT, ((E > 1 || NT > 8) ? 256 : 512) / TT) indiv_mstep2_kernel(IndivData dd, IndivWork w, int nmax, int M,
                                                                     const double* __restrict__ theta0,
                                                                     double* __restrict__ theta_out, int maxit,
                                                                     int* __restrict__ nfev, int* __restrict__ niter,
                                                                     int* __restrict__ status, int* __restrict__ ctl,
-                                                                    int reserve, const int* __restrict__ order) {
+                                                                    int reserve, const int* __restrict__ order,
+                                                                    int solo, int solo_items, double* __restrict__ f_out) {
   extern __shared__ __align__(16) double sm[];
   __shared__ double out[4];
   __shared__ Lbfgs opt;
-  __shared__ int st, cur;
+  __shared__ int st, cur, my_role;
   if (threadIdx.x == 0) {
     int role = 1;
-    if (reserve > 0) {
+    if (reserve > 0 || solo > 0) {
       unsigned smid;
       asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-      int* flag = ctl + 2 + (smid & 1023);
+      smid &= 1023;
+      int* flag = ctl + 2 + smid;
       const int old = atomicCAS(flag, 0, 3);
       if (old == 0) {
-        role = (atomicAdd(ctl + 1, 1) < reserve) ? 2 : 1;
+        const int ord = atomicAdd(ctl + 1, 1);
+        role = (ord < reserve) ? 2 : (ord < reserve + solo ? 4 : 1);
         __threadfence();
         atomicExch(flag, role);
       } else {
         role = old;
         while (role == 3) role = *((volatile int*)flag);
       }
+      if (role == 4 && atomicAdd(ctl + 1027 + smid, 1) > 0) role = 2;   // a solo SM keeps its first CTA only
     }
+    my_role = role;
     cur = (role == 2) ? -1 : 0;
   }
   tsync<TT>();
   if (cur < 0) return;
+  const bool is_solo = (my_role == 4);
   EvalSm2<NT> s = eval2_carve<NT>(sm);
   int bad = 0;
   for (;;) {
     tsync<TT>();
-    if (threadIdx.x == 0) cur = atomicAdd(ctl, 1);
+    if (threadIdx.x == 0) {
+      int i;
+      if (is_solo) {
+        i = atomicAdd(ctl, 1);
+        if (i >= solo_items) { i = solo_items + atomicAdd(ctl + 1026, 1); if (i >= M) i = -1; }
+      } else {
+        i = solo_items + atomicAdd(ctl + 1026, 1);
+        if (i >= M) { i = atomicAdd(ctl, 1); if (i >= solo_items) i = -1; }
+      }
+      cur = i;
+    }
     tsync<TT>();
-    if (cur >= M) break;
+    if (cur < 0) break;
     const int slot = cur;
     const int i = order ? order[slot] : slot;  // longest-expected-first order when the previous M-step's counts exist
     const int o0 = dd.off[i], n = dd.off[i + 1] - o0;
     eval2_load<TT, NT>(s, n, dd.t + o0, dd.y + o0, w.c1 + o0, w.c2 + dd.woff[i]);
     int bI[E], bJ[E];
-    eval2_decode<E, TT>(n, bI, bJ);
+    if constexpr (VER != 3) eval2_decode<E, TT>(n, bI, bJ);
     if (threadIdx.x == 0) {
       lb_init(opt, 3, theta0 + 3 * (size_t)i, maxit);
       st = LB_EVAL;
@@ -423,7 +454,8 @@ __global__ void __launch_bounds__(TT, (E > 1 ? 256 : 512) / TT) indiv_mstep2_ker
     tsync<TT>();
     while (true) {
       const double a = opt.x[0], b = opt.x[1], c = opt.x[2];
-      indiv_eval_v2<E, TT, NT>(s, n, bI, bJ, a, b, c, true, out, &bad, slot);
+      if constexpr (VER == 3) indiv_eval_v3<TT, NT>(s, n, a, b, c, true, out, &bad, slot);
+      else indiv_eval_v2<E, TT, NT>(s, n, bI, bJ, a, b, c, true, out, &bad, slot);
       if (threadIdx.x == 0) st = lb_advance(opt, out[0], out + 1);
       tsync<TT>();
       if (st != LB_EVAL) break;
@@ -435,6 +467,9 @@ __global__ void __launch_bounds__(TT, (E > 1 ? 256 : 512) / TT) indiv_mstep2_ker
       nfev[i] = opt.nfev;
       niter[i] = opt.iter;
       status[i] = st;
+      // objective at the returned point (the ELBO at the new hp needs exactly this); a start point without a finite
+      // objective poisons the sum on purpose
+      if (f_out) f_out[i] = (st == LB_NONFINITE) ? nan("") : opt.f;
     }
   }
 }
@@ -516,9 +551,20 @@ static void eval_shape(int nmax, int* TT, int* E) {
   } while (0)
 
 // second design: TT = 64 while the lower block triangle fits 64 threads, else 128 (E = 2 above n = 56); NT = tile bucket
+// E == 0 selects the third design (needs 8 NT >= nmax + 2): TT = 64 for NT = 4, else 128.
 static bool eval2_shape(int nmax, int* TT, int* E, int* NT) {
   static const bool v1 = getenv("MCB_EVAL_V1") != nullptr;
+  static const bool v2 = getenv("MCB_EVAL_V2") != nullptr;
+  static const bool v3 = getenv("MCB_EVAL_V3") != nullptr;
   if (v1 || nmax > 80) return false;
+  // measured (tools/dbg/eval_prof.cu, cycles per evaluation at full occupancy): n = 50: 87 k (second design) vs 116 k
+  // (third), n = 30: 64 k vs 64 k, n = 72: 123 k vs 105 k -> the blocked DMMA sweep only pays for the largest bucket
+  if (!v2 && nmax <= 78 && (v3 || nmax > 56)) {
+    *NT = (nmax <= 30) ? 4 : (nmax <= 54 ? 7 : 10);
+    *TT = (*NT == 4) ? 64 : 128;
+    *E = 0;
+    return true;
+  }
   const int nbk = (nmax + 2 + 3) / 4, nblk = nbk * (nbk + 1) / 2;
   *TT = (nblk <= 64) ? 64 : 128;
   *E = (nblk + *TT - 1) / *TT;
@@ -531,10 +577,13 @@ static size_t eval2_smem_bytes(int NT) {
 
 #define MCB_DISPATCH_EVAL2(MACRO)                                   \
   do {                                                              \
-    if (TT == 64 && E == 1 && NT == 4) MACRO(1, 64, 4);             \
-    else if (TT == 64 && E == 1 && NT == 7) MACRO(1, 64, 7);        \
-    else if (TT == 128 && E == 1 && NT == 7) MACRO(1, 128, 7);      \
-    else if (TT == 128 && E == 2 && NT == 10) MACRO(2, 128, 10);    \
+    if (TT == 64 && E == 0 && NT == 4) MACRO(1, 64, 4, 3);          \
+    else if (TT == 128 && E == 0 && NT == 7) MACRO(1, 128, 7, 3);   \
+    else if (TT == 128 && E == 0 && NT == 10) MACRO(1, 128, 10, 3); \
+    else if (TT == 64 && E == 1 && NT == 4) MACRO(1, 64, 4, 2);     \
+    else if (TT == 64 && E == 1 && NT == 7) MACRO(1, 64, 7, 2);     \
+    else if (TT == 128 && E == 1 && NT == 7) MACRO(1, 128, 7, 2);   \
+    else if (TT == 128 && E == 2 && NT == 10) MACRO(2, 128, 10, 2); \
     else return cudaErrorInvalidValue;                              \
   } while (0)
 
@@ -546,10 +595,10 @@ cudaError_t launch_indiv_eval(cudaStream_t s, const IndivData& dd, int M, int nm
     if (eval2_shape(nmax, &TT, &E, &NT)) {
       const size_t sm2 = eval2_smem_bytes(NT);
       cudaError_t e;
-#define MCB_LAUNCH_EVAL2(EE, T_, N_)                                                                                   \
-  do {                                                                                                                 \
-    if ((e = set_smem_t(indiv_eval2_kernel<EE, T_, N_>, sm2)) != cudaSuccess) return e;                                \
-    indiv_eval2_kernel<EE, T_, N_><<<M, T_, sm2, s>>>(dd, w, nmax, theta, theta_stride, want_grad, f, g, sum4, info);  \
+#define MCB_LAUNCH_EVAL2(EE, T_, N_, V_)                                                                                   \
+  do {                                                                                                                     \
+    if ((e = set_smem_t(indiv_eval2_kernel<EE, T_, N_, V_>, sm2)) != cudaSuccess) return e;                                \
+    indiv_eval2_kernel<EE, T_, N_, V_><<<M, T_, sm2, s>>>(dd, w, nmax, theta, theta_stride, want_grad, f, g, sum4, info);  \
   } while (0)
       MCB_DISPATCH_EVAL2(MCB_LAUNCH_EVAL2);
 #undef MCB_LAUNCH_EVAL2
@@ -572,7 +621,9 @@ cudaError_t launch_indiv_eval(cudaStream_t s, const IndivData& dd, int M, int nm
 
 cudaError_t launch_indiv_mstep(cudaStream_t s, const IndivData& dd, int M, int nmax, const IndivWork& w,
                                const double* theta0, double* theta_out, int maxit, int* nfev, int* niter,
-                               int* status, int* ctl, int reserve_sms, const int* order) {
+                               int* status, int* ctl, int reserve_sms, const int* order, double* f_out,
+                               int* f_out_written) {
+  if (f_out_written) *f_out_written = 0;
   const size_t sm = eval_smem_bytes(nmax);
   int TT, E;
   eval_shape(nmax, &TT, &E);
@@ -580,23 +631,32 @@ cudaError_t launch_indiv_mstep(cudaStream_t s, const IndivData& dd, int M, int n
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  if ((e = cudaMemsetAsync(ctl, 0, sizeof(int) * (2 + 1024), s)) != cudaSuccess) return e;
+  if ((e = cudaMemsetAsync(ctl, 0, sizeof(int) * kMstepCtlWords, s)) != cudaSuccess) return e;
   {
     int NT;
     if (eval2_shape(nmax, &TT, &E, &NT)) {
       const size_t sm2 = eval2_smem_bytes(NT);
       static const int cap_per_sm = getenv("MCB_MSTEP_CTAS") ? atoi(getenv("MCB_MSTEP_CTAS")) : 0;
-#define MCB_LAUNCH_MSTEP2(EE, T_, N_)                                                                                  \
+      static const int solo_sms = getenv("MCB_SOLO_SMS") ? atoi(getenv("MCB_SOLO_SMS")) : -1;
+#define MCB_LAUNCH_MSTEP2(EE, T_, N_, V_)                                                                              \
   do {                                                                                                                 \
-    if ((e = set_smem_t(indiv_mstep2_kernel<EE, T_, N_>, sm2)) != cudaSuccess) return e;                               \
+    if ((e = set_smem_t(indiv_mstep2_kernel<EE, T_, N_, V_>, sm2)) != cudaSuccess) return e;                           \
     int per_sm = 1;                                                                                                    \
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, indiv_mstep2_kernel<EE, T_, N_>, T_, sm2);                  \
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, indiv_mstep2_kernel<EE, T_, N_, V_>, T_, sm2);              \
     if (per_sm < 1) per_sm = 1;                                                                                        \
     if (cap_per_sm > 0 && per_sm > cap_per_sm) per_sm = cap_per_sm;                                                    \
     int grid = per_sm * sms;                                                                                           \
-    if (grid > M && reserve_sms == 0) grid = M;                                                                        \
-    indiv_mstep2_kernel<EE, T_, N_><<<grid, T_, sm2, s>>>(dd, w, nmax, M, theta0, theta_out, maxit, nfev, niter,       \
-                                                          status, ctl, reserve_sms, order);                            \
+    int solo = 0, solo_items = 0;                                                                                      \
+    if (order && per_sm > 1 && M >= 2 * sms) {                                                                         \
+      /* solo SMs pay off while the optimisations outnumber the CTA slots only a few times (tail-bound regime) */      \
+      solo = solo_sms >= 0 ? solo_sms : ((long long)M < 8LL * per_sm * sms ? (sms - reserve_sms) / 8 : 0);            \
+      if (solo > sms - reserve_sms - 1) solo = sms - reserve_sms - 1;                                                  \
+      solo_items = 2 * solo;                                                                                           \
+    }                                                                                                                  \
+    if (grid > M && reserve_sms == 0 && solo == 0) grid = M;                                                           \
+    indiv_mstep2_kernel<EE, T_, N_, V_><<<grid, T_, sm2, s>>>(dd, w, nmax, M, theta0, theta_out, maxit, nfev, niter,   \
+                                                          status, ctl, reserve_sms, order, solo, solo_items, f_out);   \
+    if (f_out_written) *f_out_written = f_out ? 1 : 0;                                                                 \
   } while (0)
       MCB_DISPATCH_EVAL2(MCB_LAUNCH_MSTEP2);
 #undef MCB_LAUNCH_MSTEP2

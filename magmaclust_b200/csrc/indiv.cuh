@@ -37,9 +37,12 @@ cudaError_t launch_tau(cudaStream_t s, const IndivData& dd, int M, int nmax, int
 cudaError_t launch_indiv_eval(cudaStream_t s, const IndivData& dd, int M, int nmax, const IndivWork& w,
                               const double* theta, int theta_stride, int want_grad, double* f, double* g,
                               double* sum4, int* info);
+constexpr int kMstepCtlWords = 2 + 1024 + 1 + 1024;
+// f_out (optional, [M]): objective at the returned theta; *f_out_written tells whether the kernel variant filled it
 cudaError_t launch_indiv_mstep(cudaStream_t s, const IndivData& dd, int M, int nmax, const IndivWork& w,
                                const double* theta0, double* theta_out, int maxit, int* nfev, int* niter,
-                               int* status, int* ctl /* [2 + 1024] ints */, int reserve_sms,
-                               const int* order /* [M] processing order or NULL */);
+                               int* status, int* ctl /* [kMstepCtlWords] ints */, int reserve_sms,
+                               const int* order /* [M] processing order or NULL */, double* f_out = nullptr,
+                               int* f_out_written = nullptr);
 
 }  // namespace mcb

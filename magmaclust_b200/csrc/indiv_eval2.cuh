@@ -45,7 +45,7 @@ struct Eval2Geo {
   static constexpr int NTOT4 = NP8 + 4;                                   // >= roundup4(n + 2)
   static constexpr int CS = NTOT4 + 4;                                    // stride of the two pivot-column buffers
   static constexpr int MAT = NP8 * LDM;
-  static constexpr int DOUBLES = 2 * MAT + 2 * CS + NTOT4 + 2 + 3 * NP8 + 16 * 4;
+  static constexpr int DOUBLES = 2 * MAT + 2 * CS + NTOT4 + 2 + 3 * NP8 + 16 * 4 + 64;  // last 64: L^-1 tile of indiv_eval3
 };
 
 template <int NT>
@@ -82,6 +82,7 @@ __device__ __forceinline__ void eval2_load(const EvalSm2<NT>& s, int n, const do
   using G = Eval2Geo<NT>;
   double2* z = reinterpret_cast<double2*>(s.W);
   for (int e = threadIdx.x; e < G::MAT; e += TT) z[e] = make_double2(0.0, 0.0);  // W and S are adjacent
+  for (int e = threadIdx.x; e < 64; e += TT) s.red[64 + e] = 0.0;                 // L^-1 tile (zero above the diagonal)
   for (int a = threadIdx.x; a < n; a += TT) {
     s.t[a] = tg[a];
     s.y[a] = yg[a];

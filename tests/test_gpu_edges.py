@@ -26,12 +26,29 @@ def _check_eval(session, db, hp, tau, m_k, seed=0):
     return ref, got
 
 
-@pytest.mark.parametrize("nrange,n_grid", [((1, 3), 12), ((38, 44), 90), ((60, 75), 120), ((78, 80), 120)])
+@pytest.mark.parametrize("nrange,n_grid", [((1, 3), 12), ((20, 30), 60), ((31, 40), 90), ((38, 44), 90), ((45, 54), 100),
+                                           ((55, 56), 100), ((60, 75), 120), ((78, 80), 120)])
 def test_individual_sizes_cover_all_kernel_shapes(session, nrange, n_grid):
-    """n_i from 1 (scalar branch, CF.R:167-170) to 80 (the shared-memory limit): 64-thread and 128-thread shapes with
-    1, 2 and 4 register blocks per thread"""
+    """n_i from 1 (scalar branch, CF.R:167-170) to 80 (the shared-memory limit): every (threads, tile bucket, design)
+    instantiation of the evaluation kernels (indiv.cu: eval2_shape)"""
     db, hp, tau, m_k = small_problem(M=6, K=2, n=nrange, n_grid=n_grid, seed=11)
     _check_eval(session, db, hp, tau, m_k)
+
+
+@pytest.mark.parametrize("var", ["MCB_EVAL_V3", "MCB_EVAL_V2", "MCB_EVAL_V1"])
+def test_other_evaluator_designs_agree_with_the_oracle(var):
+    """the design is chosen once per process (environment variable read at the first launch): re-run the size sweep in a
+    child process with the blocked-DMMA (V3), rank-1 (V2) and first (V1) evaluators forced for every bucket they support"""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ)
+    env[var] = "1"
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_edges.py"), "-q", "-x", "-m", "gpu",
+                        "-k", "test_individual_sizes_cover_all_kernel_shapes"], env=env, cwd=root, capture_output=True,
+                       text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
 
 
 def test_more_than_80_observations_is_rejected(session):

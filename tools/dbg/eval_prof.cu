@@ -9,6 +9,7 @@
 #define MCB_PROF 1
 #include "../../magmaclust_b200/csrc/indiv_eval.cuh"
 #include "../../magmaclust_b200/csrc/indiv_eval2.cuh"
+#include "../../magmaclust_b200/csrc/indiv_eval3.cuh"
 #include "../../magmaclust_b200/csrc/lbfgs.h"
 
 using namespace mcb;
@@ -44,7 +45,7 @@ __global__ void __launch_bounds__(TT) prof_kernel(int n, int nmax, const double*
   if (threadIdx.x == 0) sink[blockIdx.x] = out[0] + out[1] + bad;
 }
 
-template <int E, int TT, int NT, int MINB>
+template <int E, int TT, int NT, int MINB, int VER = 2>
 __global__ void __launch_bounds__(TT, MINB) prof2_kernel(int n, int nmax, const double* t, const double* y, const double* c1,
                                                          const double* c2, int evals, double* sink, long long* total) {
   extern __shared__ __align__(16) double sm[];
@@ -62,7 +63,8 @@ __global__ void __launch_bounds__(TT, MINB) prof2_kernel(int n, int nmax, const 
   long long t0 = clock64(), tl = 0;
   for (int it = 0; it < evals; ++it) {
     const double a = opt.x[0], b = opt.x[1], c = opt.x[2];
-    indiv_eval_v2<E, TT, NT>(s, n, bI, bJ, a, b, c, true, out, &bad, blockIdx.x);
+    if constexpr (VER == 3) indiv_eval_v3<TT, NT>(s, n, a, b, c, true, out, &bad, blockIdx.x);
+    else indiv_eval_v2<E, TT, NT>(s, n, bI, bJ, a, b, c, true, out, &bad, blockIdx.x);
     if (it == 0 && threadIdx.x == 0 && blockIdx.x == 0) { sink[4000] = out[0]; sink[4001] = out[1]; sink[4002] = out[2]; sink[4003] = out[3]; }
     long long q0 = clock64();
     if (threadIdx.x == 0) {
@@ -133,6 +135,19 @@ int main(int argc, char** argv) {
   } else {
     run(prof2_kernel<2, 128, 10, 2>, 1, "v2 1 CTA");
     run(prof2_kernel<2, 128, 10, 2>, 296, "v2 2 CTA/SM");
+  }
+  printf("v3:\n");
+  if (n <= 30) {
+    run(prof2_kernel<1, 64, 4, 8, 3>, 1, "v3 1 CTA", 64);
+    run(prof2_kernel<1, 64, 4, 8, 3>, 148 * 8, "v3 8 CTA/SM", 64);
+  } else if (n <= 54) {
+    run(prof2_kernel<1, 128, 7, 4, 3>, 1, "v3 1 CTA");
+    run(prof2_kernel<1, 128, 7, 4, 3>, 148, "v3 1 CTA/SM");
+    run(prof2_kernel<1, 128, 7, 4, 3>, 296, "v3 2 CTA/SM");
+    run(prof2_kernel<1, 128, 7, 4, 3>, 592, "v3 4 CTA/SM");
+  } else if (n <= 78) {
+    run(prof2_kernel<1, 128, 10, 2, 3>, 1, "v3 1 CTA");
+    run(prof2_kernel<1, 128, 10, 2, 3>, 296, "v3 2 CTA/SM");
   }
   return 0;
 }
