@@ -22,6 +22,24 @@
 #include "common.cuh"
 #include "factor32.cuh"
 
+#ifdef SLAB_PROF
+// tools/dbg/slab_prof.cu: cycles per segment of a pivot-block step, by role of the CTA in that step
+// (0 look-ahead CTA in the pivot column part = critical path, 1 other CTAs of the pivot column part, 2 the rest)
+__device__ long long g_slab_prof[3][16];
+#define SP_BEGIN(cls) const int sp_cls_ = (cls); long long sp_t_ = clock64();
+#define SP(k)                                                       \
+  do {                                                              \
+    if (threadIdx.x == 0 && blockIdx.y == 0) {                      \
+      const long long now_ = clock64();                             \
+      atomicAdd((unsigned long long*)&g_slab_prof[sp_cls_][k], (unsigned long long)(now_ - sp_t_)); \
+      sp_t_ = now_;                                                 \
+    }                                                               \
+  } while (0)
+#else
+#define SP_BEGIN(cls)
+#define SP(k) do {} while (0)
+#endif
+
 namespace mcb {
 
 constexpr int kSlabThreads = 256;
@@ -148,10 +166,12 @@ spd_inverse_slab_kernel(double* __restrict__ Aall, int N, int ld, long long stri
     double* Vg = Vbuf + buf * sPall + z * sPz;
     double* Pg = Pbuf + buf * sPall + z * sPz;
     const double* Lg = Lbuf + ((size_t)(b & 1) * gridDim.y + z) * kNB * kNB;
+    SP_BEGIN(((b + 1 < nblk) && I == b + 1 && ((b + 1) / Wb == q) && own_piv) ? 0 : (own_piv ? 1 : 2))
 
     // ---- phase 2: V_I = R L^-T, P_I = V L^-1 -------------------------------------------------------------
     if (own_piv) {
       slab_wait(lflag, (unsigned)(b + 1));
+      SP(0);
       for (int e = tid; e < kNB * kNB; e += kSlabThreads) {
         const int r = e >> 5, c = e & 31;
         Ls[r * kLp + c] = __ldcg(Lg + e);
@@ -161,8 +181,10 @@ spd_inverse_slab_kernel(double* __restrict__ Aall, int N, int ld, long long stri
         Rs[r * kLp + c] = v;
       }
       __syncthreads();
+      SP(1);
       mm32_nt(Rs, Ls, Vs, warp, lane);     // V[r][c] = sum_b R[r][b] Linv[c][b]
       __syncthreads();
+      SP(2);
       // P[r][c] = sum_b V[r][b] Linv[b][c]: B operand rows = columns of Linv
       {
 #pragma unroll
@@ -181,6 +203,7 @@ spd_inverse_slab_kernel(double* __restrict__ Aall, int N, int ld, long long stri
         }
       }
       __syncthreads();
+      SP(3);
       for (int e = tid; e < kNB * kNB; e += kSlabThreads) {
         const int r = e >> 5, c = e & 31;
         Vg[(size_t)(r0 + r) * kNB + c] = Vs[r * kLp + c];
@@ -188,8 +211,10 @@ spd_inverse_slab_kernel(double* __restrict__ Aall, int N, int ld, long long stri
       }
     }
     slab_arrive(counter);
+    SP(4);
     const bool look = (b + 1 < nblk) && I == b + 1 && ((b + 1) / Wb == q);
     if (!(look && own_piv)) slab_wait(counter, (unsigned)(b + 1) * (unsigned)ncta);
+    SP(5);
 
     // ---- phase 3 --------------------------------------------------------------------------------------
     if (look) {
@@ -213,7 +238,9 @@ spd_inverse_slab_kernel(double* __restrict__ Aall, int N, int ld, long long stri
         Rs[r * kLp + c + 1] = (r < nb1 && c + 1 < nb1) ? cp[1] - n1 : (r == c + 1 ? 1.0 : 0.0);
       }
       __syncthreads();
+      SP(6);
       factor_block(b + 1, false);
+      SP(7);
     } else if (I == b + 1) {
       // the other column parts of the next pivot rows: dead until they are replaced at the next step
     } else if (I != b) {
@@ -233,6 +260,7 @@ spd_inverse_slab_kernel(double* __restrict__ Aall, int N, int ld, long long stri
         for (int k = 0; k < 8; ++k) bf[t][k] = live ? __ldcg(vj + 4 * k) : 0.0;
       }
       if (!own_piv) fetch_V(Vg);
+      SP(8);
 #pragma unroll
       for (int t = 0; t < kMaxT; ++t) {
         const int tj = warp + 8 * t;
@@ -277,6 +305,7 @@ spd_inverse_slab_kernel(double* __restrict__ Aall, int N, int ld, long long stri
       }
     }
     __syncthreads();
+    SP(9);
   }
 
   if (warp == 7) {

@@ -638,6 +638,7 @@ cudaError_t launch_indiv_mstep(cudaStream_t s, const IndivData& dd, int M, int n
       const size_t sm2 = eval2_smem_bytes(NT);
       static const int cap_per_sm = getenv("MCB_MSTEP_CTAS") ? atoi(getenv("MCB_MSTEP_CTAS")) : 0;
       static const int solo_sms = getenv("MCB_SOLO_SMS") ? atoi(getenv("MCB_SOLO_SMS")) : -1;
+      static const int solo_mult = getenv("MCB_SOLO_MULT") ? atoi(getenv("MCB_SOLO_MULT")) : 1;
 #define MCB_LAUNCH_MSTEP2(EE, T_, N_, V_)                                                                              \
   do {                                                                                                                 \
     if ((e = set_smem_t(indiv_mstep2_kernel<EE, T_, N_, V_>, sm2)) != cudaSuccess) return e;                           \
@@ -651,7 +652,7 @@ cudaError_t launch_indiv_mstep(cudaStream_t s, const IndivData& dd, int M, int n
       /* solo SMs pay off while the optimisations outnumber the CTA slots only a few times (tail-bound regime) */      \
       solo = solo_sms >= 0 ? solo_sms : ((long long)M < 8LL * per_sm * sms ? (sms - reserve_sms) / 8 : 0);            \
       if (solo > sms - reserve_sms - 1) solo = sms - reserve_sms - 1;                                                  \
-      solo_items = 2 * solo;                                                                                           \
+      solo_items = solo_mult * solo;                                                                                   \
     }                                                                                                                  \
     if (grid > M && reserve_sms == 0 && solo == 0) grid = M;                                                           \
     indiv_mstep2_kernel<EE, T_, N_, V_><<<grid, T_, sm2, s>>>(dd, w, nmax, M, theta0, theta_out, maxit, nfev, niter,   \

@@ -97,8 +97,8 @@ __device__ void indiv_eval_v3(const EvalSm2<NT>& s, int n, double th1, double th
   const int ntb = (n + 2 + 7) >> 3;   // tile rows of the bordered matrix
   const int nt = (n + 7) >> 3;        // tile rows of Psi
   const int role = (warp + rot) % NW;
-  const double hl = exp(-th2) * 0.5;
-  const double e1 = exp(th1);
+  const double hl = ev_exp(-th2) * 0.5;
+  const double e1 = ev_exp(th1);
   const double dg = e1 + sg * sg;
 #ifdef MCB_PROF
   long long prof_t_ = clock64();
@@ -134,7 +134,7 @@ __device__ void indiv_eval_v3(const EvalSm2<NT>& s, int n, double th1, double th
             if (row == c) v[q] = dg;
             else {
               const double d = trow - s.t[c];
-              v[q] = exp(th1 - hl * (d * d));
+              v[q] = ev_exp(th1 - hl * (d * d));
             }
           } else if (row < n + 2 && c < n) {
             v[q] = (row == n) ? s.y[c] : s.c1[c];       // border rows
@@ -290,7 +290,7 @@ __device__ void indiv_eval_v3(const EvalSm2<NT>& s, int n, double th1, double th
   }
   for (int k = tid; k < n; k += TT) {
     const double d = s.piv[k];
-    v13[7] += log(d);
+    v13[7] += ev_log(d);
     if (!(d > 0.0)) *bad = 1;
   }
   tsync<TT>();
@@ -348,7 +348,7 @@ __device__ void indiv_eval_v3(const EvalSm2<NT>& s, int n, double th1, double th
           if (rok && c < n) {
             const double d = trv - s.t[c];
             const double g2 = hl * (d * d);
-            const double kv = (row == c) ? e1 : exp(th1 - g2);
+            const double kv = (row == c) ? e1 : ev_exp(th1 - g2);
             const double k2 = g2 * kv;            // dPsi/dth2 = g K0, zero on the diagonal
             const double pu = dtile ? pr * uv[c] : pr * uv[c] + pv[c] * ur;
             v13[9] += wgt * hq[q] * kv;
