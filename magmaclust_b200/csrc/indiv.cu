@@ -346,6 +346,10 @@ __global__ void __launch_bounds__(TT) indiv_mstep_kernel(IndivData dd, IndivWork
   }
 }
 
+// The optimiser update is ~7 k SASS instructions of which ~900 run per call (thread 0 only): kept out of line so that
+// the evaluation loop of the persistent kernels stays contiguous in the instruction cache.
+__device__ __noinline__ int lb_advance_dev(Lbfgs& o, double f, const double* g) { return lb_advance(o, f, g); }
+
 // ---- second design of the evaluator (indiv_eval2.cuh): same contracts as the two kernels above -------------------
 // VER = 2: indiv_eval2.cuh (rank-1 sweep on 4 x 4 register blocks), VER = 3: indiv_eval3.cuh (blocked DMMA sweep)
 template <int E, int TT, int NT, int VER>
@@ -456,7 +460,7 @@ __global__ void __launch_bounds__(TT, ((E > 1 || NT > 8) ? 256 : 512) / TT) indi
       const double a = opt.x[0], b = opt.x[1], c = opt.x[2];
       if constexpr (VER == 3) indiv_eval_v3<TT, NT>(s, n, a, b, c, true, out, &bad, slot);
       else indiv_eval_v2<E, TT, NT>(s, n, bI, bJ, a, b, c, true, out, &bad, slot);
-      if (threadIdx.x == 0) st = lb_advance(opt, out[0], out + 1);
+      if (threadIdx.x == 0) st = lb_advance_dev(opt, out[0], out + 1);
       tsync<TT>();
       if (st != LB_EVAL) break;
     }
