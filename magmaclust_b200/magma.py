@@ -489,6 +489,9 @@ def full_algo_clust(db, new_db, timestamps, kern_i, ini_tau_i_k=None, common_hp_
             "logL_iterations": list_hp.get("logL_iterations")}
 
 
+from .init_io import ini_kmeans, ini_tau_i_k, read_db_csv, write_db_csv  # noqa: E402,F401  (MAGMAclust.R:562-607)
+
+
 def pred_max_cluster(tau_i_k):
     """MC.R:349-355: which.max per individual (first maximum wins), 1-based."""
     names_k = list(tau_i_k.keys())
