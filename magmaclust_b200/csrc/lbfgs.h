@@ -15,8 +15,12 @@
 
 #ifdef __CUDACC__
 #define MCB_HD __host__ __device__ __forceinline__
+// the larger building blocks stay out of line in device code: the persistent M-step kernel is instruction-fetch bound and
+// this update runs on one thread between two evaluations (same arithmetic either way)
+#define MCB_HD_BIG static __host__ __device__ __noinline__
 #else
 #define MCB_HD inline
+#define MCB_HD_BIG static inline
 #endif
 
 namespace mcb {
@@ -32,7 +36,7 @@ struct LineSearch {
 };
 
 // one safeguarded cubic/quadratic interpolation step (More'-Thuente section 4)
-MCB_HD void mt_step(double& stx, double& fx, double& dx, double& sty, double& fy, double& dy, double& stp,
+MCB_HD_BIG void mt_step(double& stx, double& fx, double& dx, double& sty, double& fy, double& dy, double& stp,
                     double fp, double dp, int& brackt, double stpmin, double stpmax) {
   double sgnd = dp * (dx / fabs(dx));
   double stpf, stpc, stpq, theta, s, gamma, p, q, r;
@@ -187,7 +191,7 @@ MCB_HD void lb_init(Lbfgs& o, int D, const double* x0, int maxit = 100, double f
   o.stp = 0; o.f = 0;
 }
 
-MCB_HD void lb_direction(Lbfgs& o) {
+MCB_HD_BIG void lb_direction(Lbfgs& o) {
   // two-loop recursion over the stored pairs, newest first
   double q[LB_MAXD], alpha[LB_MEM];
   const int D = o.D;
@@ -217,7 +221,7 @@ MCB_HD void lb_direction(Lbfgs& o) {
   for (int j = 0; j < D; ++j) o.d[j] = -q[j];
 }
 
-MCB_HD void lb_begin_search(Lbfgs& o) {
+MCB_HD_BIG void lb_begin_search(Lbfgs& o) {
   const int D = o.D;
   for (;;) {
     lb_direction(o);
