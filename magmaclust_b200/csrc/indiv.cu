@@ -478,6 +478,66 @@ __global__ void __launch_bounds__(TT, ((E > 1 || NT > 8) ? 256 : 512) / TT) indi
   }
 }
 
+// E-step, part 1 on the evaluator machinery: the same register-blocked sweep (or blocked DMMA sweep) that the M-step uses
+// leaves W = Psi_i^-1, p = W y and y'Wy in shared memory (objective-only call with corr1 = 0 and corr2 = 0, for which
+// F = (n log 2pi + log|Psi| + y'Wy) / 2 gives the log determinant back); then the tau-weighted scatter onto A_k, w_k as
+// in indiv_factor_scatter_kernel, which remains the path for n_i > 80.
+template <int E, int TT, int NT, int VER>
+__global__ void __launch_bounds__(TT, ((E > 1 || NT > 8) ? 256 : 512) / TT) indiv_factor2_kernel(
+    IndivData dd, const double* __restrict__ theta_i, const double* __restrict__ tau, int K, double* __restrict__ acc,
+    int ldN, long long strideA, double* __restrict__ wk, IndivWork w, int* __restrict__ info) {
+  using G = Eval2Geo<NT>;
+  extern __shared__ __align__(16) double sm[];
+  __shared__ double out[4];
+  const int i = blockIdx.x;
+  const int o0 = dd.off[i], n = dd.off[i + 1] - o0;
+  EvalSm2<NT> s = eval2_carve<NT>(sm);
+  {
+    double2* z = reinterpret_cast<double2*>(s.W);
+    for (int e = threadIdx.x; e < G::MAT; e += TT) z[e] = make_double2(0.0, 0.0);   // W and S (= 0 here)
+    for (int e = threadIdx.x; e < 64; e += TT) s.red[64 + e] = 0.0;
+    for (int a = threadIdx.x; a < n; a += TT) {
+      s.t[a] = dd.t[o0 + a];
+      s.y[a] = dd.y[o0 + a];
+      s.c1[a] = 0.0;
+    }
+  }
+  tsync<TT>();
+  const double th1 = theta_i[3 * i], th2 = theta_i[3 * i + 1], sg = theta_i[3 * i + 2];
+  if constexpr (VER == 3) {
+    indiv_eval_v3<TT, NT>(s, n, th1, th2, sg, false, out, info, i);
+  } else {
+    int bI[E], bJ[E];
+    eval2_decode<E, TT>(n, bI, bJ);
+    indiv_eval_v2<E, TT, NT>(s, n, bI, bJ, th1, th2, sg, false, out, info, i);
+  }
+  // after the call: W in s.W (both triangles, ld = LDM), p in s.col, y'Wy in s.corner[0]
+  int* idx = reinterpret_cast<int*>(s.S);   // the S buffer is free from here on
+  for (int a = threadIdx.x; a < n; a += TT) idx[a] = dd.gidx[o0 + a];
+  double* Wg = w.Winv + dd.woff[i];
+  for (int e = threadIdx.x; e < n * n; e += TT) {
+    const int a = e / n, b = e - a * n;
+    Wg[e] = s.W[a * G::LDM + b];
+  }
+  for (int a = threadIdx.x; a < n; a += TT) w.pvec[o0 + a] = s.col[a];
+  if (threadIdx.x == 0) {
+    const double yWy = s.corner[0];
+    w.yWy[i] = yWy;
+    w.logdet[i] = 2.0 * out[0] - (double)n * kLog2Pi - yWy;
+  }
+  tsync<TT>();
+  for (int k = 0; k < K; ++k) {
+    const double tk = tau[(size_t)i * K + k];
+    if (tk == 0.0) continue;  // exact zeros (one-hot initial tau) contribute nothing
+    double* Ak = acc + k * strideA;
+    for (int e = threadIdx.x; e < n * n; e += TT) {
+      const int a = e / n, b = e - a * n;
+      atomicAdd(Ak + (size_t)idx[a] * ldN + idx[b], tk * s.W[a * G::LDM + b]);
+    }
+    for (int a = threadIdx.x; a < n; a += TT) atomicAdd(wk + (size_t)k * ldN + idx[a], tk * s.col[a]);
+  }
+}
+
 // -------------------------------------------------------------------------------------------------
 // host launchers
 // -------------------------------------------------------------------------------------------------
@@ -492,16 +552,6 @@ size_t tau_smem_bytes(int nmax, int K) {
 static cudaError_t set_smem(const void* fn, size_t bytes) {
   if (bytes <= 48 * 1024) return cudaSuccess;
   return cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-}
-
-cudaError_t launch_factor_scatter(cudaStream_t s, const IndivData& dd, int M, int nmax, const double* theta_i,
-                                  const double* tau, int K, double* acc, int ldN, long long strideA, double* wk,
-                                  const IndivWork& w, int* info) {
-  const size_t sm = factor_smem_bytes(nmax);
-  cudaError_t e = set_smem((const void*)indiv_factor_scatter_kernel, sm);
-  if (e != cudaSuccess) return e;
-  indiv_factor_scatter_kernel<<<M, kT, sm, s>>>(dd, theta_i, tau, K, acc, ldN, strideA, wk, w, info);
-  return cudaGetLastError();
 }
 
 cudaError_t launch_tau(cudaStream_t s, const IndivData& dd, int M, int nmax, int K, const double* mean,
@@ -590,6 +640,32 @@ static size_t eval2_smem_bytes(int NT) {
     else if (TT == 128 && E == 2 && NT == 10) MACRO(2, 128, 10, 2); \
     else return cudaErrorInvalidValue;                              \
   } while (0)
+
+cudaError_t launch_factor_scatter(cudaStream_t s, const IndivData& dd, int M, int nmax, const double* theta_i,
+                                  const double* tau, int K, double* acc, int ldN, long long strideA, double* wk,
+                                  const IndivWork& w, int* info) {
+  {
+    int TT, E, NT;
+    static const bool old_path = getenv("MCB_FACTOR_V1") != nullptr;
+    if (!old_path && eval2_shape(nmax, &TT, &E, &NT)) {
+      const size_t sm2 = eval2_smem_bytes(NT);
+      cudaError_t e2;
+#define MCB_LAUNCH_FACTOR2(EE, T_, N_, V_)                                                                              \
+  do {                                                                                                                 \
+    if ((e2 = set_smem_t(indiv_factor2_kernel<EE, T_, N_, V_>, sm2)) != cudaSuccess) return e2;                        \
+    indiv_factor2_kernel<EE, T_, N_, V_><<<M, T_, sm2, s>>>(dd, theta_i, tau, K, acc, ldN, strideA, wk, w, info);      \
+  } while (0)
+      MCB_DISPATCH_EVAL2(MCB_LAUNCH_FACTOR2);
+#undef MCB_LAUNCH_FACTOR2
+      return cudaGetLastError();
+    }
+  }
+  const size_t sm = factor_smem_bytes(nmax);
+  cudaError_t e = set_smem((const void*)indiv_factor_scatter_kernel, sm);
+  if (e != cudaSuccess) return e;
+  indiv_factor_scatter_kernel<<<M, kT, sm, s>>>(dd, theta_i, tau, K, acc, ldN, strideA, wk, w, info);
+  return cudaGetLastError();
+}
 
 cudaError_t launch_indiv_eval(cudaStream_t s, const IndivData& dd, int M, int nmax, const IndivWork& w,
                               const double* theta, int theta_stride, int want_grad, double* f, double* g,
