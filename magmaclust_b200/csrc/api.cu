@@ -88,6 +88,8 @@ extern "C" int mcb_create(mcb_handle** out, int device) {
   h->device = device;
   if ((e = cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking)) != cudaSuccess ||
       (e = cudaStreamCreateWithFlags(&h->st2, cudaStreamNonBlocking)) != cudaSuccess ||
+      (e = [&] { int lo = 0, hi = 0; cudaDeviceGetStreamPriorityRange(&lo, &hi);
+                 return cudaStreamCreateWithPriority(&h->st_hi, cudaStreamNonBlocking, hi); }()) != cudaSuccess ||
       (e = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming)) != cudaSuccess ||
       (e = cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming)) != cudaSuccess ||
       (e = h->mstep_ctl.ensure(mcb::kMstepCtlWords)) != cudaSuccess ||
@@ -110,6 +112,7 @@ extern "C" void mcb_destroy(mcb_handle* h) {
   for (auto& kv : h->eval_graphs) cudaGraphExecDestroy(kv.second.exec);
   if (h->mopt_exec) cudaGraphExecDestroy(h->mopt_exec);
   if (h->st_cap) cudaStreamDestroy(h->st_cap);
+  if (h->st_hi) cudaStreamDestroy(h->st_hi);
   h->mopt_state.release();
   for (auto e : h->evpool) cudaEventDestroy(e);
   mcb::DevBuf<double>* dbl[] = {&h->t, &h->y, &h->grid, &h->theta_i, &h->theta_k, &h->pi, &h->mk, &h->tau,
@@ -917,6 +920,7 @@ static int build_mean_opt_graph(mcb_handle* h) {
   H_CUDA(h->mopt_state.ensure(kMoptWords + 16));
   if (!h->st_cap) H_CUDA(cudaStreamCreateWithFlags(&h->st_cap, cudaStreamNonBlocking));
   double* state = h->mopt_state.p;
+  int* ginfo = h->info.p + 1;   // the loop's own not-positive-definite flag: it may run next to kernels that use info[0]
   double* result = state + kMoptWords;
   cudaGraph_t graph = nullptr;
   const long long before = h->launches;
@@ -931,6 +935,7 @@ static int build_mean_opt_graph(mcb_handle* h) {
   };
   cudaError_t ce;
   if ((ce = cudaMemsetAsync(result, 0, sizeof(double) * 16, h->st)) != cudaSuccess) return fail("memset", ce);
+  if ((ce = cudaMemsetAsync(ginfo, 0, sizeof(int), h->st)) != cudaSuccess) return fail("memset", ce);
   mean_opt_init_kernel<<<1, 32, 0, h->st>>>(h->theta_k.p, state, h->etheta.p, h->egmap.p, K);
   ++h->launches;
   sum_groups(h->st, N, ld, sN, h->cov.p, h->egmap.p, K, h->eCsum.p, 1, &h->launches);
@@ -967,7 +972,7 @@ static int build_mean_opt_graph(mcb_handle* h) {
         KTRACE(s, 0);
         se_build(s, h->eK.p, h->eD1.p, h->eD2.p, N, ld, sN, h->grid.p, h->etheta.p, 3, 1, &h->launches, &zj);
         KTRACE(s, 1);
-        ie = spd_inverse_slab(s, h->eK.p, N, ld, sN, 1, h->elogdet.p, h->info.p, h->ws, &h->launches, true);
+        ie = spd_inverse_slab(s, h->eK.p, N, ld, sN, 1, h->elogdet.p, ginfo, h->ws, &h->launches, true);
         MeanFuse mf{K, ld, h->rvec.p, h->pz.p, h->ered.p};
         KTRACE(s, 2);
         mean_stage1(s, N, h->eK.p, h->eCsum.p, h->eX.p, ld, h->eD1.p, h->eD2.p, mf, &h->launches);
@@ -979,7 +984,7 @@ static int build_mean_opt_graph(mcb_handle* h) {
       KTRACE(s, 0);
       se_build(s, h->eK.p, h->eD1.p, h->eD2.p, N, ld, sN, h->grid.p, h->etheta.p, 3, 1, &h->launches);
       KTRACE(s, 1);
-      ie = spd_inverse(s, h->eK.p, N, ld, sN, 1, h->elogdet.p, h->info.p, h->ws, &h->launches);
+      ie = spd_inverse(s, h->eK.p, N, ld, sN, 1, h->elogdet.p, ginfo, h->ws, &h->launches);
       KTRACE(s, 2);
       symv_mapped(s, N, ld, sN, h->eK.p, h->egmap.p, h->rvec.p, h->pz.p, K, &h->launches);
       double* redg = h->ered.p;
@@ -996,7 +1001,7 @@ static int build_mean_opt_graph(mcb_handle* h) {
       gemm_nt_trace(s, N, h->eX.p, ld, sN, h->eK.p, ld, sN, h->eD1.p, h->eD2.p, ld, sN, redt, 4, 1, &h->launches);
       KTRACE(s, 7);
     }
-    mean_opt_advance_kernel<<<1, 32, 0, s>>>(state, h->ered.p, h->elogdet.p, h->info.p, h->etheta.p, N, K, fused ? 1 : 0,
+    mean_opt_advance_kernel<<<1, 32, 0, s>>>(state, h->ered.p, h->elogdet.p, ginfo, h->etheta.p, N, K, fused ? 1 : 0,
                                              handle, result);
     ++h->launches;
     cudaError_t ee = cudaStreamEndCapture(s, nullptr);
@@ -1022,14 +1027,14 @@ static int build_mean_opt_graph(mcb_handle* h) {
 
 // Runs the whole optimisation; out[0..2] = theta, nfev / iterations returned through the pointers. Enqueue only when
 // !wait (the caller synchronises h->st later and then calls with collect = true).
-static int mean_opt_launch(mcb_handle* h) {
+static int mean_opt_launch(mcb_handle* h, cudaStream_t stream = nullptr) {
   if (h->mopt_exec && h->mopt_budget != h->ws.max_ctas) {  // captured with another SM budget
     cudaGraphExecDestroy(h->mopt_exec);
     h->mopt_exec = nullptr;
   }
   if (!h->mopt_exec) MCB_TRY(build_mean_opt_graph(h));
   h->mopt_budget = h->ws.max_ctas;
-  H_CUDA(cudaGraphLaunch(h->mopt_exec, h->st));
+  H_CUDA(cudaGraphLaunch(h->mopt_exec, stream ? stream : h->st));
   h->csum_valid = true;
   h->csum_gmap.assign(h->K, 0);
   return MCB_OK;
@@ -1065,6 +1070,21 @@ static int m_step_impl(mcb_handle* h, int common_hp_k, int common_hp_i, int* sta
   // replaces the third entry of theta_k afterwards, CF.R:666-668): run them concurrently.
   static const bool no_overlap = getenv("MCB_NO_OVERLAP") != nullptr;
   const bool overlap = !no_overlap && !common_hp_i && common_hp_k && spd_inverse_slab_ok(h->N, h->ld);
+  // Shared theta_i (one host-driven optimiser over sum_i F_i, one batched kernel per evaluation) and shared theta_k:
+  // the two optimisations are independent here too. The device-side theta_k loop goes to a high-priority stream, so
+  // its kernels (a few CTAs each) are placed as soon as CTAs of the batched theta_i evaluation retire.
+  static const bool host_loop_k = getenv("MCB_HOST_THETA_K") != nullptr || getenv("MCB_NO_GRAPH") != nullptr;
+  const bool overlap_c = !no_overlap && common_hp_i && common_hp_k && !host_loop_k && spd_inverse_slab_ok(h->N, h->ld);
+  if (overlap_c) {
+    H_CUDA(cudaEventRecord(h->ev_fork, h->st));
+    H_CUDA(cudaStreamWaitEvent(h->st_hi, h->ev_fork, 0));
+    {
+      PhaseScope ps(h, PH_MSTEP_K, h->st_hi);
+      h->ws.max_ctas = 0;
+      MCB_TRY(mean_opt_launch(h, h->st_hi));
+    }
+    H_CUDA(cudaEventRecord(h->ev_join, h->st_hi));
+  }
   // Work-queue order of the per-individual optimisations: longest first, predicted by the evaluation counts of
   // the previous M-step on the same individuals (shortens the tail of the persistent kernel).
   const int* order = nullptr;
@@ -1152,7 +1172,12 @@ static int m_step_impl(mcb_handle* h, int common_hp_k, int common_hp_i, int* sta
       // then discarded: opm(...)[1, 1:2] keeps (a, b) and pen_diag becomes the third entry (CF.R:666-668)
       Lbfgs opt;
       static const bool host_loop = getenv("MCB_HOST_THETA_K") != nullptr || getenv("MCB_NO_GRAPH") != nullptr;
-      if (!host_loop) {
+      if (overlap_c) {
+        // launched before the theta_i optimiser (above): join
+        H_CUDA(cudaStreamWaitEvent(h->st, h->ev_join, 0));
+        H_CUDA(cudaStreamSynchronize(h->st));
+        mean_opt_collect(h, opt.x, &nfev_k, &nit_k);
+      } else if (!host_loop) {
         // the loop runs on the device (WHILE graph node); one launch, one wait
         MCB_TRY(mean_opt_launch(h));
         H_CUDA(cudaStreamSynchronize(h->st));
