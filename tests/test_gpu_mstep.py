@@ -119,3 +119,23 @@ def test_m_step_matches_oracle_optimum(session, common_k, common_i):
         assert np.allclose(new_got["theta_k"][k], new_ref["theta_k"][k], atol=5e-3), k
     pen = np.mean([new_got["theta_i"][i][2] for i in new_got["theta_i"]])
     assert abs(new_got["theta_k"][next(iter(m_k))][2] - pen) < 1e-12
+
+
+def test_m_step_with_more_than_eight_clusters(session):
+    """K = 9 takes the unfused evaluation of the shared-theta_k objective inside the device-side optimiser loop (the fused
+    stages keep the per-cluster products K^-1 r_z in eight registers); same contract as above."""
+    from magmaclust_b200 import magma
+    db, hp, tau, m_k = small_problem(M=27, K=9, seed=6, common_hp_i=False)
+    first = next(iter(hp["theta_k"].values()))
+    hp["theta_k"] = {k: first.copy() for k in hp["theta_k"]}
+    ref, got = _setup(session, db, hp, tau, m_k)
+    new_ref = O.m_step_VEM(db, hp, ref, O.kernel_mu, O.kernel, m_k, True, False)
+    new_got = magma.m_step_VEM(db, hp, got, magma.kernel_mu, magma.kernel, m_k, True, False, session=session)
+    assert np.allclose(new_got["pi_k"], new_ref["pi_k"], rtol=0, atol=1e-12)
+    for k in new_ref["theta_k"]:
+        assert np.allclose(new_got["theta_k"][k], new_ref["theta_k"][k], atol=5e-3), k
+    th_g = next(iter(new_got["theta_k"].values()))
+    th_r = next(iter(new_ref["theta_k"].values()))
+    f_g = O.logL_GP_mod_common_hp_k(th_g[:2], ref["mean"], m_k, O.kernel_mu, ref["cov"], th_g[2])
+    f_r = O.logL_GP_mod_common_hp_k(th_r[:2], ref["mean"], m_k, O.kernel_mu, ref["cov"], th_r[2])
+    assert abs(f_g - f_r) <= 1e-5 * abs(f_r)
