@@ -98,8 +98,9 @@ struct GemmParams {
   const double* B; int ldb; long long sB;
   double* C; int ldc; long long sC;
   double alpha, beta;
-  // sweep epilogue
-  const double* Pbuf; long long sP; int c0, nb; double sign;
+  // sweep epilogue: pivot rows [r0p, r0p + nb), pivot columns [c0, c0 + nb) of C; column j of C is row j + cro of the
+  // full matrix (0 unless C is a column panel); Pbuf row stride ldp
+  const double* Pbuf; long long sP; int c0, nb; double sign; int r0p, cro, ldp;
   // trace epilogue
   const double* D1; const double* D2; int ldd; long long sD; double* out; int out_stride;
   // fused mean-process stages
@@ -208,7 +209,7 @@ __global__ void __launch_bounds__(128) gemm_nt_kernel(GemmParams p) {
         }
       } else if (MODE == EPI_SWEEP) {
         double* c = p.C + z * p.sC + (size_t)gi * p.ldc + gj;
-        const bool ip = gi >= p.c0 && gi < p.c0 + p.nb;
+        const bool ip = gi >= p.r0p && gi < p.r0p + p.nb;
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
           if (q == 1 && !two) break;
@@ -216,8 +217,8 @@ __global__ void __launch_bounds__(128) gemm_nt_kernel(GemmParams p) {
           const bool jp = gq >= p.c0 && gq < p.c0 + p.nb;
           double r;
           if (!ip && !jp) r = c[q] - acc[i][j][q];
-          else if (jp) r = p.Pbuf[z * p.sP + (size_t)gi * kNB + (gq - p.c0)];
-          else r = p.Pbuf[z * p.sP + (size_t)gq * kNB + (gi - p.c0)];
+          else if (jp) r = p.Pbuf[z * p.sP + (size_t)gi * p.ldp + (gq - p.c0)];
+          else r = p.Pbuf[z * p.sP + (size_t)(gq + p.cro) * p.ldp + (gi - p.r0p)];
           c[q] = p.sign * r;
         }
       } else if (MODE == EPI_TRACE) {
@@ -442,9 +443,12 @@ void mean_stage2(cudaStream_t s, int N, const double* X, const double* Kinv, int
 // fatal for smooth SE kernels with a small jitter.
 constexpr int kPanelRows = 32;
 
+// The pivot block sits at rows [c0, c0 + nb) and COLUMNS [cc0, cc0 + nb) of the matrix it is given: the two differ when
+// the matrix is a column panel of the full one (wide path below). V goes to Vbuf with row stride ldv.
 __global__ void __launch_bounds__(256) sweep_panel_kernel(const double* __restrict__ Aall, int N, int ld,
-                                                          long long stride, int c0, int nb,
-                                                          double* __restrict__ Vbuf, double* __restrict__ Pbuf,
+                                                          long long stride, int c0, int cc0, int nb,
+                                                          double* __restrict__ Vbuf, int ldv, long long sV,
+                                                          double* __restrict__ Pbuf,
                                                           long long sP, double* __restrict__ logdet,
                                                           int* __restrict__ info) {
   __shared__ double D[kNB][kNB + 1];
@@ -461,13 +465,13 @@ __global__ void __launch_bounds__(256) sweep_panel_kernel(const double* __restri
   for (int q = 0; q < 4; ++q) {
     const int c = tc + q;
     // identity padding keeps a partial last block a no-op for the extra pivots
-    D[ti][c] = (ti < nb && c < nb) ? A[(size_t)(c0 + ti) * ld + c0 + c] : (ti == c ? 1.0 : 0.0);
+    D[ti][c] = (ti < nb && c < nb) ? A[(size_t)(c0 + ti) * ld + cc0 + c] : (ti == c ? 1.0 : 0.0);
     W[ti][c] = (ti == c) ? 1.0 : 0.0;
     const int gr = r0 + ti;
     double v = 0.0;
     if (gr < N && c < nb) {
       if (gr >= c0 && gr < c0 + nb) v = (gr - c0 == c) ? 1.0 : 0.0;
-      else v = A[(size_t)gr * ld + c0 + c];
+      else v = A[(size_t)gr * ld + cc0 + c];
     }
     R[ti][c] = v;
   }
@@ -515,7 +519,7 @@ __global__ void __launch_bounds__(256) sweep_panel_kernel(const double* __restri
     double acc = 0.0;
     for (int b = 0; b <= c; ++b) acc += R[ti][b] * D[c][b];
     V[ti][c] = acc;
-    if (gr < N) Vbuf[z * sP + (size_t)gr * kNB + c] = acc;
+    if (gr < N) Vbuf[z * sV + (size_t)gr * ldv + c] = acc;
   }
   __syncthreads();
   // P = V L^-1 : P[r][c] = sum_{b>=c} V[r][b] Linv[b][c]
@@ -529,43 +533,98 @@ __global__ void __launch_bounds__(256) sweep_panel_kernel(const double* __restri
   }
 }
 
+constexpr int kWide = 128;   // outer pivot block of the large-grid path (4 inner blocks of kNB)
+
 cudaError_t spd_inverse_reserve(DenseWs& ws, int N, int Z) {
   const int ld16 = (N + 15) & ~15;
   if (spd_inverse_slab_ok(N, ld16)) return spd_inverse_slab_reserve(ws, N, Z);
   const int nblk = (N + kNB - 1) / kNB;
-  const size_t need = (size_t)nblk * kNB * kNB * Z;
+  const size_t rows = (size_t)nblk * kNB;
   cudaError_t e;
-  if ((e = ws.Pbuf.ensure(need)) != cudaSuccess) return e;
-  return ws.Cold.ensure(need);
+  if ((e = ws.Pbuf.ensure(rows * kWide * Z)) != cudaSuccess) return e;
+  if ((e = ws.Cold.ensure(rows * kWide * Z)) != cudaSuccess) return e;
+  return ws.red.ensure(rows * kNB * Z);
+}
+
+// Pn[r][c] = A[r][c0 + c] for c < nbw (zero beyond, and for the pad rows): the column panel of an outer block
+__global__ void panel_gather_kernel(const double* __restrict__ A, int N, int ld, long long stride, int c0, int nbw,
+                                    double* __restrict__ Pn, long long sPn, int rows) {
+  const int z = blockIdx.z;
+  const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (e >= (long long)rows * kWide) return;
+  const int r = (int)(e / kWide), c = (int)(e - (long long)r * kWide);
+  Pn[z * sPn + e] = (r < N && c < nbw) ? A[z * stride + (size_t)r * ld + c0 + c] : 0.0;
+}
+
+static void launch_sweep_update(cudaStream_t s, int M, int Ncols, int K, const double* Va, int lda, long long sA,
+                                const double* Vb, int ldb, long long sB, double* C, int ldc, long long sC,
+                                const double* P, int ldp, long long sP, int r0p, int c0, int nb, int cro, double sign,
+                                int Z) {
+  GemmParams p{};
+  p.M = M; p.N = Ncols; p.K = K;
+  p.A = Va; p.lda = lda; p.sA = sA;
+  p.B = Vb; p.ldb = ldb; p.sB = sB;
+  p.C = C; p.ldc = ldc; p.sC = sC;
+  p.Pbuf = P; p.sP = sP; p.ldp = ldp; p.r0p = r0p; p.c0 = c0; p.nb = nb; p.cro = cro;
+  p.sign = sign;
+  launch_gemm<EPI_SWEEP>(s, p, Z, nullptr);
 }
 
 cudaError_t spd_inverse(cudaStream_t s, double* A, int N, int ld, long long stride, int Z, double* logdet,
                         int* info, DenseWs& ws, long long* launches) {
   static const bool no_slab = getenv("MCB_NO_SLAB") != nullptr;
+  static const bool narrow = getenv("MCB_NARROW_SWEEP") != nullptr;
   if (!no_slab && ld % 16 == 0 && spd_inverse_slab_ok(N, ld))
     return spd_inverse_slab(s, A, N, ld, stride, Z, logdet, info, ws, launches);
   const int nblk = (N + kNB - 1) / kNB;
-  const long long sP = (long long)nblk * kNB * kNB;
+  const int rows = nblk * kNB;
   cudaError_t e;
-  {
-    const size_t need = (size_t)sP * Z;
-    if ((e = ws.Pbuf.ensure(need)) != cudaSuccess) return e;
-    if ((e = ws.Cold.ensure(need)) != cudaSuccess) return e;
-  }
+  if ((e = ws.Pbuf.ensure((size_t)rows * kWide * Z)) != cudaSuccess) return e;
+  if ((e = ws.Cold.ensure((size_t)rows * kWide * Z)) != cudaSuccess) return e;
+  if ((e = ws.red.ensure((size_t)rows * kNB * Z)) != cudaSuccess) return e;
   if ((e = cudaMemsetAsync(logdet, 0, sizeof(double) * Z, s)) != cudaSuccess) return e;
-  for (int b = 0; b < nblk; ++b) {
-    const int c0 = b * kNB;
-    const int nb = (N - c0 < kNB) ? N - c0 : kNB;
-    sweep_panel_kernel<<<dim3(nblk, 1, Z), 256, 0, s>>>(A, N, ld, stride, c0, nb, ws.Cold.p, ws.Pbuf.p, sP,
-                                                        logdet, info);
-    GemmParams p{};
-    p.M = N; p.N = N; p.K = kNB;
-    p.A = ws.Cold.p; p.lda = kNB; p.sA = sP;   // V
-    p.B = ws.Cold.p; p.ldb = kNB; p.sB = sP;   // V
-    p.C = A; p.ldc = ld; p.sC = stride;
-    p.Pbuf = ws.Pbuf.p; p.sP = sP; p.c0 = c0; p.nb = nb;
-    p.sign = (b == nblk - 1) ? -1.0 : 1.0;
-    launch_gemm<EPI_SWEEP>(s, p, Z, nullptr);
+  if (narrow) {
+    // first version: one rank-32 update of the whole matrix per 32 pivots (each re-reads and re-writes the matrix)
+    const long long sP = (long long)rows * kNB;
+    for (int b = 0; b < nblk; ++b) {
+      const int c0 = b * kNB;
+      const int nb = (N - c0 < kNB) ? N - c0 : kNB;
+      sweep_panel_kernel<<<dim3(nblk, 1, Z), 256, 0, s>>>(A, N, ld, stride, c0, c0, nb, ws.Cold.p, kNB, sP, ws.Pbuf.p,
+                                                          sP, logdet, info);
+      launch_sweep_update(s, N, N, kNB, ws.Cold.p, kNB, sP, ws.Cold.p, kNB, sP, A, ld, stride, ws.Pbuf.p, kNB, sP, c0,
+                          c0, nb, 0, (b == nblk - 1) ? -1.0 : 1.0, Z);
+      if (launches) *launches += 2;
+    }
+    return cudaGetLastError();
+  }
+  // Wide path: 128 pivots per pass over the matrix. The column panel A[:, B] of the outer block B is copied out and
+  // swept on its own (4 inner blocks of 32 pivots: factorisation, V_j, P_j and a rank-32 update of the 128 panel
+  // columns only, 8 MB at N = 8192); the V_j side by side are the operand of ONE rank-128 update of the whole matrix,
+  // whose epilogue takes the pivot rows / columns from the finished panel. Same arithmetic as 4 narrow steps (the
+  // updates of the columns outside B are additive), a quarter of the matrix traffic, and a GEMM with K = 128.
+  double* Pn = ws.Pbuf.p;     // [Z][rows][kWide] the panel, becomes P (= A[:, B] D^-1, -D^-1 on the pivot rows)
+  double* Vc = ws.Cold.p;     // [Z][rows][kWide] V_1 .. V_4
+  double* Pin = ws.red.p;     // [Z][rows][kNB]   P_j of the current inner block
+  const long long sW = (long long)rows * kWide, sI = (long long)rows * kNB;
+  const int nout = (N + kWide - 1) / kWide;
+  for (int ob = 0; ob < nout; ++ob) {
+    const int c0 = ob * kWide;
+    const int nbw = (N - c0 < kWide) ? N - c0 : kWide;
+    const long long nel = (long long)rows * kWide;
+    panel_gather_kernel<<<dim3((unsigned)((nel + 255) / 256), 1, Z), 256, 0, s>>>(A, N, ld, stride, c0, nbw, Pn, sW, rows);
+    const int nin = (nbw + kNB - 1) / kNB;
+    for (int j = 0; j < nin; ++j) {
+      const int cj = j * kNB;
+      const int nbj = (nbw - cj < kNB) ? nbw - cj : kNB;
+      sweep_panel_kernel<<<dim3(nblk, 1, Z), 256, 0, s>>>(Pn, N, kWide, sW, c0 + cj, cj, nbj, Vc + cj, kWide, sW, Pin, sI,
+                                                          logdet, info);
+      // panel columns: Pn[i][c] -= V_j[i] . V_j[c0 + c] (column c of the panel is row c0 + c of the matrix)
+      launch_sweep_update(s, N, nbw, kNB, Vc + cj, kWide, sW, Vc + (size_t)c0 * kWide + cj, kWide, sW, Pn, kWide, sW, Pin,
+                          kNB, sI, c0 + cj, cj, nbj, c0, 1.0, Z);
+      if (launches) *launches += 2;
+    }
+    launch_sweep_update(s, N, N, nin * kNB, Vc, kWide, sW, Vc, kWide, sW, A, ld, stride, Pn, kWide, sW, c0, c0, nbw, 0,
+                        (ob == nout - 1) ? -1.0 : 1.0, Z);
     if (launches) *launches += 2;
   }
   return cudaGetLastError();

@@ -52,3 +52,16 @@ def test_estep_one_hot_tau_and_vector_prior(session):
     ref = O.e_step_VEM(db, m_k, O.kernel_mu, O.kernel, hp, tau)
     got = magma.e_step_VEM(db, m_k, magma.kernel_mu, magma.kernel, hp, tau, session=session)
     assert_param_close(got, ref, names)
+
+
+def test_estep_large_grid_takes_the_multi_launch_inverse(session):
+    """N > 768 union timestamps: the N x N solves leave the shared-memory slab kernel for the multi-launch blocked sweep
+    (128 pivots per pass over the matrix: panel sweeps + one rank-128 DMMA update, dense.cu)"""
+    from magmaclust_b200 import magma
+    db, hp, tau, m_k = small_problem(M=90, K=2, n=(25, 30), n_grid=1000, seed=13)
+    N = np.unique(db["Timestamp"]).shape[0]
+    assert N > 768
+    ref = O.e_step_VEM(db, m_k, O.kernel_mu, O.kernel, hp, tau, return_logL=True)
+    got = magma.e_step_VEM(db, m_k, magma.kernel_mu, magma.kernel, hp, tau, session=session)
+    assert_param_close(got, ref, list(m_k.keys()))
+    assert rel_err(got["mat_logL"], ref["mat_logL"]) < RTOL_LL
