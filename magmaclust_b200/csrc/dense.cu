@@ -101,6 +101,7 @@ struct GemmParams {
   // sweep epilogue: pivot rows [r0p, r0p + nb), pivot columns [c0, c0 + nb) of C; column j of C is row j + cro of the
   // full matrix (0 unless C is a column panel); Pbuf row stride ldp
   const double* Pbuf; long long sP; int c0, nb; double sign; int r0p, cro, ldp;
+  int sym;   // C symmetric and A == B: only the tiles on and below the diagonal are computed, results are mirrored
   // trace epilogue
   const double* D1; const double* D2; int ldd; long long sD; double* out; int out_stride;
   // fused mean-process stages
@@ -135,6 +136,7 @@ __global__ void __launch_bounds__(128) gemm_nt_kernel(GemmParams p) {
   const double* B = p.B + z * p.sB;
   const int K16 = (p.K + 15) & ~15;
   if (MODE == EPI_TRACE_F && n0 > m0 + BM - 1) return;   // G = X Kinv is symmetric: strictly upper tiles are not needed
+  if (MODE == EPI_SWEEP && p.sym && n0 > m0 + BM - 1) return;
 
   double acc[FM][FN][2];
 #pragma unroll
@@ -214,12 +216,14 @@ __global__ void __launch_bounds__(128) gemm_nt_kernel(GemmParams p) {
         for (int q = 0; q < 2; ++q) {
           if (q == 1 && !two) break;
           const int gq = gj + q;
+          if (p.sym && gq > gi) continue;   // owned by the tile that holds (gq, gi): it mirrors its result up here
           const bool jp = gq >= p.c0 && gq < p.c0 + p.nb;
           double r;
           if (!ip && !jp) r = c[q] - acc[i][j][q];
           else if (jp) r = p.Pbuf[z * p.sP + (size_t)gi * p.ldp + (gq - p.c0)];
           else r = p.Pbuf[z * p.sP + (size_t)(gq + p.cro) * p.ldp + (gi - p.r0p)];
           c[q] = p.sign * r;
+          if (p.sym && gq < gi) p.C[z * p.sC + (size_t)gq * p.ldc + gi] = p.sign * r;
         }
       } else if (MODE == EPI_TRACE) {
         const size_t o = z * p.sD + (size_t)gi * p.ldd + gj;
@@ -559,7 +563,7 @@ __global__ void panel_gather_kernel(const double* __restrict__ A, int N, int ld,
 static void launch_sweep_update(cudaStream_t s, int M, int Ncols, int K, const double* Va, int lda, long long sA,
                                 const double* Vb, int ldb, long long sB, double* C, int ldc, long long sC,
                                 const double* P, int ldp, long long sP, int r0p, int c0, int nb, int cro, double sign,
-                                int Z) {
+                                int Z, int sym = 0) {
   GemmParams p{};
   p.M = M; p.N = Ncols; p.K = K;
   p.A = Va; p.lda = lda; p.sA = sA;
@@ -567,6 +571,7 @@ static void launch_sweep_update(cudaStream_t s, int M, int Ncols, int K, const d
   p.C = C; p.ldc = ldc; p.sC = sC;
   p.Pbuf = P; p.sP = sP; p.ldp = ldp; p.r0p = r0p; p.c0 = c0; p.nb = nb; p.cro = cro;
   p.sign = sign;
+  p.sym = sym;
   launch_gemm<EPI_SWEEP>(s, p, Z, nullptr);
 }
 
@@ -624,7 +629,7 @@ cudaError_t spd_inverse(cudaStream_t s, double* A, int N, int ld, long long stri
       if (launches) *launches += 2;
     }
     launch_sweep_update(s, N, N, nin * kNB, Vc, kWide, sW, Vc, kWide, sW, A, ld, stride, Pn, kWide, sW, c0, c0, nbw, 0,
-                        (ob == nout - 1) ? -1.0 : 1.0, Z);
+                        (ob == nout - 1) ? -1.0 : 1.0, Z, 1);
     if (launches) *launches += 2;
   }
   return cudaGetLastError();
