@@ -537,7 +537,7 @@ __global__ void __launch_bounds__(256) sweep_panel_kernel(const double* __restri
   }
 }
 
-constexpr int kWide = 128;   // outer pivot block of the large-grid path (4 inner blocks of kNB)
+constexpr int kWide = 256;   // outer pivot block of the large-grid path (8 inner blocks of kNB)
 
 cudaError_t spd_inverse_reserve(DenseWs& ws, int N, int Z) {
   const int ld16 = (N + 15) & ~15;
