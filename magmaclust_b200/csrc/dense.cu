@@ -191,6 +191,40 @@ __global__ void __launch_bounds__(128) gemm_nt_kernel(GemmParams p) {
     }
   }
 
+  if constexpr (MODE == EPI_SWEEP) {
+    // Fast path for the tiles of the rank-k update that touch neither the pivot rows / columns nor the matrix edge (nor,
+    // in the symmetric case, the diagonal): all C values of the thread are requested in one batch of independent
+    // 16-byte loads (the generic loop below interleaves loads, tests and stores and was the longer half of the kernel)
+    const bool clean = (m0 + BM <= p.r0p || m0 >= p.r0p + p.nb) && (n0 + BN <= p.c0 || n0 >= p.c0 + p.nb) &&
+                       m0 + BM <= p.M && n0 + BN <= p.N && (!p.sym || n0 + BN - 1 < m0) && (p.ldc % 2 == 0);
+    if (clean) {
+      double* Cz = p.C + z * p.sC;
+      double2 cv[FM][FN];
+#pragma unroll
+      for (int i = 0; i < FM; ++i)
+#pragma unroll
+        for (int j = 0; j < FN; ++j)
+          cv[i][j] = *reinterpret_cast<const double2*>(Cz + (size_t)(m0 + wm + 8 * i + (lane >> 2)) * p.ldc + n0 + wn +
+                                                       8 * j + (lane & 3) * 2);
+#pragma unroll
+      for (int i = 0; i < FM; ++i) {
+        const int gi = m0 + wm + 8 * i + (lane >> 2);
+#pragma unroll
+        for (int j = 0; j < FN; ++j) {
+          const int gj = n0 + wn + 8 * j + (lane & 3) * 2;
+          const double r0 = p.sign * (cv[i][j].x - acc[i][j][0]);
+          const double r1 = p.sign * (cv[i][j].y - acc[i][j][1]);
+          *reinterpret_cast<double2*>(Cz + (size_t)gi * p.ldc + gj) = make_double2(r0, r1);
+          if (p.sym) {
+            Cz[(size_t)gj * p.ldc + gi] = r0;
+            Cz[(size_t)(gj + 1) * p.ldc + gi] = r1;
+          }
+        }
+      }
+      return;
+    }
+  }
+
   double t1 = 0, t2 = 0, t0 = 0, u1 = 0, u2 = 0;
 #pragma unroll
   for (int i = 0; i < FM; ++i) {
