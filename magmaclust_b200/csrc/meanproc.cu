@@ -52,7 +52,7 @@ __global__ void cluster_reduce_kernel(int N, int ld, long long stride, const dou
   const int g = gmap[z];
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
-  if (row >= N) return;
+  if (row >= N || g < 0) return;   // g < 0: cluster not part of this evaluation
   const double* pz = p + (size_t)z * ld;
   double u1 = 0, u2 = 0;
   if (D1) {
@@ -86,7 +86,7 @@ __global__ void symv_mapped_kernel(int N, int ld, long long stride, const double
   const int z = blockIdx.z;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
-  if (row >= N) return;
+  if (row >= N || gmap[z] < 0) return;   // gmap < 0: cluster not part of this evaluation (its p is not used)
   const double* a = Kinv + gmap[z] * stride + (size_t)row * ld;
   const double* x = r + (size_t)z * ld;
   double acc = 0;

@@ -138,4 +138,4 @@ def test_m_step_with_more_than_eight_clusters(session):
     th_r = next(iter(new_ref["theta_k"].values()))
     f_g = O.logL_GP_mod_common_hp_k(th_g[:2], ref["mean"], m_k, O.kernel_mu, ref["cov"], th_g[2])
     f_r = O.logL_GP_mod_common_hp_k(th_r[:2], ref["mean"], m_k, O.kernel_mu, ref["cov"], th_r[2])
-    assert abs(f_g - f_r) <= 1e-5 * abs(f_r)
+    assert f_g <= f_r + 1e-5 * abs(f_r)   # the GPU optimum is not worse (it may be slightly better: end points are loose)
