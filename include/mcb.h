@@ -155,6 +155,18 @@ int mcb_predict(mcb_handle* h, int B, const int* offsets, const int* obs_idx, co
                 const double* theta_new, const double* pi_k, int Tp, const int* pred_idx, double* out_tau,
                 double* out_mean, double* out_var);
 
+/* ---- stand-alone building blocks (the vector branches the reference also calls directly, e.g. MC.R:261-264) ------------ */
+/* kern_to_cov(x, kern, theta, sigma), vector branch CF.R:68-86: SE covariance of the SORTED timestamps x[n] (the reference
+ * sorts them, CF.R:76; pass them sorted), theta2 = (a, b): exp(a - exp(-b)/2 d^2) off the diagonal, exp(a) + sigma^2 on it.
+ * out: n x n row-major. */
+int mcb_kern_to_cov(mcb_handle* h, int n, const double* x, const double* theta2, double sigma, double* out);
+/* kern_to_inv(x, kern, theta, sigma), vector branch CF.R:130-149: inverse of the matrix above (+ log det of the covariance in
+ * *logdet when not NULL). MCB_ENOTPD where the reference would fall over to MASS::ginv. */
+int mcb_kern_to_inv(mcb_handle* h, int n, const double* x, const double* theta2, double sigma, double* out, double* logdet);
+/* dmvnorm(x, mu, inv_Sigma, log) CF.R:10-35: Gaussian (log-)density from a symmetric positive definite PRECISION matrix
+ * inv_Sigma (n x n row-major): -(n log 2pi - log det inv_Sigma + z' inv_Sigma z) / 2, z = x - mu. */
+int mcb_dmvnorm(mcb_handle* h, int n, const double* x, const double* mu, const double* inv_Sigma, int want_log, double* out);
+
 /* ---- measurement helpers ----------------------------------------------------------------------------- */
 /* Device time (ms, CUDA events on the handle's stream) of the kernels launched by the last compute call,
  * per phase: [0] per-individual E-step kernel, [1] dense hyper-posterior, [2] tau kernel, [3] M-step

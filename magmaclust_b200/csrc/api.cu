@@ -117,7 +117,7 @@ extern "C" void mcb_destroy(mcb_handle* h) {
   for (auto e : h->evpool) cudaEventDestroy(e);
   mcb::DevBuf<double>* dbl[] = {&h->t, &h->y, &h->grid, &h->theta_i, &h->theta_k, &h->pi, &h->mk, &h->tau,
                                 &h->theta_i_new, &h->theta_k_new, &h->pi_new, &h->tau_new, &h->logL, &h->Winv,
-                                &h->pvec, &h->yWy, &h->logdet_i, &h->c1, &h->c2, &h->Fi, &h->Fnew, &h->fi_tmp, &h->gi_tmp,
+                                &h->pvec, &h->yWy, &h->logdet_i, &h->c1, &h->c2, &h->Fi, &h->Fnew, &h->kscr, &h->fi_tmp, &h->gi_tmp,
                                 &h->theta_g, &h->Kinv, &h->cov, &h->wk, &h->mean, &h->rvec, &h->pz, &h->logdetK,
                                 &h->logdetA, &h->eK, &h->eD1, &h->eD2, &h->eCsum, &h->eX, &h->etheta, &h->ered,
                                 &h->elogdet, &h->ws.Pbuf, &h->ws.Cold, &h->ws.red, &h->ws.slabV, &h->ws.slabP, &h->ws.slabL, &h->scal, &h->pgrid, &h->pKinv,
@@ -1341,6 +1341,118 @@ extern "C" int mcb_vem_iteration(mcb_handle* h, int common_hp_k, int common_hp_i
 // ---- measurement -------------------------------------------------------------------------------------
 // out[0..3] as mcb_m_step's stats; out[4] = total number of individual objective+gradient evaluations of the
 // last M-step on this rank (sum over individuals), out[5] = number of individuals
+// ---- stand-alone building blocks ---------------------------------------------------------------------------------
+// scratch layout in h->kscr: [matrix n x ld][second matrix n x ld][x (ld)][theta 3][logdet 1][quad 1]
+static int kern_scratch(mcb_handle* h, int n, int* ld_out, double** mat, double** mat2, double** vec, double** small) {
+  const int ld = (n + 15) & ~15;
+  const size_t need = 2 * (size_t)n * ld + 2 * (size_t)ld + 16;
+  H_CUDA(h->kscr.ensure(need));
+  *ld_out = ld;
+  *mat = h->kscr.p;
+  *mat2 = *mat + (size_t)n * ld;
+  *vec = *mat2 + (size_t)n * ld;
+  *small = *vec + 2 * (size_t)ld;
+  return MCB_OK;
+}
+
+static int kern_build(mcb_handle* h, int n, const double* x, const double* theta2, double sigma, double** mat_out,
+                      int* ld_out, double** small_out) {
+  for (int a = 1; a < n; ++a) H_CHECK(x[a] >= x[a - 1], MCB_EINVAL, "kern_to_cov / kern_to_inv: timestamps must be sorted");
+  int ld;
+  double *mat, *mat2, *vec, *small;
+  MCB_TRY(kern_scratch(h, n, &ld, &mat, &mat2, &vec, &small));
+  const double th[3] = {theta2[0], theta2[1], sigma};
+  H_CUDA(cudaMemcpyAsync(vec, x, sizeof(double) * n, cudaMemcpyHostToDevice, h->st));
+  H_CUDA(cudaMemcpyAsync(small, th, sizeof th, cudaMemcpyHostToDevice, h->st));
+  H_CUDA(cudaMemsetAsync(mat, 0, sizeof(double) * (size_t)n * ld, h->st));   // zero pads (contract of the dense toolkit)
+  se_build(h->st, mat, nullptr, nullptr, n, ld, (long long)n * ld, vec, small, 3, 1, &h->launches);
+  *mat_out = mat;
+  *ld_out = ld;
+  *small_out = small;
+  return MCB_OK;
+}
+
+extern "C" int mcb_kern_to_cov(mcb_handle* h, int n, const double* x, const double* theta2, double sigma, double* out) {
+  if (!h) return MCB_EINVAL;
+  H_CHECK(n >= 1 && x && theta2 && out, MCB_EINVAL, "mcb_kern_to_cov: bad argument");
+  H_CUDA(cudaSetDevice(h->device));
+  double *mat, *small;
+  int ld;
+  MCB_TRY(kern_build(h, n, x, theta2, sigma, &mat, &ld, &small));
+  H_CUDA(cudaMemcpy2DAsync(out, sizeof(double) * n, mat, sizeof(double) * ld, sizeof(double) * n, n,
+                           cudaMemcpyDeviceToHost, h->st));
+  H_CUDA(cudaStreamSynchronize(h->st));
+  return MCB_OK;
+}
+
+extern "C" int mcb_kern_to_inv(mcb_handle* h, int n, const double* x, const double* theta2, double sigma, double* out,
+                               double* logdet) {
+  if (!h) return MCB_EINVAL;
+  H_CHECK(n >= 1 && x && theta2 && out, MCB_EINVAL, "mcb_kern_to_inv: bad argument");
+  H_CUDA(cudaSetDevice(h->device));
+  double *mat, *small;
+  int ld;
+  MCB_TRY(kern_build(h, n, x, theta2, sigma, &mat, &ld, &small));
+  h->ws.max_ctas = 0;
+  H_CUDA(cudaMemsetAsync(h->info.p, 0, sizeof(int), h->st));
+  H_CUDA(spd_inverse(h->st, mat, n, ld, (long long)n * ld, 1, small + 4, h->info.p, h->ws, &h->launches));
+  H_CUDA(cudaMemcpy2DAsync(out, sizeof(double) * n, mat, sizeof(double) * ld, sizeof(double) * n, n,
+                           cudaMemcpyDeviceToHost, h->st));
+  H_CUDA(cudaMemcpyAsync(h->hbuf + 640, small + 4, sizeof(double), cudaMemcpyDeviceToHost, h->st));
+  MCB_TRY(check_info(h, "kern_to_inv"));
+  if (logdet) *logdet = h->hbuf[640];
+  return MCB_OK;
+}
+
+// quad[0] = z' A z with z = x - mu (one CTA; A n x ld)
+__global__ void quad_form_kernel(int n, int ld, const double* __restrict__ A, const double* __restrict__ x,
+                                 const double* __restrict__ mu, double* __restrict__ quad) {
+  __shared__ double red[32];
+  double acc = 0.0;
+  for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+    const int a = e / n, b = e - a * n;
+    acc += (x[a] - mu[a]) * A[(size_t)a * ld + b] * (x[b] - mu[b]);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[w];
+    quad[0] = s;
+  }
+}
+
+extern "C" int mcb_dmvnorm(mcb_handle* h, int n, const double* x, const double* mu, const double* inv_Sigma, int want_log,
+                           double* out) {
+  if (!h) return MCB_EINVAL;
+  H_CHECK(n >= 1 && x && mu && inv_Sigma && out, MCB_EINVAL, "mcb_dmvnorm: bad argument");
+  H_CUDA(cudaSetDevice(h->device));
+  int ld;
+  double *mat, *mat2, *vec, *small;
+  MCB_TRY(kern_scratch(h, n, &ld, &mat, &mat2, &vec, &small));
+  H_CUDA(cudaMemsetAsync(mat, 0, sizeof(double) * 2 * (size_t)n * ld, h->st));
+  H_CUDA(cudaMemcpy2DAsync(mat, sizeof(double) * ld, inv_Sigma, sizeof(double) * n, sizeof(double) * n, n,
+                           cudaMemcpyHostToDevice, h->st));
+  H_CUDA(cudaMemcpy2DAsync(mat2, sizeof(double) * ld, inv_Sigma, sizeof(double) * n, sizeof(double) * n, n,
+                           cudaMemcpyHostToDevice, h->st));
+  H_CUDA(cudaMemcpyAsync(vec, x, sizeof(double) * n, cudaMemcpyHostToDevice, h->st));
+  H_CUDA(cudaMemcpyAsync(vec + ld, mu, sizeof(double) * n, cudaMemcpyHostToDevice, h->st));
+  quad_form_kernel<<<1, 256, 0, h->st>>>(n, ld, mat2, vec, vec + ld, small + 5);
+  ++h->launches;
+  // log det of the precision matrix from the pivots of its factorisation (the inverse itself is not used)
+  h->ws.max_ctas = 0;
+  H_CUDA(cudaMemsetAsync(h->info.p, 0, sizeof(int), h->st));
+  H_CUDA(spd_inverse(h->st, mat, n, ld, (long long)n * ld, 1, small + 4, h->info.p, h->ws, &h->launches));
+  H_CUDA(cudaMemcpyAsync(h->hbuf + 640, small + 4, sizeof(double) * 2, cudaMemcpyDeviceToHost, h->st));
+  MCB_TRY(check_info(h, "dmvnorm"));
+  const double logdet_prec = h->hbuf[640], ssq = h->hbuf[641];
+  const double ll = -0.5 * ((double)n * kLog2Pi - logdet_prec + ssq);
+  *out = want_log ? ll : exp(ll);
+  return MCB_OK;
+}
+
 extern "C" int mcb_last_mstep_stats(mcb_handle* h, long long out[6]) {
   if (!h || !out) return MCB_EINVAL;
   H_CHECK(h->has_cand, MCB_ESTATE, "mcb_last_mstep_stats: no M-step has run");

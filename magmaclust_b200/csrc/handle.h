@@ -38,6 +38,7 @@ struct mcb_handle {
   // ---- per-individual work ----
   mcb::DevBuf<double> Winv, pvec, yWy, logdet_i, c1, c2, Fi, fi_tmp, gi_tmp;
   mcb::DevBuf<int> nfev_i, niter_i, status_i, order_i;
+  mcb::DevBuf<double> kscr;   // scratch of the stand-alone kern_to_cov / kern_to_inv / dmvnorm entry points
   mcb::DevBuf<double> Fnew;   // F_i at theta_i_new as left by the per-individual M-step kernel
   bool fnew_valid = false;
   bool nfev_valid = false;   // nfev_i holds the counts of a previous per-individual M-step on this data set

@@ -204,6 +204,32 @@ class Engine:
         return float(out[0]), float(out[1]), bool(out[2] != 0.0)
 
     # ------------------------------------------------------------------------------------------
+    def kern_to_cov(self, x, theta2, sigma):
+        """vector branch of kern_to_cov (CF.R:68-86) for SORTED timestamps x; n x n array"""
+        x, th = f64(x), f64(theta2)
+        out = np.empty((x.shape[0], x.shape[0]))
+        self._ck(self.lib.mcb_kern_to_cov(self.h, x.shape[0], dptr(x), dptr(th), float(sigma), dptr(out)))
+        return out
+
+    def kern_to_inv(self, x, theta2, sigma):
+        """vector branch of kern_to_inv (CF.R:130-149) for SORTED timestamps x; (inverse, log det of the covariance)"""
+        x, th = f64(x), f64(theta2)
+        out = np.empty((x.shape[0], x.shape[0]))
+        ld = C.c_double(0.0)
+        self._ck(self.lib.mcb_kern_to_inv(self.h, x.shape[0], dptr(x), dptr(th), float(sigma), dptr(out), C.byref(ld)))
+        return out, float(ld.value)
+
+    def dmvnorm(self, x, mu, inv_Sigma, log=False):
+        """dmvnorm (CF.R:10-35) from a precision matrix"""
+        x, mu, P = f64(np.atleast_1d(x)), f64(np.atleast_1d(mu)), f64(np.atleast_2d(inv_Sigma))
+        n = mu.shape[0]
+        if P.shape != (n, n) or x.shape[0] != n:
+            raise ValueError("incompatible arguments")
+        out = C.c_double(0.0)
+        self._ck(self.lib.mcb_dmvnorm(self.h, n, dptr(x), dptr(mu), dptr(P), 1 if log else 0, C.byref(out)))
+        return float(out.value)
+
+    # ------------------------------------------------------------------------------------------
     def posterior_mu_k(self, timestamps, tau=None, want_mean=True, want_cov=True):
         ts = f64(timestamps)
         T = ts.shape[0]

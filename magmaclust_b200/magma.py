@@ -183,6 +183,77 @@ def default_session():
 
 
 # ---------------------------------------------------------------------------------------------
+# building blocks the reference also exposes (CF.R:10-191, 436-446)
+# ---------------------------------------------------------------------------------------------
+def mat_dist(x, y):
+    """CF.R:37-40 -- squared distances between all pairs of x and y (host: a pure index pattern, no arithmetic to offload)."""
+    x = np.atleast_1d(np.asarray(x, dtype=np.float64))
+    y = np.atleast_1d(np.asarray(y, dtype=np.float64))
+    d = x[:, None] - y[None, :]
+    return d * d
+
+
+def deriv_hp1(mat, theta):
+    """CF.R:436-439 -- d kernel / d theta1 on squared distances (host formula; on the device it is fused into the gradient kernels)."""
+    return np.exp(theta[0] - np.exp(-theta[1]) / 2.0 * np.asarray(mat, dtype=np.float64))
+
+
+def deriv_hp2(mat, theta):
+    """CF.R:441-446 -- d kernel / d theta2 on squared distances."""
+    grad = 0.5 * np.exp(-theta[1]) * np.asarray(mat, dtype=np.float64)
+    return np.exp(theta[0]) * grad * np.exp(-grad)
+
+
+def _per_id_theta(db, theta, sigma):
+    ids = Canon(db).ids
+    if isinstance(theta, dict):
+        return ids, {i: np.asarray(theta[i], dtype=np.float64) for i in ids}
+    th = np.r_[np.asarray(theta, dtype=np.float64)[:2], sigma]
+    return ids, {i: th for i in ids}
+
+
+def kern_to_cov(x, kern=kernel, theta=(1.0, 0.5), sigma=0.2, session=None):
+    """CF.R:61-121 -- covariance matrix of a vector of timestamps (sorted like the reference does, CF.R:76), or one per
+    individual for a `db` (theta: dict ID -> (a, b, sigma), or one (a, b) with `sigma`). Built on the GPU."""
+    _check_kernels(kern)
+    s = session or default_session()
+    if not isinstance(x, dict):
+        xs = np.sort(np.atleast_1d(np.asarray(x, dtype=np.float64)))
+        return NamedMat(s.eng.kern_to_cov(xs, np.asarray(theta, dtype=np.float64)[:2], sigma), xs)
+    ids, th = _per_id_theta(x, theta, sigma)
+    idc, ts = np.asarray(x["ID"]), np.asarray(x["Timestamp"], dtype=np.float64)
+    out = {}
+    for i in ids:
+        xs = np.sort(ts[idc == i])
+        out[i] = NamedMat(s.eng.kern_to_cov(xs, th[i][:2], th[i][2]), xs)
+    return next(iter(out.values())) if len(out) == 1 else out
+
+
+def kern_to_inv(x, kern=kernel, theta=(1.0, 0.5), sigma=0.2, session=None):
+    """CF.R:123-191 -- inverse covariance (same argument conventions as kern_to_cov; in the db branch theta[[i]][3] is
+    the noise sd, CF.R:157-176). Raises McbError (MCB_ENOTPD) where the reference would switch to MASS::ginv."""
+    _check_kernels(kern)
+    s = session or default_session()
+    if not isinstance(x, dict):
+        xs = np.sort(np.atleast_1d(np.asarray(x, dtype=np.float64)))
+        return NamedMat(s.eng.kern_to_inv(xs, np.asarray(theta, dtype=np.float64)[:2], sigma)[0], xs)
+    ids, th = _per_id_theta(x, theta, sigma)
+    idc, ts = np.asarray(x["ID"]), np.asarray(x["Timestamp"], dtype=np.float64)
+    out = {}
+    for i in ids:
+        xs = np.sort(ts[idc == i])
+        out[i] = NamedMat(s.eng.kern_to_inv(xs, th[i][:2], th[i][2])[0], xs)
+    return next(iter(out.values())) if len(out) == 1 else out
+
+
+def dmvnorm(x, mu, inv_Sigma, log=False, session=None):
+    """CF.R:10-35 -- Gaussian (log-)density from a precision matrix."""
+    s = session or default_session()
+    P = inv_Sigma.m if isinstance(inv_Sigma, NamedMat) else inv_Sigma
+    return s.eng.dmvnorm(x, mu, P, log)
+
+
+# ---------------------------------------------------------------------------------------------
 # E step / M step (CF.R:589-687)
 # ---------------------------------------------------------------------------------------------
 def e_step_VEM(db, m_k, kern_0, kern_i, hp, old_tau_i_k, session=None, want_cov=True):

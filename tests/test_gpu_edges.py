@@ -151,3 +151,37 @@ def test_full_algo_clust_end_to_end(session):
         assert abs(got["Hyperparameters"]["new_i"]["tau_k"][k] - ref["Hyperparameters"]["new_i"]["tau_k"][k]) < 1e-3
         assert np.allclose(got["Prediction"][k]["Mean"], ref["Prediction"][k]["Mean"], rtol=2e-3, atol=2e-3)
         assert np.allclose(got["Prediction"][k]["Var"], ref["Prediction"][k]["Var"], rtol=5e-3, atol=1e-4)
+
+
+@pytest.mark.parametrize("n", [1, 2, 7, 33, 120, 801])
+def test_standalone_kern_to_cov_inv_dmvnorm(session, n):
+    """the vector branches of kern_to_cov / kern_to_inv (CF.R:61-149) and dmvnorm (CF.R:10-35) as their own entry points
+    (n = 801 takes the multi-launch inverse)"""
+    from magmaclust_b200 import magma
+    rng = np.random.default_rng(n)
+    x = rng.permutation(np.round(np.sort(rng.uniform(0, 10, n)), 6))        # unsorted on purpose: both sides sort
+    theta, sigma = (0.8, 0.3), 0.45
+    c_ref, c_got = O.kern_to_cov(x, O.kernel, theta, sigma), magma.kern_to_cov(x, magma.kernel, theta, sigma, session=session)
+    assert np.array_equal(c_ref.t, c_got.t)
+    assert rel_err(c_got.m, c_ref.m) < 1e-14
+    i_ref, i_got = O.kern_to_inv(x, O.kernel, theta, sigma), magma.kern_to_inv(x, magma.kernel, theta, sigma, session=session)
+    assert rel_err(i_got.m, i_ref.m) < RTOL_POST
+    mu = rng.normal(size=n)
+    xv = mu + 0.3 * rng.normal(size=n)
+    for lg in (True, False):
+        d_ref = O.dmvnorm(xv, mu, i_ref.m, log=lg)
+        d_got = magma.dmvnorm(xv, mu, i_got, log=lg, session=session)
+        assert abs(d_got - d_ref) <= RTOL_LL * max(abs(d_ref), 1e-300)
+    assert np.array_equal(magma.mat_dist(x[:5], x[:3]), O.mat_dist(x[:5], x[:3]))
+    assert np.array_equal(magma.deriv_hp2(O.mat_dist(x, x), theta), O.deriv_hp2(O.mat_dist(x, x), theta))
+
+
+def test_standalone_kern_to_inv_db_branch(session):
+    """db branch: one matrix per ID with theta[[i]][3] as the noise sd (CF.R:153-190)"""
+    from magmaclust_b200 import magma
+    db, hp, tau, m_k = small_problem(M=4, K=2, n=(4, 9), n_grid=30, seed=9)
+    ref = O.kern_to_inv(db, O.kernel, hp["theta_i"])
+    got = magma.kern_to_inv(db, magma.kernel, hp["theta_i"], session=session)
+    assert list(ref.keys()) == list(got.keys())
+    for i in ref:
+        assert rel_err(got[i].m, ref[i].m) < RTOL_POST
