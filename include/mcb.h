@@ -92,7 +92,9 @@ int mcb_e_step_VEM(mcb_handle* h, int K, const double* theta_k, const double* th
 
 /* Install an explicit hyper-posterior — the `mu_k_param` / `list_mu_param` / `new_cov` arguments of the
  * reference's callbacks (CF.R:218, 280, 327, 631) — instead of the one left by the last E-step:
- * mean[K][N], cov[K][N][N], tau[M][K] (host). Evaluated against the resident hp. */
+ * mean[K][N], cov[K][N][N], tau[M][K] (host). Evaluated against the resident hp.
+ * tau == NULL: the responsibilities are computed from (mean, cov, resident hp and pi_k) instead, i.e.
+ * update_tau_i_k_VEM (CF.R:733-762); read them with mcb_get_tau_new, the K x M log-likelihoods with mcb_get_mat_logL. */
 int mcb_set_posterior(mcb_handle* h, const double* mean, const double* cov, const double* tau);
 
 /* ---- M-step objectives and gradients (the optimiser callbacks of CF.R:647-677) ----------------------- */

@@ -481,7 +481,7 @@ extern "C" int mcb_e_step_VEM(mcb_handle* h, int K, const double* theta_k, const
 // Install an explicit hyper-posterior (the `mu_k_param` / `list_mu_param` argument of the reference's
 // callbacks) instead of the one left by mcb_e_step: mean[K][N], cov[K][N][N], tau[M][K] from host memory.
 extern "C" int mcb_set_posterior(mcb_handle* h, const double* mean, const double* cov, const double* tau) {
-  if (!h || !mean || !cov || !tau) return MCB_EINVAL;
+  if (!h || !mean || !cov) return MCB_EINVAL;
   H_CHECK(h->has_state, MCB_ESTATE, "mcb_set_posterior: call mcb_set_data and mcb_set_state first");
   H_CUDA(cudaSetDevice(h->device));
   spans_reset(h);
@@ -492,13 +492,14 @@ extern "C" int mcb_set_posterior(mcb_handle* h, const double* mean, const double
   for (int k = 0; k < K; ++k)
     H_CUDA(cudaMemcpy2DAsync(h->cov.p + k * sN, sizeof(double) * ld, cov + (size_t)k * N * N, sizeof(double) * N,
                              sizeof(double) * N, N, cudaMemcpyHostToDevice, h->st));
-  H_CUDA(cudaMemcpyAsync(h->tau_new.p, tau, sizeof(double) * (size_t)M * K, cudaMemcpyHostToDevice, h->st));
-  // Psi_i^-1 at the resident theta_i (no scatter: K = 0), then corr1/corr2/F_i with the supplied tau
+  if (tau) H_CUDA(cudaMemcpyAsync(h->tau_new.p, tau, sizeof(double) * (size_t)M * K, cudaMemcpyHostToDevice, h->st));
+  // Psi_i^-1 at the resident theta_i (no scatter: K = 0), then corr1/corr2/F_i with the supplied tau, or, without one,
+  // with the responsibilities these means and covariances imply (update_tau_i_k_VEM, CF.R:733-762)
   H_CUDA(launch_factor_scatter(h->st, h->idata(), M, h->nmax, h->theta_i.p, h->tau.p, 0, h->cov.p, ld, sN, h->wk.p,
                                h->iwork(), h->info.p));
   vec_sub(h->st, K * ld, h->mean.p, h->mk.p, h->rvec.p, &h->launches);
   H_CUDA(launch_tau(h->st, h->idata(), M, h->nmax, K, h->mean.p, h->cov.p, ld, sN, h->pi.p, h->iwork(),
-                    h->tau_new.p, h->logL.p, 1));
+                    h->tau_new.p, h->logL.p, tau ? 1 : 0));
   h->launches += 2;
   // K_k^-1 and log|K_k| at the resident theta_k, log|C_k| of the supplied covariances (for the ELBO)
   std::vector<double> groups;

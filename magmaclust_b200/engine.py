@@ -134,8 +134,10 @@ class Engine:
         return mean, cov, tau, logL
 
     def set_posterior(self, mean, cov, tau):
-        mean, cov, tau = f64(mean), f64(cov), f64(tau)
-        assert mean.shape == (self.K, self.N) and cov.shape == (self.K, self.N, self.N) and tau.shape == (self.M, self.K)
+        mean, cov = f64(mean), f64(cov)
+        tau = f64(tau) if tau is not None else None   # None: responsibilities computed on the device (update_tau_i_k_VEM)
+        assert mean.shape == (self.K, self.N) and cov.shape == (self.K, self.N, self.N)
+        assert tau is None or tau.shape == (self.M, self.K)
         self._ck(self.lib.mcb_set_posterior(self.h, dptr(mean), dptr(cov), dptr(tau)))
 
     # ------------------------------------------------------------------------------------------

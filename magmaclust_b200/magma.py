@@ -249,7 +249,7 @@ def kern_to_inv(x, kern=kernel, theta=(1.0, 0.5), sigma=0.2, session=None):
 def dmvnorm(x, mu, inv_Sigma, log=False, session=None):
     """CF.R:10-35 -- Gaussian (log-)density from a precision matrix."""
     s = session or default_session()
-    P = inv_Sigma.m if isinstance(inv_Sigma, NamedMat) else inv_Sigma
+    P = getattr(inv_Sigma, "m", inv_Sigma)
     return s.eng.dmvnorm(x, mu, P, log)
 
 
@@ -269,6 +269,25 @@ def e_step_VEM(db, m_k, kern_0, kern_i, hp, old_tau_i_k, session=None, want_cov=
     out = s.param_from_device(names_k, s.eng.get_tau_new(), want_cov)
     out["mat_logL"] = s.eng.get_mat_logL().T  # K x M like CF.R:738
     return out
+
+
+def update_tau_i_k_VEM(db, m_k, mean_k, cov_k, kern_i, hp, pi_k, session=None):
+    """CF.R:733-762 -> tau_i_k (list over clusters of lists over individuals) from given means / covariances of the mean
+    processes: log-likelihoods, max-shift and normalisation on the device (pi_k multiplied positionally, quirk Q3)."""
+    _check_kernels(kern_i)
+    s = session or default_session()
+    s.ensure_data(db)
+    names_k = list(m_k.keys())
+    hp_full = hp if "theta_k" in hp else dict(hp, theta_k={k: np.array([1.0, 1.0, 0.2]) for k in names_k})  # unused here
+    theta_k, theta_i = s.pack_hp(hp_full, names_k)
+    M = theta_i.shape[0]
+    s.eng.set_state(theta_k, theta_i, np.asarray(pi_k, dtype=np.float64), s.pack_mk(m_k, names_k),
+                    np.full((M, len(names_k)), 1.0 / len(names_k)))
+    mean = np.array([np.asarray(mean_k[k]["Output"], dtype=np.float64) for k in names_k])
+    cov = np.array([np.asarray(getattr(cov_k[k], "m", cov_k[k]), dtype=np.float64) for k in names_k])
+    s.eng.set_posterior(mean, cov, None)
+    s._post_token = None
+    return s.unpack_tau(s.eng.get_tau_new(), names_k)
 
 
 def m_step_VEM(db, old_hp, list_mu_param, kern_0, kern_i, m_k, common_hp_k, common_hp_i, session=None, stats=None):

@@ -65,3 +65,18 @@ def test_estep_large_grid_takes_the_multi_launch_inverse(session):
     got = magma.e_step_VEM(db, m_k, magma.kernel_mu, magma.kernel, hp, tau, session=session)
     assert_param_close(got, ref, list(m_k.keys()))
     assert rel_err(got["mat_logL"], ref["mat_logL"]) < RTOL_LL
+
+
+def test_update_tau_i_k_VEM_standalone(session):
+    """CF.R:733-762 as its own call: responsibilities from GIVEN means / covariances (here the oracle's E-step output at
+    other hyper-parameters than the ones the responsibilities are evaluated with)"""
+    from magmaclust_b200 import magma
+    db, hp, tau, m_k = small_problem(M=9, seed=12)
+    ref = O.e_step_VEM(db, m_k, O.kernel_mu, O.kernel, hp, tau)
+    hp2 = dict(hp, theta_i={i: np.asarray(v) + 0.1 for i, v in hp["theta_i"].items()})
+    pi = np.array([0.5, 0.3, 0.2])
+    t_ref, _ = O.update_tau_i_k_VEM(db, m_k, ref["mean"], ref["cov"], O.kernel, hp2, pi)
+    t_got = magma.update_tau_i_k_VEM(db, m_k, ref["mean"], ref["cov"], magma.kernel, hp2, pi, session=session)
+    A, B = O.tau_to_array(t_got), O.tau_to_array(t_ref)
+    assert np.max(np.abs(A - B)) < RTOL_LL
+    assert np.array_equal(A.argmax(1), B.argmax(1))
