@@ -170,16 +170,17 @@ spd_inverse_slab_kernel(double* __restrict__ Aall, int N, int ld, long long stri
 
     // ---- phase 2: V_I = R L^-T, P_I = V L^-1 -------------------------------------------------------------
     if (own_piv) {
-      slab_wait(lflag, (unsigned)(b + 1));
-      SP(0);
+      // the rows of the pivot columns are staged BEFORE waiting for L^-1: they only depend on this CTA's own slab
       for (int e = tid; e < kNB * kNB; e += kSlabThreads) {
         const int r = e >> 5, c = e & 31;
-        Ls[r * kLp + c] = __ldcg(Lg + e);
         double v;
         if (I == b) v = (r == c && r < nb) ? 1.0 : 0.0;          // identity rows -> P = D^-1
         else v = (c < nb) ? slab[(size_t)r * lds + c0 - cbeg + c] : 0.0;
         Rs[r * kLp + c] = v;
       }
+      slab_wait(lflag, (unsigned)(b + 1));
+      SP(0);
+      for (int e = tid; e < kNB * kNB; e += kSlabThreads) Ls[(e >> 5) * kLp + (e & 31)] = __ldcg(Lg + e);
       __syncthreads();
       SP(1);
       mm32_nt(Rs, Ls, Vs, warp, lane);     // V[r][c] = sum_b R[r][b] Linv[c][b]
