@@ -100,6 +100,7 @@ extern "C" int mcb_create(mcb_handle** out, int device) {
     return MCB_ECUDA;
   }
   cudaMemset(h->info.p, 0, sizeof(int) * 4);
+  cudaDeviceSynchronize();   // default-stream fill vs the handle's non-blocking streams
   *out = h;
   return MCB_OK;
 }

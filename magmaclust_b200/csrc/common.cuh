@@ -48,8 +48,12 @@ struct DevBuf {
     cudaError_t e = cudaMalloc(&p, n * sizeof(T));
     if (e != cudaSuccess) return e;
     cap = n;
-    // zero fill: dense buffers rely on zero padding of every row up to ld (ld % 16 == 0)
-    return cudaMemset(p, 0, n * sizeof(T));
+    // zero fill: dense buffers rely on zero padding of every row up to ld (ld % 16 == 0). cudaMemset runs on the legacy
+    // default stream, asynchronously to the host, and the library's streams are NON-BLOCKING: without the synchronisation
+    // below the fill can land after the first kernel has already written the new buffer (seen at N = 4096: a 268 MB
+    // fill overtaken by se_build). Allocation is rare (growth only), so the full synchronisation costs nothing.
+    if ((e = cudaMemset(p, 0, n * sizeof(T))) != cudaSuccess) return e;
+    return cudaDeviceSynchronize();
   }
   void release() {
     if (p) cudaFree(p);

@@ -101,6 +101,7 @@ struct GemmParams {
   // sweep epilogue: pivot rows [r0p, r0p + nb), pivot columns [c0, c0 + nb) of C; column j of C is row j + cro of the
   // full matrix (0 unless C is a column panel); Pbuf row stride ldp
   const double* Pbuf; long long sP; int c0, nb; double sign; int r0p, cro, ldp;
+  int nofast;  // debug: disable the batched epilogue
   int sym;   // C symmetric and A == B: only the tiles on and below the diagonal are computed, results are mirrored
   // trace epilogue
   const double* D1; const double* D2; int ldd; long long sD; double* out; int out_stride;
@@ -196,7 +197,7 @@ __global__ void __launch_bounds__(128) gemm_nt_kernel(GemmParams p) {
     // in the symmetric case, the diagonal): all C values of the thread are requested in one batch of independent
     // 16-byte loads (the generic loop below interleaves loads, tests and stores and was the longer half of the kernel)
     const bool clean = (m0 + BM <= p.r0p || m0 >= p.r0p + p.nb) && (n0 + BN <= p.c0 || n0 >= p.c0 + p.nb) &&
-                       m0 + BM <= p.M && n0 + BN <= p.N && (!p.sym || n0 + BN - 1 < m0) && (p.ldc % 2 == 0);
+                       m0 + BM <= p.M && n0 + BN <= p.N && (!p.sym || n0 + BN - 1 < m0) && (p.ldc % 2 == 0) && !p.nofast;
     if (clean) {
       double* Cz = p.C + z * p.sC;
       double2 cv[FM][FN];
@@ -605,7 +606,10 @@ static void launch_sweep_update(cudaStream_t s, int M, int Ncols, int K, const d
   p.C = C; p.ldc = ldc; p.sC = sC;
   p.Pbuf = P; p.sP = sP; p.ldp = ldp; p.r0p = r0p; p.c0 = c0; p.nb = nb; p.cro = cro;
   p.sign = sign;
-  p.sym = sym;
+  static const bool nosym = getenv("MCB_SWEEP_NOSYM") != nullptr;
+  static const bool nofast = getenv("MCB_SWEEP_NOFAST") != nullptr;
+  p.sym = nosym ? 0 : sym;
+  p.nofast = nofast ? 1 : 0;
   launch_gemm<EPI_SWEEP>(s, p, Z, nullptr);
 }
 
