@@ -29,8 +29,17 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-# stdout carries exactly one JSON line: NCCL's own banner / debug output (it goes to stdout by default) is sent to stderr
-os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+# stdout carries exactly one JSON line. Native libraries write to file descriptor 1 behind Python's back (NCCL prints its
+# version banner there when NCCL_DEBUG is set), so descriptor 1 is pointed at stderr for the whole run and the result line
+# goes to a private duplicate of the original stdout.
+sys.stdout.flush()
+_RESULT_FD = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line):
+    os.write(_RESULT_FD, (json.dumps(line) + "\n").encode())
+
 
 METRIC = "VEM iterations/sec at M individuals x K clusters"
 
@@ -209,7 +218,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "individual-VEM-iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -430,7 +439,7 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "mstep_evals_per_step": {"theta_i_total": nfev_i_sum / args.steps, "theta_k": nfev_k / args.steps},
         }
-        print(json.dumps(line))
+        emit(line)
     for a in pinned:
         eng.unpin(a)
     eng.close()
