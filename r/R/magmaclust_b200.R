@@ -66,3 +66,35 @@ m_step_VEM <- function(db, old_hp, list_mu_param, kern_0, kern_i, m_k, common_hp
   theta_i <- lapply(seq_along(cn$ids), function(i) res[[2]][, i])
   list(theta_k = setNames(theta_k, names_k), theta_i = setNames(theta_i, cn$ids), pi_k = setNames(res[[3]], names_k))
 }
+
+## the building blocks the reference also calls directly (vector branches only; the db branches loop over the IDs in R)
+kern_to_cov <- function(x, kern = kernel, theta = c(1, 0.5), sigma = 0.2) {
+  .check_kernels(kern)
+  if (is.vector(x)) {
+    x <- sort(x)
+    m <- .Call('mcbR_kern', mcb_session(), as.numeric(x), as.numeric(theta)[1:2], sigma, FALSE)
+    dimnames(m) <- list(paste0('X', x), paste0('X', x)); m
+  } else {
+    floop <- function(i) { th <- if (is.list(theta)) theta[[i]] else c(theta, sigma)
+      kern_to_cov(x$Timestamp[x$ID == i], kern, th[1:2], th[[3]]) }
+    res <- sapply(unique(x$ID), floop, simplify = FALSE, USE.NAMES = TRUE)
+    if (length(res) == 1) res[[1]] else res
+  }
+}
+kern_to_inv <- function(x, kern = kernel, theta = c(1, 0.5), sigma = 0.2) {
+  .check_kernels(kern)
+  if (is.vector(x)) {
+    x <- sort(x)
+    m <- .Call('mcbR_kern', mcb_session(), as.numeric(x), as.numeric(theta)[1:2], sigma, TRUE)
+    attr(m, 'logdet') <- NULL
+    dimnames(m) <- list(paste0('X', x), paste0('X', x)); m
+  } else {
+    floop <- function(i) { th <- if (is.list(theta)) theta[[i]] else c(theta, sigma)
+      kern_to_inv(x$Timestamp[x$ID == i], kern, th[1:2], th[[3]]) }
+    res <- sapply(unique(x$ID), floop, simplify = FALSE, USE.NAMES = TRUE)
+    if (length(res) == 1) res[[1]] else res
+  }
+}
+dmvnorm <- function(x, mu, inv_Sigma, log = FALSE)
+  .Call('mcbR_dmvnorm', mcb_session(), as.numeric(x), as.numeric(mu), as.numeric(inv_Sigma), log)
+

@@ -178,3 +178,42 @@ SEXP mcbR_predict(SEXP hp, SEXP offsets, SEXP obs_idx, SEXP y, SEXP theta_new, S
   UNPROTECT(4);
   return out;
 }
+
+/* kern_to_cov / kern_to_inv, vector branch (CF.R:68-86, 130-149): x sorted, theta = c(a, b); n x n matrix (symmetric, so the
+ * row-major result needs no transpose). want_inv: the inverse, with attr(, "logdet") = log det of the covariance. */
+SEXP mcbR_kern(SEXP hp, SEXP x, SEXP theta, SEXP sigma, SEXP want_inv) {
+  mcb_handle* h = get_handle(hp);
+  int n = Rf_length(x);
+  SEXP out = PROTECT(Rf_allocMatrix(REALSXP, n, n));
+  if (Rf_asLogical(want_inv)) {
+    double logdet = 0.0;
+    check(h, mcb_kern_to_inv(h, n, REAL(x), REAL(theta), Rf_asReal(sigma), REAL(out), &logdet), 1);
+    SEXP ld = PROTECT(Rf_ScalarReal(logdet));
+    Rf_setAttrib(out, Rf_install("logdet"), ld);
+    UNPROTECT(1);
+  } else {
+    check(h, mcb_kern_to_cov(h, n, REAL(x), REAL(theta), Rf_asReal(sigma), REAL(out)), 1);
+  }
+  UNPROTECT(1);
+  return out;
+}
+
+/* dmvnorm(x, mu, inv_Sigma, log) CF.R:10-35 */
+SEXP mcbR_dmvnorm(SEXP hp, SEXP x, SEXP mu, SEXP inv_Sigma, SEXP want_log) {
+  mcb_handle* h = get_handle(hp);
+  double out = 0.0;
+  check(h, mcb_dmvnorm(h, Rf_length(mu), REAL(x), REAL(mu), REAL(inv_Sigma), Rf_asLogical(want_log), &out), 0);
+  return Rf_ScalarReal(out);
+}
+
+/* update_tau_i_k_VEM (CF.R:733-762): responsibilities from given means (N x K) and covariances (N x N x K) */
+SEXP mcbR_update_tau(SEXP hp, SEXP mean, SEXP cov, SEXP K_, SEXP M_) {
+  mcb_handle* h = get_handle(hp);
+  int K = Rf_asInteger(K_), M = Rf_asInteger(M_);
+  SEXP tau = PROTECT(Rf_allocMatrix(REALSXP, K, M));
+  check(h, mcb_set_posterior(h, REAL(mean), REAL(cov), NULL), 1);
+  check(h, mcb_get_tau_new(h, REAL(tau)), 1);
+  UNPROTECT(1);
+  return tau;
+}
+
