@@ -341,11 +341,8 @@ def run_ours(args):
     def step_e2e():
         eng.set_data(host["offsets"], host["grid_idx"], host["y"], host["grid"], M_total=sh["M_total"])
         eng.set_state(host["theta_k"], host["theta_i"], host["pi"], host["m_k"], host["tau0"])
-        r = eng.vem_iteration(True, common_i)
-        eng._ck(eng.lib.mcb_get_mean(eng.h, dptr(out_mean)))
-        for k in range(K):
-            eng._ck(eng.lib.mcb_get_cov(eng.h, k, dptr(out_cov[k])))
-        eng._ck(eng.lib.mcb_get_tau_new(eng.h, dptr(out_tau)))
+        # one call per loop body of training_VEM, param of the E-step delivered to the (pinned) host buffers
+        r = eng.vem_iteration_host(True, common_i, out_mean, out_cov, out_tau)
         hp = eng.get_new_hp()
         return r, hp
 

@@ -138,6 +138,12 @@ int mcb_get_new_hp(mcb_handle* h, double* theta_k, double* theta_i, double* pi_k
 /* E-step, ELBO(hp), M-step, eps = (L(new_hp) - L(hp)) / |L(new_hp)|, acceptance rule of MC.R:83-90.
  * out[0] = ELBO total appended to logL_iterations (MC.R:77), out[1] = eps, out[2] = 1 if converged. */
 int mcb_vem_iteration(mcb_handle* h, int common_hp_k, int common_hp_i, double out[3]);
+/* Host-buffer form of the same call (what the `.Call` shim binds for the loop body of training_VEM): additionally delivers
+ * `param` of this iteration's E-step (MC.R:48) to caller-owned host buffers: out_mean[K][N], out_cov[K][N][N],
+ * out_tau[M][K] (any may be NULL). The copies start as soon as the E-step has finished, on their own stream, and run
+ * behind the M-step; everything has landed when the call returns. */
+int mcb_vem_iteration_host(mcb_handle* h, int common_hp_k, int common_hp_i, double out[3], double* out_mean,
+                           double* out_cov, double* out_tau);
 
 /* ---- prediction -------------------------------------------------------------------------------------- */
 /* posterior_mu_k (MC.R:196-233): hyper-posterior on a prediction grid `timestamps[T]` (sorted, must

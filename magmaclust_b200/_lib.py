@@ -54,6 +54,7 @@ SIGNATURES = {
     "mcb_accept_hp": (C.c_int, [H]),
     "mcb_get_new_hp": (C.c_int, [H, c_double_p, c_double_p, c_double_p]),
     "mcb_vem_iteration": (C.c_int, [H, C.c_int, C.c_int, c_double_p]),
+    "mcb_vem_iteration_host": (C.c_int, [H, C.c_int, C.c_int, c_double_p, c_double_p, c_double_p, c_double_p]),
     "mcb_posterior_mu_k": (C.c_int, [H, C.c_int, c_double_p, c_double_p, c_double_p, c_double_p]),
     "mcb_predict": (C.c_int, [H, C.c_int, c_int_p, c_int_p, c_double_p, c_double_p, c_double_p, C.c_int, c_int_p,
                               c_double_p, c_double_p, c_double_p]),

@@ -114,6 +114,7 @@ extern "C" void mcb_destroy(mcb_handle* h) {
   if (h->mopt_exec) cudaGraphExecDestroy(h->mopt_exec);
   if (h->st_cap) cudaStreamDestroy(h->st_cap);
   if (h->st_hi) cudaStreamDestroy(h->st_hi);
+  if (h->st_copy) { cudaStreamDestroy(h->st_copy); cudaEventDestroy(h->ev_copy0); cudaEventDestroy(h->ev_copy1); }
   h->mopt_state.release();
   for (auto e : h->evpool) cudaEventDestroy(e);
   mcb::DevBuf<double>* dbl[] = {&h->t, &h->y, &h->grid, &h->theta_i, &h->theta_k, &h->pi, &h->mk, &h->tau,
@@ -1308,12 +1309,19 @@ extern "C" int mcb_accept_hp(mcb_handle* h) {
 }
 
 // ---- one iteration of training_VEM's loop (MC.R:44-93) --------------------------------------------
+static int vem_iteration_impl(mcb_handle* h, int common_hp_k, int common_hp_i, double out[3], double* out_mean,
+                              double* out_cov, double* out_tau);
+
 extern "C" int mcb_vem_iteration(mcb_handle* h, int common_hp_k, int common_hp_i, double out[3]) {
-  if (!h || !out) return MCB_EINVAL;
-  H_CHECK(h->has_state, MCB_ESTATE, "mcb_vem_iteration: call mcb_set_data and mcb_set_state first");
-  H_CUDA(cudaSetDevice(h->device));
-  spans_reset(h);
-  MCB_TRY(e_step_impl(h));
+  return vem_iteration_impl(h, common_hp_k, common_hp_i, out, nullptr, nullptr, nullptr);
+}
+
+extern "C" int mcb_vem_iteration_host(mcb_handle* h, int common_hp_k, int common_hp_i, double out[3], double* out_mean,
+                                      double* out_cov, double* out_tau) {
+  return vem_iteration_impl(h, common_hp_k, common_hp_i, out, out_mean, out_cov, out_tau);
+}
+
+static int vem_rest(mcb_handle* h, int common_hp_k, int common_hp_i, double out[3], bool copies) {
   double e_old[2], e_new[2];
   MCB_TRY(elbo_impl(h, nullptr, nullptr, e_old));           // MC.R:51-53; also the second term of MC.R:71
   MCB_TRY(m_step_impl(h, common_hp_k, common_hp_i, nullptr));
@@ -1336,13 +1344,46 @@ extern "C" int mcb_vem_iteration(mcb_handle* h, int common_hp_k, int common_hp_i
     H_CUDA(cudaMemcpyAsync(h->tau.p, h->tau_new.p, sizeof(double) * (size_t)h->M * h->K, cudaMemcpyDeviceToDevice, h->st));
     out[2] = 0.0;
   }
+  if (copies) H_CUDA(cudaStreamWaitEvent(h->st, h->ev_copy1, 0));
   H_CUDA(cudaStreamSynchronize(h->st));
   return MCB_OK;
 }
 
-// ---- measurement -------------------------------------------------------------------------------------
-// out[0..3] as mcb_m_step's stats; out[4] = total number of individual objective+gradient evaluations of the
-// last M-step on this rank (sum over individuals), out[5] = number of individuals
+static int vem_iteration_impl(mcb_handle* h, int common_hp_k, int common_hp_i, double out[3], double* out_mean,
+                              double* out_cov, double* out_tau) {
+  if (!h || !out) return MCB_EINVAL;
+  H_CHECK(h->has_state, MCB_ESTATE, "mcb_vem_iteration: call mcb_set_data and mcb_set_state first");
+  H_CUDA(cudaSetDevice(h->device));
+  spans_reset(h);
+  MCB_TRY(e_step_impl(h));
+  const bool copies = out_mean || out_cov || out_tau;
+  if (copies) {
+    // param of this E-step to the caller's buffers, behind the M-step (mean, cov, tau_new are only read from here on)
+    if (!h->st_copy) {
+      H_CUDA(cudaStreamCreateWithFlags(&h->st_copy, cudaStreamNonBlocking));
+      H_CUDA(cudaEventCreateWithFlags(&h->ev_copy0, cudaEventDisableTiming));
+      H_CUDA(cudaEventCreateWithFlags(&h->ev_copy1, cudaEventDisableTiming));
+    }
+    const int N = h->N, ld = h->ld, K = h->K;
+    H_CUDA(cudaEventRecord(h->ev_copy0, h->st));
+    H_CUDA(cudaStreamWaitEvent(h->st_copy, h->ev_copy0, 0));
+    if (out_mean)
+      H_CUDA(cudaMemcpy2DAsync(out_mean, sizeof(double) * N, h->mean.p, sizeof(double) * ld, sizeof(double) * N, K,
+                               cudaMemcpyDeviceToHost, h->st_copy));
+    if (out_cov)
+      for (int k = 0; k < K; ++k)
+        H_CUDA(cudaMemcpy2DAsync(out_cov + (size_t)k * N * N, sizeof(double) * N, h->cov.p + (size_t)k * N * ld,
+                                 sizeof(double) * ld, sizeof(double) * N, N, cudaMemcpyDeviceToHost, h->st_copy));
+    if (out_tau)
+      H_CUDA(cudaMemcpyAsync(out_tau, h->tau_new.p, sizeof(double) * (size_t)h->M * K, cudaMemcpyDeviceToHost, h->st_copy));
+    H_CUDA(cudaEventRecord(h->ev_copy1, h->st_copy));
+  }
+  const int rc = vem_rest(h, common_hp_k, common_hp_i, out, copies);
+  if (copies) cudaStreamSynchronize(h->st_copy);   // never leave copies into caller memory in flight, error or not
+  return rc;
+}
+
+
 // ---- stand-alone building blocks ---------------------------------------------------------------------------------
 // scratch layout in h->kscr: [matrix n x ld][second matrix n x ld][x (ld)][theta 3][logdet 1][quad 1]
 static int kern_scratch(mcb_handle* h, int n, int* ld_out, double** mat, double** mat2, double** vec, double** small) {
@@ -1373,6 +1414,7 @@ static int kern_build(mcb_handle* h, int n, const double* x, const double* theta
   *small_out = small;
   return MCB_OK;
 }
+
 
 extern "C" int mcb_kern_to_cov(mcb_handle* h, int n, const double* x, const double* theta2, double sigma, double* out) {
   if (!h) return MCB_EINVAL;
@@ -1455,6 +1497,9 @@ extern "C" int mcb_dmvnorm(mcb_handle* h, int n, const double* x, const double* 
   return MCB_OK;
 }
 
+// ---- measurement -------------------------------------------------------------------------------------
+// out[0..3] as mcb_m_step's stats; out[4] = total number of individual objective+gradient evaluations of the
+// last M-step on this rank (sum over individuals), out[5] = number of individuals
 extern "C" int mcb_last_mstep_stats(mcb_handle* h, long long out[6]) {
   if (!h || !out) return MCB_EINVAL;
   H_CHECK(h->has_cand, MCB_ESTATE, "mcb_last_mstep_stats: no M-step has run");

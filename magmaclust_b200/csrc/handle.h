@@ -10,6 +10,8 @@ struct mcb_handle {
   int device = 0;
   cudaStream_t st = nullptr;
   cudaStream_t st2 = nullptr;              // second stream: theta_i optimisations overlapped with theta_k
+  cudaStream_t st_copy = nullptr;          // result copies of mcb_vem_iteration_host behind the M-step
+  cudaEvent_t ev_copy0 = nullptr, ev_copy1 = nullptr;
   cudaStream_t st_hi = nullptr;            // high-priority stream: the theta_k chain next to host-driven theta_i evaluations
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   mcb::DevBuf<int> mstep_ctl;               // work queue + SM reservation flags of indiv_mstep_kernel

@@ -205,6 +205,16 @@ class Engine:
         self._ck(self.lib.mcb_vem_iteration(self.h, int(common_hp_k), int(common_hp_i), dptr(out)))
         return float(out[0]), float(out[1]), bool(out[2] != 0.0)
 
+    def vem_iteration_host(self, common_hp_k, common_hp_i, out_mean=None, out_cov=None, out_tau=None):
+        """the same iteration with `param` of its E-step delivered to the given host arrays ([K][N], [K][N][N], [M][K],
+        C-contiguous float64; pinned ones make the copies overlap the M-step)"""
+        out = np.empty(3)
+        for a, shp in ((out_mean, (self.K, self.N)), (out_cov, (self.K, self.N, self.N)), (out_tau, (self.M, self.K))):
+            assert a is None or (a.dtype == np.float64 and a.flags.c_contiguous and a.shape == shp)
+        self._ck(self.lib.mcb_vem_iteration_host(self.h, int(common_hp_k), int(common_hp_i), dptr(out), dptr(out_mean),
+                                                 dptr(out_cov), dptr(out_tau)))
+        return float(out[0]), float(out[1]), bool(out[2] != 0.0)
+
     # ------------------------------------------------------------------------------------------
     def kern_to_cov(self, x, theta2, sigma):
         """vector branch of kern_to_cov (CF.R:68-86) for SORTED timestamps x; n x n array"""

@@ -144,3 +144,34 @@ def test_c5_full_size_prediction_properties(eng):
     assert v1.min() > 0.0 and np.array_equal(v1, v2) and np.array_equal(v1, v3)    # the variance does not depend on y
     # per cluster the predictive mean is affine in y: the midpoint of the inputs gives the midpoint of the outputs
     assert np.abs(m3 - 0.5 * (m1 + m2)).max() <= 1e-9 * max(np.abs(m1).max(), np.abs(m2).max())
+
+
+@pytest.mark.parametrize("common_i", [False, True])
+def test_vem_iteration_host_delivers_the_e_step_results(eng, common_i):
+    """mcb_vem_iteration_host: the copies that leave behind the M-step carry exactly what the getters return, and the
+    iteration's statistics are those of the plain call from the same state"""
+    ds = synth.make_dataset(M=300, K=3, n=24, n_grid=97, common_hp_i=common_i, seed=77)
+    K, M, N = 3, 300, 97
+    tk, ti, mk = _start(ds, K)
+    eng.set_data(ds["offsets"], ds["grid_idx_full"], ds["y"], ds["grid_full"])
+    eng.set_state(tk, ti, ds["tau0"].mean(0), mk, ds["tau0"])
+    ref = eng.vem_iteration(True, common_i)
+    ref_hp = eng.get_new_hp()
+    ref_mean, ref_cov, ref_tau = eng.get_mean(), eng.get_cov(), eng.get_tau_new()
+    eng.set_state(tk, ti, ds["tau0"].mean(0), mk, ds["tau0"])
+    om, oc, ot = np.full((K, N), np.nan), np.full((K, N, N), np.nan), np.full((M, K), np.nan)
+    got = eng.vem_iteration_host(True, common_i, om, oc, ot)
+    assert np.array_equal(om, eng.get_mean()) and np.array_equal(oc, eng.get_cov()) and np.array_equal(ot, eng.get_tau_new())
+    assert np.abs(om - ref_mean).max() <= 1e-10 * np.abs(ref_mean).max()       # scatter order differs between calls
+    assert np.abs(oc - ref_cov).max() <= 1e-10 * np.abs(ref_cov).max()
+    assert np.abs(ot - ref_tau).max() < 1e-9
+    assert abs(got[0] - ref[0]) <= 1e-8 * abs(ref[0]) and got[2] == ref[2]
+    # the optimisers stop on a relative decrease of the objective: two runs whose inputs differ in the last bits agree in
+    # the bound (above) far more tightly than in the position along its flat directions
+    for a, b in zip(eng.get_new_hp(), ref_hp):
+        assert np.all(np.isfinite(a)) and np.abs(a - b).max() <= 5e-2 * max(1.0, np.abs(b).max())
+    # any subset of the three destinations may be absent
+    eng.set_state(tk, ti, ds["tau0"].mean(0), mk, ds["tau0"])
+    ot2 = np.empty((M, K))
+    eng.vem_iteration_host(True, common_i, None, None, ot2)
+    assert np.abs(ot2 - ot).max() < 1e-9
