@@ -170,7 +170,10 @@ extern "C" int mcb_set_data(mcb_handle* h, int M, int N, long long P, const int*
   H_CHECK(eval_smem_bytes(nmax) <= 227 * 1024, MCB_EINVAL,
           "mcb_set_data: an individual has too many observations for the shared-memory path (n_i <= 80)");
   H_CUDA(cudaSetDevice(h->device));
-  h->K = 0;  // forces the state buffers to be re-sized for the new N
+  // a dataset of another shape forces the state buffers to be re-sized and the captured graphs (which hold M, N, P and
+  // the buffer addresses) to be rebuilt; re-uploading a dataset of the SAME shape (the host-buffer loop) keeps both
+  const bool same_shape = M == h->M && N == h->N && P == h->P && nmax == h->nmax && M_total == h->M_total;
+  if (!same_shape) h->K = 0;
   h->M = M; h->N = N; h->ld = (N + 15) & ~15; h->P = P; h->nmax = nmax; h->M_total = M_total; h->W2 = woff[M];
   H_CUDA(h->off.ensure(M + 1)); H_CUDA(h->gidx.ensure(P)); H_CUDA(h->woff.ensure(M + 1));
   H_CUDA(h->t.ensure(P)); H_CUDA(h->y.ensure(P)); H_CUDA(h->grid.ensure(N));
@@ -188,7 +191,9 @@ extern "C" int mcb_set_data(mcb_handle* h, int M, int N, long long P, const int*
   H_CUDA(h->theta_i.ensure(3 * (size_t)M)); H_CUDA(h->theta_i_new.ensure(3 * (size_t)M));
   H_CUDA(cudaStreamSynchronize(h->st));  // host vectors go out of scope
   h->has_data = true; h->has_state = false; h->has_post = false; h->has_cand = false; h->has_pred = false;
-  h->nfev_valid = false;
+  // the evaluation counts of the last M-step only ORDER the work queue of the next one (never its results): they stay a
+  // useful prediction for a re-uploaded dataset of the same shape
+  if (!same_shape) h->nfev_valid = false;
   return MCB_OK;
 }
 

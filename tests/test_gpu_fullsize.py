@@ -175,3 +175,28 @@ def test_vem_iteration_host_delivers_the_e_step_results(eng, common_i):
     ot2 = np.empty((M, K))
     eng.vem_iteration_host(True, common_i, None, None, ot2)
     assert np.abs(ot2 - ot).max() < 1e-9
+
+
+def test_same_shape_dataset_reupload_keeps_nothing_of_the_old_data(eng):
+    """mcb_set_data with a dataset of the SAME shape keeps the state buffers and the captured theta_k graphs (the host-buffer
+    loop relies on it): the iteration on the second dataset must equal the one of a fresh handle that never saw the first"""
+    K = 3
+    a = synth.make_dataset(M=200, K=K, n=20, n_grid=81, common_hp_i=False, seed=5)
+    b = synth.make_dataset(M=200, K=K, n=20, n_grid=81, common_hp_i=False, seed=6)
+    assert a["y"].shape == b["y"].shape and not np.array_equal(a["y"], b["y"])
+    tk, ti, mk = _start(a, K)
+    for ds in (a, b):
+        eng.set_data(ds["offsets"], ds["grid_idx_full"], ds["y"], ds["grid_full"])
+        eng.set_state(tk, ti, ds["tau0"].mean(0), mk, ds["tau0"])
+        got = eng.vem_iteration(True, False)
+    got_mean, got_tau = eng.get_mean(), eng.get_tau_new()
+    fresh = Engine(0)
+    try:
+        fresh.set_data(b["offsets"], b["grid_idx_full"], b["y"], b["grid_full"])
+        fresh.set_state(tk, ti, b["tau0"].mean(0), mk, b["tau0"])
+        ref = fresh.vem_iteration(True, False)
+        assert np.abs(got_mean - fresh.get_mean()).max() <= 1e-10 * np.abs(got_mean).max()
+        assert np.abs(got_tau - fresh.get_tau_new()).max() < 1e-9
+        assert abs(got[0] - ref[0]) <= 1e-8 * abs(ref[0])
+    finally:
+        fresh.close()
