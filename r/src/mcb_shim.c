@@ -150,6 +150,26 @@ SEXP mcbR_vem_iteration(SEXP hp, SEXP common_hp_k, SEXP common_hp_i) {
   return out;
 }
 
+/* the same iteration with `param` of its E-step in R arrays: the library copies them out on a second stream while the
+   M-step runs (mcb.h: mcb_vem_iteration_host). K, M, N as set by mcbR_set_data / mcbR_set_state */
+SEXP mcbR_vem_iteration_host(SEXP hp, SEXP common_hp_k, SEXP common_hp_i, SEXP K_, SEXP M_, SEXP N_) {
+  mcb_handle* h = get_handle(hp);
+  int K = Rf_asInteger(K_), M = Rf_asInteger(M_), N = Rf_asInteger(N_);
+  SEXP stats = PROTECT(Rf_allocVector(REALSXP, 3));
+  SEXP mean = PROTECT(Rf_allocMatrix(REALSXP, N, K));
+  SEXP cov = PROTECT(Rf_alloc3DArray(REALSXP, N, N, K));
+  SEXP tau = PROTECT(Rf_allocMatrix(REALSXP, K, M));
+  check(h, mcb_vem_iteration_host(h, Rf_asLogical(common_hp_k), Rf_asLogical(common_hp_i), REAL(stats), REAL(mean),
+                                  REAL(cov), REAL(tau)), 4);
+  SEXP out = PROTECT(Rf_allocVector(VECSXP, 4));
+  SET_VECTOR_ELT(out, 0, stats);
+  SET_VECTOR_ELT(out, 1, mean);
+  SET_VECTOR_ELT(out, 2, cov);
+  SET_VECTOR_ELT(out, 3, tau);
+  UNPROTECT(5);
+  return out;
+}
+
 SEXP mcbR_posterior_mu_k(SEXP hp, SEXP timestamps, SEXP tau, SEXP K_) {
   mcb_handle* h = get_handle(hp);
   int T = Rf_length(timestamps), K = Rf_asInteger(K_);
