@@ -60,7 +60,9 @@ int mcb_comm_init(mcb_handle* h, int nranks, int rank, const unsigned char id[12
 
 /* ---- data ----------------------------------------------------------------------------------------- */
 /* Upload the (local shard of the) training set. M_total = number of individuals over all ranks (== M when
- * single-GPU); it is the denominator of pi_k = mean_i tau_ik (CF.R:682). */
+ * single-GPU); it is the denominator of pi_k = mean_i tau_ik (CF.R:682). The call invalidates the state (call
+ * mcb_set_state next). A dataset of the same shape (M, N, P, longest individual, M_total) as the previous one re-uses
+ * the device buffers and the captured optimiser graphs, so a loop that re-uploads every iteration stays cheap. */
 int mcb_set_data(mcb_handle* h, int M, int N, long long P, const int* offsets, const int* grid_idx,
                  const double* y, const double* grid, long long M_total);
 

@@ -588,3 +588,26 @@ def pred_max_cluster(tau_i_k):
     ids = list(tau_i_k[names_k[0]].keys())
     mat = np.array([[tau_i_k[k][i] for k in names_k] for i in ids])
     return np.argmax(mat, axis=1) + 1
+
+
+# ---- trained models on disk (the `.rds` lists of Simulation_study.R:554-582) --------------------------
+def save_trained(res, path):
+    """saveRDS(training_VEM(...), path): the R list layout of MC.R:94-98 (`rds_io.trained_to_r`)"""
+    from . import rds_io
+    rds_io.save_trained(res, path)
+
+
+def load_trained(path_or_obj, id_type=str):
+    """readRDS of a `training_VEM` result — a file, or an already decoded R list such as `[[d]]$MAGMAclust` of the study's
+    stored outputs. R keeps individual IDs as names (strings); `id_type` converts them back to the type of `db['ID']`
+    (e.g. `int`). Covariances come back as `NamedMat`, so the result can go straight into `posterior_mu_k` / `BIC`."""
+    from . import rds_io
+    obj = rds_io.read_rds(path_or_obj) if isinstance(path_or_obj, (str, bytes)) or hasattr(path_or_obj, "__fspath__") else path_or_obj
+    res = rds_io.trained_from_r(obj)
+    res["hp"]["theta_i"] = {id_type(i): v for i, v in res["hp"]["theta_i"].items()}
+    p = res.get("param", {})
+    if "tau_i_k" in p:
+        p["tau_i_k"] = {k: {id_type(i): x for i, x in per_i.items()} for k, per_i in p["tau_i_k"].items()}
+    if "cov" in p and "mean" in p:
+        p["cov"] = {k: NamedMat(m, p["mean"][k]["Timestamp"]) for k, m in p["cov"].items()}
+    return res

@@ -125,3 +125,23 @@ def test_training_from_kmeans_initialisation(session, d):
     stored = O.tau_to_array(tau_stored).argmax(1)
     agree = max(sum(p[h - 1] == s for h, s in zip(hard, stored)) for p in itertools.permutations(range(3)))
     assert agree >= 18
+
+
+def test_trained_model_through_an_rds_file(session, tmp_path):
+    """training_VEM -> saveRDS layout -> readRDS -> posterior_mu_k: the file carries everything the prediction chain
+    needs, bit for bit"""
+    from magmaclust_b200 import magma
+    db, hp, tau, m_k = small_problem(M=10, seed=11, common_hp_i=True)
+    trained = magma.training_VEM(db, m_k, None, magma.kernel_mu, magma.kernel, tau, True, True, n_loop_max=3, session=session)
+    path = str(tmp_path / "trained.rds")
+    magma.save_trained(trained, path)
+    ids = list(trained["hp"]["theta_i"].keys())
+    loaded = magma.load_trained(path, id_type=type(ids[0]))
+    assert list(loaded["hp"]["theta_i"].keys()) == ids
+    t_pred = np.unique(np.r_[np.round(np.linspace(0.1, 9.9, 11), 3), db["Timestamp"]])
+    a = magma.posterior_mu_k(db, t_pred, m_k, magma.kernel_mu, magma.kernel, trained, session=session)
+    b = magma.posterior_mu_k(db, t_pred, m_k, magma.kernel_mu, magma.kernel, loaded, session=session)
+    for k in m_k:
+        assert np.array_equal(loaded["param"]["cov"][k].m, trained["param"]["cov"][k].m)
+        assert rel_err(b["mean"][k]["Output"], a["mean"][k]["Output"]) < 1e-12
+        assert rel_err(b["cov"][k].m, a["cov"][k].m) < 1e-12
