@@ -165,6 +165,32 @@ int mcb_predict(mcb_handle* h, int B, const int* offsets, const int* obs_idx, co
                 const double* theta_new, const double* pi_k, int Tp, const int* pred_idx, double* out_tau,
                 double* out_mean, double* out_var);
 
+/* New individuals with FREE hyper-parameters: the free-hp branch of train_new_gp_EM (MC.R:142-186), repaired (upstream it
+ * cannot run: undefined `t`, stray `db$Timestamp -` in the objective). Batched over B new individuals against
+ * the prediction posterior of mcb_posterior_mu_k.
+ *
+ * mcb_new_indiv_logl: the building block. For npts evaluation points (pt_ind[p] = new individual, pt_theta[p][3] = its
+ * trial hyper-parameters) out_logl[p][K] = log N(y*; m_k(t*), Psi_theta(t*) + C_k(t*, t*)) — dmvnorm(..., log = T) of
+ * CF.R:776-780 and MC.R:156-161. NaN where that covariance is not numerically positive definite.
+ *
+ * mcb_train_new_indiv: the EM loop (at most n_loop_max passes, MC.R:143: 25). E step: update_tau_star_k_EM at the current
+ * theta; M step: L-BFGS on - sum_k tau_k log N(...) with optim's central-difference gradient (no `gr` at MC.R:166,
+ * ndeps = 1e-3); stop when 0 < sum |theta' - theta| < 1e-3 (MC.R:175-181). theta0[3], or [B][3] if theta0_per_indiv;
+ * pi_k NULL: as in mcb_predict. out_theta[B][3] = theta' of the last M step, out_tau[B][K] = tau_k of the last E step
+ * (MC.R:192), out_loops[B] (may be NULL) = passes done, -1 if the start point already gave a non-positive-definite
+ * covariance (out_tau NaN then).
+ *
+ * mcb_new_indiv_em is the same loop as host code over a caller-supplied log-density (what mcb_train_new_indiv runs with the
+ * GPU kernel behind `fn`): fn(ctx, npts, pt_ind, pt_theta, out_logl) fills out_logl[npts][K] and returns MCB_OK. */
+typedef int (*mcb_logl_fn)(void* ctx, int npts, const int* pt_ind, const double* pt_theta, double* out_logl);
+int mcb_new_indiv_logl(mcb_handle* h, int B, const int* offsets, const int* obs_idx, const double* y, int npts,
+                       const int* pt_ind, const double* pt_theta, double* out_logl);
+int mcb_train_new_indiv(mcb_handle* h, int B, const int* offsets, const int* obs_idx, const double* y,
+                        const double* theta0, int theta0_per_indiv, const double* pi_k, int n_loop_max,
+                        double* out_theta, double* out_tau, int* out_loops);
+int mcb_new_indiv_em(int B, int K, const double* theta0, int theta0_per_indiv, const double* pi_k, int n_loop_max,
+                     mcb_logl_fn fn, void* ctx, double* out_theta, double* out_tau, int* out_loops);
+
 /* ---- stand-alone building blocks (the vector branches the reference also calls directly, e.g. MC.R:261-264) ------------ */
 /* kern_to_cov(x, kern, theta, sigma), vector branch CF.R:68-86: SE covariance of the SORTED timestamps x[n] (the reference
  * sorts them, CF.R:76; pass them sorted), theta2 = (a, b): exp(a - exp(-b)/2 d^2) off the diagonal, exp(a) + sigma^2 on it.

@@ -20,6 +20,8 @@ c_float_p = C.POINTER(C.c_float)
 c_ll_p = C.POINTER(C.c_longlong)
 c_ubyte_p = C.POINTER(C.c_ubyte)
 H = C.c_void_p
+# mcb_logl_fn: int fn(void* ctx, int npts, const int* pt_ind, const double* pt_theta, double* out_logl)
+LOGL_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, c_int_p, c_double_p, c_double_p)
 
 # name -> (restype, argtypes); must list every symbol include/mcb.h declares (checked by tests/test_abi.py)
 SIGNATURES = {
@@ -58,6 +60,11 @@ SIGNATURES = {
     "mcb_posterior_mu_k": (C.c_int, [H, C.c_int, c_double_p, c_double_p, c_double_p, c_double_p]),
     "mcb_predict": (C.c_int, [H, C.c_int, c_int_p, c_int_p, c_double_p, c_double_p, c_double_p, C.c_int, c_int_p,
                               c_double_p, c_double_p, c_double_p]),
+    "mcb_new_indiv_logl": (C.c_int, [H, C.c_int, c_int_p, c_int_p, c_double_p, C.c_int, c_int_p, c_double_p, c_double_p]),
+    "mcb_train_new_indiv": (C.c_int, [H, C.c_int, c_int_p, c_int_p, c_double_p, c_double_p, C.c_int, c_double_p, C.c_int,
+                                      c_double_p, c_double_p, c_int_p]),
+    "mcb_new_indiv_em": (C.c_int, [C.c_int, C.c_int, c_double_p, C.c_int, c_double_p, C.c_int, LOGL_FN, C.c_void_p,
+                                   c_double_p, c_double_p, c_int_p]),
     "mcb_kern_to_cov": (C.c_int, [H, C.c_int, c_double_p, c_double_p, C.c_double, c_double_p]),
     "mcb_kern_to_inv": (C.c_int, [H, C.c_int, c_double_p, c_double_p, C.c_double, c_double_p, c_double_p]),
     "mcb_dmvnorm": (C.c_int, [H, C.c_int, c_double_p, c_double_p, c_double_p, C.c_int, c_double_p]),

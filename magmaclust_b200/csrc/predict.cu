@@ -165,6 +165,61 @@ __global__ void __launch_bounds__(kTP) predict_kernel(int K, int T, int ldT, con
   }
 }
 
+// log N(y*; m_k[t*], Psi_theta(t*) + C_k[t*,t*]) of new individuals at FREE hyper-parameters: one CTA per evaluation point
+// (pt_ind[p] = new individual, pt_theta[p] = its trial theta), the objective terms of the repaired M-step of
+// train_new_gp_EM (MC.R:151-166). The kernel matrix cannot be shared over the grid here (theta differs per point), so it is
+// evaluated n*^2 times per cluster in place. A trial theta that makes a covariance numerically singular yields NaN for
+// that term (the line search treats it as a failed step), not an error.
+__global__ void __launch_bounds__(kTP) new_indiv_logl_kernel(int K, int T, int ldT, const double* __restrict__ pgrid,
+                                                             const double* __restrict__ pmean,
+                                                             const double* __restrict__ pcov, const int* __restrict__ off,
+                                                             const int* __restrict__ oidx, const double* __restrict__ yv,
+                                                             const int* __restrict__ pt_ind,
+                                                             const double* __restrict__ pt_theta, int nmax,
+                                                             double* __restrict__ out) {
+  extern __shared__ double sm[];
+  __shared__ int bad;
+  const int p = blockIdx.x;
+  const int b = pt_ind[p];
+  const int o0 = off[b], n = off[b + 1] - o0;
+  const int ntot = n + 1, ld = ntot | 1;
+  double* A = sm;                               // (nmax+1) x ld
+  double* ts = A + (size_t)(nmax + 1) * ((nmax + 1) | 1);
+  int* idx = (int*)(ts + nmax);
+  const double th1 = pt_theta[3 * p], th2 = pt_theta[3 * p + 1], sg = pt_theta[3 * p + 2];
+  for (int a = threadIdx.x; a < n; a += kTP) {
+    idx[a] = oidx[o0 + a];
+    ts[a] = pgrid[idx[a]];
+  }
+  __syncthreads();
+  const long long sC = (long long)T * ldT;
+  for (int k = 0; k < K; ++k) {
+    const double* Ck = pcov + k * sC;
+    const double* mk = pmean + (size_t)k * ldT;
+    if (threadIdx.x == 0) bad = 0;
+    for (int e = threadIdx.x; e < ntot * ntot; e += kTP) {
+      const int a = e / ntot, c = e - a * ntot;
+      double v;
+      if (a < n && c < n) {
+        const double d = ts[a] - ts[c];
+        const double kv = (a == c) ? exp(th1) + sg * sg : exp(th1 - exp(-th2) / 2.0 * (d * d));   // CF.R:43-50, 83-86
+        v = kv + Ck[(size_t)idx[a] * ldT + idx[c]];
+      } else if (a < n) {
+        v = yv[o0 + a] - mk[idx[a]];
+      } else if (c < n) {
+        v = yv[o0 + c] - mk[idx[c]];
+      } else {
+        v = 0.0;
+      }
+      A[a * ld + c] = v;
+    }
+    const double logdet = sweep_p(A, n, ntot, ld, &bad);
+    if (threadIdx.x == 0)
+      out[(size_t)p * K + k] = bad ? nan("") : -0.5 * ((double)n * kLog2Pi + logdet - A[n * ld + n]);
+    __syncthreads();
+  }
+}
+
 }  // namespace mcb
 
 extern "C" int mcb_posterior_mu_k(mcb_handle* h, int T, const double* timestamps, const double* tau,
@@ -355,4 +410,111 @@ extern "C" int mcb_predict(mcb_handle* h, int B, const int* offsets, const int* 
     return MCB_ENOTPD;
   }
   return MCB_OK;
+}
+
+// ---- new individuals with free hyper-parameters (repair of the free-hp branch of train_new_gp_EM, MC.R:142-186) ----
+namespace {
+
+// device copy of a batch of new individuals (CSR) + per-point scratch, alive for one EM run
+struct NewIndivDev {
+  mcb_handle* h;
+  int B = 0, nmax = 0;
+  size_t smem = 0;
+  mcb::DevBuf<int> off, idx, pt_ind;
+  mcb::DevBuf<double> y, pt_theta, out;
+  void release() { off.release(); idx.release(); pt_ind.release(); y.release(); pt_theta.release(); out.release(); }
+};
+
+int new_indiv_upload(mcb_handle* h, NewIndivDev& d, int B, const int* offsets, const int* obs_idx, const double* y,
+                     const char* who) {
+  const int T = h->T;
+  H_CHECK(h->has_pred, MCB_ESTATE, std::string(who) + ": call mcb_posterior_mu_k first");
+  H_CHECK(B >= 1 && offsets[0] == 0, MCB_EINVAL, std::string(who) + ": bad offsets");
+  int nmax = 0;
+  for (int b = 0; b < B; ++b) {
+    const int n = offsets[b + 1] - offsets[b];
+    H_CHECK(n >= 1, MCB_EINVAL, std::string(who) + ": empty new individual");
+    nmax = std::max(nmax, n);
+    for (int a = offsets[b]; a < offsets[b + 1]; ++a) {
+      H_CHECK(obs_idx[a] >= 0 && obs_idx[a] < T, MCB_EINVAL, std::string(who) + ": obs_idx out of range");
+      H_CHECK(a == offsets[b] || obs_idx[a] > obs_idx[a - 1], MCB_EINVAL,
+              std::string(who) + ": observations must be sorted and unique");
+    }
+  }
+  d.h = h; d.B = B; d.nmax = nmax;
+  d.smem = sizeof(double) * ((size_t)(nmax + 1) * ((nmax + 1) | 1) + nmax) + sizeof(int) * nmax + 16;
+  H_CHECK(nmax <= mcb::kMaxObs && d.smem <= 227 * 1024, MCB_EINVAL,
+          std::string(who) + ": more than 64 observations for one new individual is not supported yet");
+  H_CUDA(cudaSetDevice(h->device));
+  const long long Pn = offsets[B];
+  cudaError_t e = cudaSuccess;
+  if ((e = d.off.ensure(B + 1)) || (e = d.idx.ensure(Pn)) || (e = d.y.ensure(Pn))) {
+    d.release();
+    h->err = std::string(who) + ": " + cudaGetErrorString(e);
+    return MCB_ENOMEM;
+  }
+  cudaMemcpyAsync(d.off.p, offsets, sizeof(int) * (B + 1), cudaMemcpyHostToDevice, h->st);
+  cudaMemcpyAsync(d.idx.p, obs_idx, sizeof(int) * Pn, cudaMemcpyHostToDevice, h->st);
+  cudaMemcpyAsync(d.y.p, y, sizeof(double) * Pn, cudaMemcpyHostToDevice, h->st);
+  if (d.smem > 48 * 1024)
+    cudaFuncSetAttribute(mcb::new_indiv_logl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d.smem);
+  if ((e = cudaStreamSynchronize(h->st)) != cudaSuccess) {
+    d.release();
+    h->err = std::string(who) + ": " + cudaGetErrorString(e);
+    return MCB_ECUDA;
+  }
+  return MCB_OK;
+}
+
+// the mcb_logl_fn of the GPU path: npts evaluation points -> out[npts][K]
+int new_indiv_eval(void* ctx, int npts, const int* pt_ind, const double* pt_theta, double* out) {
+  NewIndivDev& d = *static_cast<NewIndivDev*>(ctx);
+  mcb_handle* h = d.h;
+  const int K = h->K;
+  cudaError_t e = cudaSuccess;
+  if ((e = d.pt_ind.ensure(npts)) || (e = d.pt_theta.ensure(3 * (size_t)npts)) || (e = d.out.ensure((size_t)npts * K))) {
+    h->err = std::string("new-individual objective: ") + cudaGetErrorString(e);
+    return MCB_ENOMEM;
+  }
+  cudaMemcpyAsync(d.pt_ind.p, pt_ind, sizeof(int) * npts, cudaMemcpyHostToDevice, h->st);
+  cudaMemcpyAsync(d.pt_theta.p, pt_theta, sizeof(double) * 3 * npts, cudaMemcpyHostToDevice, h->st);
+  mcb::new_indiv_logl_kernel<<<npts, mcb::kTP, d.smem, h->st>>>(K, h->T, h->ldT, h->pgrid.p, h->pmean.p, h->pcov.p, d.off.p,
+                                                                d.idx.p, d.y.p, d.pt_ind.p, d.pt_theta.p, d.nmax, d.out.p);
+  ++h->launches;
+  cudaMemcpyAsync(out, d.out.p, sizeof(double) * (size_t)npts * K, cudaMemcpyDeviceToHost, h->st);
+  if ((e = cudaGetLastError()) != cudaSuccess || (e = cudaStreamSynchronize(h->st)) != cudaSuccess) {
+    h->err = std::string("new-individual objective: ") + cudaGetErrorString(e);
+    return MCB_ECUDA;
+  }
+  return MCB_OK;
+}
+
+}  // namespace
+
+extern "C" int mcb_new_indiv_logl(mcb_handle* h, int B, const int* offsets, const int* obs_idx, const double* y, int npts,
+                                  const int* pt_ind, const double* pt_theta, double* out_logl) {
+  if (!h || !offsets || !obs_idx || !y || !pt_ind || !pt_theta || !out_logl) return MCB_EINVAL;
+  H_CHECK(npts >= 1, MCB_EINVAL, "mcb_new_indiv_logl: no evaluation point");
+  for (int p = 0; p < npts; ++p) H_CHECK(pt_ind[p] >= 0 && pt_ind[p] < B, MCB_EINVAL, "mcb_new_indiv_logl: pt_ind out of range");
+  NewIndivDev d;
+  MCB_TRY(new_indiv_upload(h, d, B, offsets, obs_idx, y, "mcb_new_indiv_logl"));
+  h->launches = 0;
+  const int rc = new_indiv_eval(&d, npts, pt_ind, pt_theta, out_logl);
+  d.release();
+  return rc;
+}
+
+extern "C" int mcb_train_new_indiv(mcb_handle* h, int B, const int* offsets, const int* obs_idx, const double* y,
+                                   const double* theta0, int theta0_per_indiv, const double* pi_k, int n_loop_max,
+                                   double* out_theta, double* out_tau, int* out_loops) {
+  if (!h || !offsets || !obs_idx || !y || !theta0 || !out_theta || !out_tau) return MCB_EINVAL;
+  NewIndivDev d;
+  MCB_TRY(new_indiv_upload(h, d, B, offsets, obs_idx, y, "mcb_train_new_indiv"));
+  h->launches = 0;
+  const double* pi = pi_k ? pi_k : h->h_pi_pred.data();
+  const int rc = mcb_new_indiv_em(B, h->K, theta0, theta0_per_indiv, pi, n_loop_max, new_indiv_eval, &d, out_theta,
+                                  out_tau, out_loops);
+  d.release();
+  if (rc != MCB_OK && h->err.empty()) h->err = "mcb_train_new_indiv: the EM driver failed";
+  return rc;
 }

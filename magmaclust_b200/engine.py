@@ -269,6 +269,29 @@ class Engine:
                                       iptr(pred_idx), dptr(tau), dptr(mean), dptr(var)))
         return tau, mean, var
 
+    def new_indiv_logl(self, offsets, obs_idx, y, pt_ind, pt_theta):
+        """log N(y*; m_k(t*), Psi_theta(t*) + C_k(t*, t*)) for evaluation points (individual pt_ind[p], hyper-parameters
+        pt_theta[p]) against the prediction posterior -> [npts][K] (NaN where not positive definite)"""
+        offsets, obs_idx, y = i32(offsets), i32(obs_idx), f64(y)
+        pt_ind, pt_theta = i32(pt_ind), f64(pt_theta).reshape(-1, 3)
+        assert pt_ind.shape[0] == pt_theta.shape[0]
+        out = np.empty((pt_ind.shape[0], self.K))
+        self._ck(self.lib.mcb_new_indiv_logl(self.h, offsets.shape[0] - 1, iptr(offsets), iptr(obs_idx), dptr(y),
+                                             pt_ind.shape[0], iptr(pt_ind), dptr(pt_theta), dptr(out)))
+        return out
+
+    def train_new_indiv(self, offsets, obs_idx, y, theta0, pi_k=None, n_loop_max=25):
+        """free-hp branch of train_new_gp_EM (MC.R:142-186, repaired), batched: (theta_new [B][3], tau [B][K], loops [B])"""
+        offsets, obs_idx, y, theta0 = i32(offsets), i32(obs_idx), f64(y), f64(theta0)
+        B = offsets.shape[0] - 1
+        per = theta0.ndim == 2
+        assert theta0.shape == ((B, 3) if per else (3,))
+        pi = f64(pi_k) if pi_k is not None else None
+        th, tau, loops = np.empty((B, 3)), np.empty((B, self.K)), np.empty(B, dtype=np.int32)
+        self._ck(self.lib.mcb_train_new_indiv(self.h, B, iptr(offsets), iptr(obs_idx), dptr(y), dptr(theta0), int(per),
+                                              dptr(pi), int(n_loop_max), dptr(th), dptr(tau), iptr(loops)))
+        return th, tau, loops
+
     # ------------------------------------------------------------------------------------------
     def last_timings(self):
         ms = (C.c_float * 8)()

@@ -530,11 +530,27 @@ def update_tau_star_k_EM(db, mean_k, cov_k, kern, hp, pi_k, session=None):
     return {k: float(tau[0, ck]) for ck, k in enumerate(names_k)}
 
 
-def train_new_gp_EM(db, param_mu_k, ini_hp=None, kern_i=kernel, hp_i=None, session=None):
-    """MC.R:137-141,187-192 — fixed-hp branch (the free-hp branch is broken upstream)."""
-    if hp_i is None:
-        raise NotImplementedError("free-hp branch of train_new_gp_EM is broken in the reference (Q9)")
+def train_new_gp_EM(db, param_mu_k, ini_hp=None, kern_i=kernel, hp_i=None, session=None, n_loop_max=25):
+    """MC.R:137-192. hp_i given: the fixed-hp branch (MC.R:187-191). hp_i = None: the free-hp EM of MC.R:142-186 — upstream
+    that branch cannot run (undefined `t`); `mcb_train_new_indiv` runs the EM it describes (E step
+    update_tau_star_k_EM, M step L-BFGS on - sum_k tau_k log N(y*; m_k, Psi + C_k) with optim's numerical gradient,
+    stop at 0 < sum |d theta| < 1e-3 or 25 passes). `db` may also be a LIST of new individuals: they are trained in one
+    batched call and a list of results comes back."""
     pi_k = {k: float(np.mean(list(v.values()))) for k, v in param_mu_k["tau_i_k"].items()}
+    if hp_i is None:
+        _check_kernels(kern_i)
+        s = session or default_session()
+        names_k = list(param_mu_k["mean"].keys())
+        ts = np.asarray(param_mu_k["mean"][names_k[0]]["Timestamp"], dtype=np.float64)
+        many = isinstance(db, (list, tuple))
+        off, idx, y = _csr_new(list(db) if many else [db], ts)
+        if ini_hp is None:
+            ini_hp = {"theta_i": np.array([1.0, 1.0, 0.2])}
+        th, tau, loops = s.eng.train_new_indiv(off, idx, y, np.asarray(ini_hp["theta_i"], dtype=np.float64).ravel()[:3],
+                                               np.array([pi_k[k] for k in names_k]), n_loop_max)
+        res = [{"theta_new": th[b], "tau_k": {k: float(tau[b, ck]) for ck, k in enumerate(names_k)}, "loops": int(loops[b])}
+               for b in range(th.shape[0])]
+        return res if many else res[0]
     new_hp = np.asarray(next(iter(hp_i["hp"]["theta_i"].values())), dtype=np.float64).ravel()[:3]
     tau_k = update_tau_star_k_EM(db, param_mu_k["mean"], param_mu_k["cov"], kern_i, new_hp, pi_k, session)
     return {"theta_new": new_hp, "tau_k": tau_k}

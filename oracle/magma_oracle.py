@@ -680,11 +680,71 @@ def posterior_mu_k(db, timestamps, m_k, kern_0, kern_i, list_hp):
     return {"mean": mean_k, "cov": cov_k, "tau_i_k": tau_i_k}
 
 
-def train_new_gp_EM(db, param_mu_k, ini_hp=None, kern_i=kernel, hp_i=None):
-    """MC.R:137-141,187-192. Fixed-hp branch only (the free-hp branch is broken upstream, Q9)."""
-    if hp_i is None:
-        raise NotImplementedError("free-hp branch of train_new_gp_EM is broken in the reference (Q9)")
+def new_indiv_logl(db, mean_k, cov_k, kern, hp):
+    """the K log-densities log N(y*; m_k(t*), Psi_hp(t*) + C_k(t*, t*)) that both steps of train_new_gp_EM are made of
+    (CF.R:776-780 for the E step, MC.R:156-161 for the M step); NaN where the covariance is not positive definite"""
+    names_k = list(mean_k.keys())
+    t_i = np.asarray(db["Timestamp"], dtype=np.float64)
+    y = np.asarray(db["Output"], dtype=np.float64)
+    hp = np.asarray(hp, dtype=np.float64)
+    out = np.full(len(names_k), np.nan)
+    for c_k, k in enumerate(names_k):
+        mk = mean_k[k]
+        mean = np.asarray(mk["Output"])[np.isin(mk["Timestamp"], t_i)]
+        cov = kern_to_cov(t_i, kern, hp[:2], hp[2]).m + cov_k[k].sub(t_i)
+        try:
+            np.linalg.cholesky(cov)
+        except np.linalg.LinAlgError:
+            continue
+        out[c_k] = dmvnorm(y, mean, np.linalg.inv(cov), log=True)
+    return out
+
+
+NEW_INDIV_NDEPS = 1e-3   # stats::optim's default finite-difference step (no `gr` is passed at MC.R:166)
+
+
+def new_indiv_objective(hp, tau, db, mean_k, cov_k, kern):
+    """REPAIRED objective of the M step of train_new_gp_EM (MC.R:151-165): - sum_k tau_k log N(y*; m_k, Psi_hp + C_k).
+    Upstream the function body reads an undefined `t` and adds `db$Timestamp` to every term (Q9); what is restated here
+    is the expected complete-data log-likelihood the surrounding EM needs. A cluster of weight exactly 0 does not enter."""
+    ll = new_indiv_logl(db, mean_k, cov_k, kern, hp)
+    tau = np.asarray(tau, dtype=np.float64)
+    return float(-np.sum(tau[tau != 0.0] * ll[tau != 0.0]))
+
+
+def new_indiv_gradient(hp, tau, db, mean_k, cov_k, kern):
+    """optim's numerical gradient: central differences with ndeps = 1e-3"""
+    hp = np.asarray(hp, dtype=np.float64)
+    g = np.zeros(3)
+    for j in range(3):
+        e = np.zeros(3)
+        e[j] = NEW_INDIV_NDEPS
+        g[j] = (new_indiv_objective(hp + e, tau, db, mean_k, cov_k, kern)
+                - new_indiv_objective(hp - e, tau, db, mean_k, cov_k, kern)) / (2.0 * NEW_INDIV_NDEPS)
+    return g
+
+
+def train_new_gp_EM(db, param_mu_k, ini_hp=None, kern_i=kernel, hp_i=None, n_loop_max=25, return_loops=False):
+    """MC.R:137-192. Fixed-hp branch as upstream; the free-hp branch (hp_i = None) with the repaired objective above
+    ("parity unpinned": upstream cannot run it, and the optimiser is scipy's L-BFGS-B as everywhere in this oracle)."""
     pi_k = {k: float(np.mean(list(v.values()))) for k, v in param_mu_k["tau_i_k"].items()}
+    if hp_i is None:
+        mean_k, cov_k = param_mu_k["mean"], param_mu_k["cov"]
+        hp = np.asarray(ini_hp["theta_i"], dtype=np.float64)[:3].copy()
+        new_hp, tau_k, loops = hp, None, 0
+        for _ in range(n_loop_max):
+            tau_k = update_tau_star_k_EM(db, mean_k, cov_k, kern_i, hp, pi_k)            # MC.R:149
+            tau = np.array([tau_k[k] for k in mean_k])
+            new_hp, _ = _lbfgsb(new_indiv_objective, new_indiv_gradient, hp, (tau, db, mean_k, cov_k, kern_i))   # MC.R:166
+            loops += 1
+            eps = float(np.sum(np.abs(new_hp - hp)))                                       # MC.R:175
+            if 0.0 < eps < 1e-3:
+                break
+            hp = new_hp
+        out = {"theta_new": new_hp, "tau_k": tau_k}
+        if return_loops:
+            out["loops"] = loops
+        return out
     new_hp = np.asarray(next(iter(hp_i["hp"]["theta_i"].values())), dtype=np.float64)
     tau_k = update_tau_star_k_EM(db, param_mu_k["mean"], param_mu_k["cov"], kern_i, new_hp, pi_k)
     return {"theta_new": new_hp, "tau_k": tau_k}
