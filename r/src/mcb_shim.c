@@ -201,6 +201,23 @@ SEXP mcbR_predict(SEXP hp, SEXP offsets, SEXP obs_idx, SEXP y, SEXP theta_new, S
 
 /* kern_to_cov / kern_to_inv, vector branch (CF.R:68-86, 130-149): x sorted, theta = c(a, b); n x n matrix (symmetric, so the
  * row-major result needs no transpose). want_inv: the inverse, with attr(, "logdet") = log det of the covariance. */
+/* train_new_gp_EM with hp_i = NULL (MC.R:142-186, repaired) for B new individuals in CSR; theta0 of length 3 */
+SEXP mcbR_train_new_indiv(SEXP hp, SEXP offsets, SEXP obs_idx, SEXP y, SEXP theta0, SEXP pi_k, SEXP n_loop_max) {
+  mcb_handle* h = get_handle(hp);
+  int B = Rf_length(offsets) - 1, K = Rf_length(pi_k);
+  SEXP theta = PROTECT(Rf_allocMatrix(REALSXP, 3, B));   /* column b = theta_new of individual b */
+  SEXP tau = PROTECT(Rf_allocMatrix(REALSXP, K, B));
+  SEXP loops = PROTECT(Rf_allocVector(INTSXP, B));
+  check(h, mcb_train_new_indiv(h, B, INTEGER(offsets), INTEGER(obs_idx), REAL(y), REAL(theta0), 0, REAL(pi_k),
+                               Rf_asInteger(n_loop_max), REAL(theta), REAL(tau), INTEGER(loops)), 3);
+  SEXP out = PROTECT(Rf_allocVector(VECSXP, 3));
+  SET_VECTOR_ELT(out, 0, theta);
+  SET_VECTOR_ELT(out, 1, tau);
+  SET_VECTOR_ELT(out, 2, loops);
+  UNPROTECT(4);
+  return out;
+}
+
 SEXP mcbR_kern(SEXP hp, SEXP x, SEXP theta, SEXP sigma, SEXP want_inv) {
   mcb_handle* h = get_handle(hp);
   int n = Rf_length(x);
