@@ -730,6 +730,8 @@ def train_new_gp_EM(db, param_mu_k, ini_hp=None, kern_i=kernel, hp_i=None, n_loo
     pi_k = {k: float(np.mean(list(v.values()))) for k, v in param_mu_k["tau_i_k"].items()}
     if hp_i is None:
         mean_k, cov_k = param_mu_k["mean"], param_mu_k["cov"]
+        if ini_hp is None:
+            ini_hp = {"theta_i": np.array([1.0, 1.0, 0.2])}
         hp = np.asarray(ini_hp["theta_i"], dtype=np.float64)[:3].copy()
         new_hp, tau_k, loops = hp, None, 0
         for _ in range(n_loop_max):
