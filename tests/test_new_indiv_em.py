@@ -106,3 +106,25 @@ def test_not_positive_definite_start_and_bad_arguments():
                                 _lib.iptr(loops)) == 7
     assert lib.mcb_new_indiv_em(0, K, _lib.dptr(theta0), 0, _lib.dptr(pi), 25, fn, None, _lib.dptr(th), _lib.dptr(tau),
                                 _lib.iptr(loops)) < 0
+
+
+def test_analytic_log_density_and_the_reference_stopping_quirk():
+    """K = 1 and log-density -|theta - c|^2 / 2: tau = 1, the M step lands on c (central differences are exact for a
+    quadratic). MC.R:177 stops on 0 < eps < 1e-3: an M step that does not move at all (eps == 0) does NOT stop the loop,
+    so the run ends at n_loop_max — mirrored, not repaired."""
+    lib = _lib.load()
+    c = np.array([[0.3, -1.2, 0.7], [2.0, 0.5, 0.1]])
+
+    def cb(ctx, npts, pt_ind, pt_theta, out):
+        for p in range(npts):
+            th = np.array([pt_theta[3 * p + j] for j in range(3)])
+            out[p] = -0.5 * float(np.sum((th - c[pt_ind[p]]) ** 2))
+        return 0
+
+    fn = _lib.LOGL_FN(cb)
+    th, tau, loops = np.empty((2, 3)), np.empty((2, 1)), np.empty(2, dtype=np.int32)
+    theta0, pi = np.array([1.0, 1.0, 0.2]), np.array([1.0])
+    assert lib.mcb_new_indiv_em(2, 1, _lib.dptr(theta0), 0, _lib.dptr(pi), 6, fn, None, _lib.dptr(th), _lib.dptr(tau),
+                                _lib.iptr(loops)) == 0
+    assert np.abs(th - c).max() < 1e-6 and np.array_equal(tau, np.ones((2, 1)))
+    assert 2 <= loops.min() and loops.max() <= 6

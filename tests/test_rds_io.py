@@ -178,3 +178,33 @@ def test_magma_save_and_load_trained(tmp_path):
     # an already decoded list is accepted as well (the study keeps one list per dataset in a single file)
     again = magma.load_trained(R.read_rds(p), id_type=int)
     assert np.array_equal(again["hp"]["pi_k"], back["hp"]["pi_k"])
+
+
+def test_random_objects_round_trip():
+    """property test: any nesting of the supported value types survives encode -> decode -> encode unchanged"""
+    from hypothesis import given, settings, strategies as st
+
+    finite = st.floats(allow_nan=False, allow_infinity=True, width=64)
+    leaf = st.one_of(
+        st.none(),
+        st.lists(finite, max_size=5).map(lambda v: R.RVector(np.array(v, dtype=np.float64), R.REALSXP)),
+        st.lists(st.integers(-2 ** 31, 2 ** 31 - 1), max_size=5).map(lambda v: R.RVector(np.array(v, dtype=np.int64), R.INTSXP)),
+        st.lists(st.booleans(), max_size=4).map(lambda v: R.RVector(np.array(v, dtype=bool), R.LGLSXP)),
+        st.lists(st.one_of(st.none(), st.text(max_size=6)), max_size=4).map(R.RStrings))
+    names = st.text(alphabet="abcXYZ_.12", min_size=1, max_size=5)
+
+    def named(children):
+        return st.lists(st.tuples(names, children), max_size=4).map(
+            lambda kv: R.RList([v for _, v in kv], names=[k for k, _ in kv]) if kv else R.RList([]))
+
+    tree = st.recursive(leaf, lambda ch: st.one_of(named(ch), st.lists(ch, max_size=3).map(R.RList)), max_leaves=12)
+
+    @settings(max_examples=150, deadline=None)
+    @given(tree, st.sampled_from([2, 3]))
+    def check(obj, version):
+        buf = R.encode(obj, version=version)
+        back, hdr = R.decode(buf)
+        assert hdr["version"] == version
+        assert R.encode(back, version=version) == buf
+
+    check()
