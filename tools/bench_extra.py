@@ -3,6 +3,7 @@ config C5 (pred_magmaclust-style prediction: 10,000 new individuals onto a 2,000
 
     python tools/bench_extra.py c5 [B] [T]
     python tools/bench_extra.py c3 [M]
+    python tools/bench_extra.py newindiv [B] [T]
 """
 import json
 import os
@@ -116,7 +117,37 @@ def c4(N=8192, K=8, M=4096, n=32):
     eng.close()
 
 
+def newindiv(B=1000, T=2000, K=5, nstar=20):
+    """free-hp EM of train_new_gp_EM (mcb_train_new_indiv) for B new individuals in one batched call, C5-shaped inputs:
+    wall time, EM passes, and the log-density kernel alone (7 B evaluation points = one optimiser round)"""
+    ds = synth.make_dataset(M=1000, K=K, n=30, n_grid=T, common_hp_i=True, seed=1005)
+    eng = Engine(0)
+    eng.set_data(ds["offsets"], ds["grid_idx_full"], ds["y"], ds["grid_full"])
+    M = ds["M"]
+    eng.set_state(np.tile([1.0, 1.0, 0.2], (K, 1)), np.tile([1.0, 1.0, 0.2], (M, 1)), ds["tau0"].mean(0), np.zeros(K), ds["tau0"])
+    eng.posterior_mu_k(ds["grid_full"], tau=ds["tau0"], want_mean=False, want_cov=False)
+    rng = np.random.default_rng(7)
+    obs = np.sort(np.argsort(rng.random((B, T)), axis=1)[:, :nstar], axis=1).astype(np.int32)
+    mu = ds["mu_true"][rng.integers(0, K, B)]
+    y = np.take_along_axis(mu, obs, axis=1) + 0.3 * rng.standard_normal((B, nstar))
+    offsets = (np.arange(B + 1) * nstar).astype(np.int32)
+    theta0 = np.array([1.0, 1.0, 0.2])
+    pts = np.repeat(np.arange(B, dtype=np.int32), 7)
+    eng.new_indiv_logl(offsets, obs.ravel(), y.ravel(), pts[:70], np.tile(theta0, (70, 1)))          # warm-up
+    t0 = time.perf_counter()
+    eng.new_indiv_logl(offsets, obs.ravel(), y.ravel(), pts, np.tile(theta0, (7 * B, 1)))
+    t_round = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    th, tau, loops = eng.train_new_indiv(offsets, obs.ravel(), y.ravel(), theta0)
+    t_em = time.perf_counter() - t0
+    print(json.dumps({"config": f"free-hp EM: {B} new individuals x {nstar} obs, {T}-point grid, K={K}",
+                      "one_round_7B_points_s": t_round, "em_s": t_em, "individuals_per_s": B / t_em,
+                      "loops_mean": float(loops.mean()), "loops_max": int(loops.max()), "failed": int((loops < 0).sum()),
+                      "tau_rowsum_err": float(np.nanmax(np.abs(tau.sum(1) - 1)))}))
+    eng.close()
+
+
 if __name__ == "__main__":
     which = sys.argv[1]
     args = [int(a) for a in sys.argv[2:]]
-    {"c5": c5, "c3": c3, "c4": c4}[which](*args)
+    {"c5": c5, "c3": c3, "c4": c4, "newindiv": newindiv}[which](*args)
