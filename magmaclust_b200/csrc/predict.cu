@@ -509,6 +509,7 @@ extern "C" int mcb_train_new_indiv(mcb_handle* h, int B, const int* offsets, con
                                    double* out_theta, double* out_tau, int* out_loops) {
   if (!h || !offsets || !obs_idx || !y || !theta0 || !out_theta || !out_tau) return MCB_EINVAL;
   NewIndivDev d;
+  h->err.clear();
   MCB_TRY(new_indiv_upload(h, d, B, offsets, obs_idx, y, "mcb_train_new_indiv"));
   h->launches = 0;
   const double* pi = pi_k ? pi_k : h->h_pi_pred.data();
