@@ -128,3 +128,15 @@ def test_analytic_log_density_and_the_reference_stopping_quirk():
                                 _lib.iptr(loops)) == 0
     assert np.abs(th - c).max() < 1e-6 and np.array_equal(tau, np.ones((2, 1)))
     assert 2 <= loops.min() and loops.max() <= 6
+
+
+def test_batch_composition_does_not_change_results():
+    """the B loops run in lock step but are independent: splitting the batch (how new individuals shard over GPUs — no
+    exchange step) gives bit-identical hyper-parameters, responsibilities and pass counts"""
+    mu, news = _setting(seed=6, n_new=(4, 7, 5))
+    theta0 = np.array([1.0, 1.0, 0.2])
+    th, tau, loops, _, _ = _run_driver(mu, news, theta0)
+    th_a, tau_a, loops_a, _, _ = _run_driver(mu, news[:2], theta0)
+    th_b, tau_b, loops_b, _, _ = _run_driver(mu, news[2:], theta0)
+    assert np.array_equal(th, np.vstack([th_a, th_b])) and np.array_equal(tau, np.vstack([tau_a, tau_b]))
+    assert list(loops) == list(loops_a) + list(loops_b)
