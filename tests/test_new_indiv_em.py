@@ -140,3 +140,20 @@ def test_batch_composition_does_not_change_results():
     th_b, tau_b, loops_b, _, _ = _run_driver(mu, news[2:], theta0)
     assert np.array_equal(th, np.vstack([th_a, th_b])) and np.array_equal(tau, np.vstack([tau_a, tau_b]))
     assert list(loops) == list(loops_a) + list(loops_b)
+
+
+def test_oracle_log_density_against_scipy():
+    """the oracle's building block against an independent implementation of the Gaussian log-density"""
+    from scipy.stats import multivariate_normal
+    mu, news = _setting(seed=3, n_new=(6, 2))
+    for new in news:
+        for th in ([1.0, 1.0, 0.2], [-0.4, 1.7, 0.05]):
+            got = O.new_indiv_logl(new, mu["mean"], mu["cov"], O.kernel, np.array(th))
+            t = np.asarray(new["Timestamp"])
+            for c, k in enumerate(mu["mean"]):
+                mk = mu["mean"][k]
+                mean = np.asarray(mk["Output"])[np.isin(mk["Timestamp"], t)]
+                d = t[:, None] - t[None, :]
+                cov = np.exp(th[0] - 0.5 * np.exp(-th[1]) * d * d) + th[2] ** 2 * np.eye(len(t)) + mu["cov"][k].sub(t)
+                ref = multivariate_normal(mean, cov).logpdf(np.asarray(new["Output"]))
+                assert abs(got[c] - ref) <= 1e-9 * max(1.0, abs(ref))
