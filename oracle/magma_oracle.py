@@ -794,7 +794,8 @@ def full_algo_clust(db, new_db, timestamps, kern_i, ini_tau_i_k=None, common_hp_
     pred = pred_gp_clust(new_db, timestamps, mu_k, kern_i, hp_new_i)
     return {"Prediction": pred, "Mean_processes": mu_k,
             "Hyperparameters": {"other_i": list_hp, "new_i": hp_new_i},
-            "logL_iterations": list_hp.get("logL_iterations")}
+            "logL_iterations": list_hp.get("logL_iterations"),
+            "ari_iterations": list_hp.get("ARI_iterations")}   # MC.R:345: never set by training_VEM, i.e. NULL
 
 
 def pred_max_cluster(tau_i_k):
