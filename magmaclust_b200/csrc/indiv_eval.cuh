@@ -97,6 +97,36 @@ template <int NV, int TT>
 __device__ __forceinline__ void cta_sum_v(double (&v)[NV], double* red) {
   constexpr int NW = TT / 32;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#if defined(MCB_SUM_TRANSPOSE)
+  // Experiment (compile-time, default off: built and counted in round 1, not yet timed — profiles/r01f_ptxas.txt): the NV
+  // butterflies of the default path are 5 NV 64-bit shuffle steps, fully unrolled (951 SASS instructions at NV = 13, the
+  // largest single block of the evaluator). A transpose-reduce halves the number of live slots per step instead: 8 + 4 +
+  // 2 + 1 exchanges with the partners at distance 16, 8, 4, 2, then one ordinary step at distance 1: 16 shuffle steps, and
+  // lane l ends up with the warp total of slot l >> 1. Only the summation order differs from the default path.
+  static_assert(NV <= 16, "transpose-reduce holds 16 slots");
+  double w[16];
+#pragma unroll
+  for (int q = 0; q < 16; ++q) w[q] = q < NV ? v[q] : 0.0;
+#pragma unroll
+  for (int off = 16, half = 8; off >= 2; off >>= 1, half >>= 1) {
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < half; ++i) {
+      const double send = upper ? w[i] : w[i + half];   // the half the partner keeps
+      const double keep = upper ? w[i + half] : w[i];
+      w[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  w[0] += __shfl_xor_sync(0xffffffffu, w[0], 1);
+  if (NW == 1) {
+#pragma unroll
+    for (int q = 0; q < NV; ++q) v[q] = __shfl_sync(0xffffffffu, w[0], 2 * q);
+    return;
+  }
+  __syncthreads();
+  if (!(lane & 1) && (lane >> 1) < NV) red[(lane >> 1) * NW + warp] = w[0];
+  __syncthreads();
+#else
 #pragma unroll
   for (int q = 0; q < NV; ++q) {
 #pragma unroll
@@ -109,6 +139,7 @@ __device__ __forceinline__ void cta_sum_v(double (&v)[NV], double* red) {
     for (int q = 0; q < NV; ++q) red[q * NW + warp] = v[q];
   }
   __syncthreads();
+#endif
 #pragma unroll
   for (int q = 0; q < NV; ++q) {
     double t = 0.0;
