@@ -154,6 +154,13 @@ int mcb_vem_iteration_host(mcb_handle* h, int common_hp_k, int common_hp_i, doub
  * "prediction posterior" (mean_p[K][T], cov_p[K][T][T]); out_mean / out_cov may be NULL. */
 int mcb_posterior_mu_k(mcb_handle* h, int T, const double* timestamps, const double* tau, double* out_mean,
                        double* out_cov);
+/* Install an explicit prediction posterior instead: the `list_mu` argument of pred_gp_clust (MC.R:235) and the `mean_k`,
+ * `cov_k` arguments of update_tau_star_k_EM (CF.R:764) when they do NOT come from this handle's last mcb_posterior_mu_k
+ * (full_algo_clust(mu_k = ...), MC.R:305; a model read from disk). timestamps[T] sorted and unique, mean[K][T],
+ * cov[K][T][T]; pi_k[K] = default mixing proportions of mcb_predict / mcb_train_new_indiv (NULL: 1/K). Needs no training
+ * set on the handle. */
+int mcb_set_pred_posterior(mcb_handle* h, int K, int T, const double* timestamps, const double* mean, const double* cov,
+                           const double* pi_k);
 /* Batched new individuals against the prediction posterior:
  *   update_tau_star_k_EM (CF.R:764-786) -> out_tau[B][K]
  *   pred_gp_clust (MC.R:235-274)        -> out_mean[B][K][Tp], out_var[B][K][Tp]
@@ -202,6 +209,15 @@ int mcb_kern_to_inv(mcb_handle* h, int n, const double* x, const double* theta2,
 /* dmvnorm(x, mu, inv_Sigma, log) CF.R:10-35: Gaussian (log-)density from a symmetric positive definite PRECISION matrix
  * inv_Sigma (n x n row-major): -(n log 2pi - log det inv_Sigma + z' inv_Sigma z) / 2, z = x - mu. */
 int mcb_dmvnorm(mcb_handle* h, int n, const double* x, const double* mu, const double* inv_Sigma, int want_log, double* out);
+
+/* logL_GP_mod / gr_GP_mod (CF.R:194-216, 448-475; Z = 1) and logL_GP_mod_common_hp_k / gr_GP_mod_common_hp_k (CF.R:250-278,
+ * 510-537; Z clusters sharing one theta) on EXPLICIT arguments (hp, db, mean, kern, new_cov, pen_diag) instead of the
+ * resident hyper-posterior: t[n] sorted timestamps (db$Timestamp), y[Z][n] (db$Output per cluster), mean with mean_len == Z
+ * (scalars, CF.R:206) or Z*n entries, new_cov[Z][n][n]; theta[nhp], nhp == 3: sigma = theta[2], nhp == 2: sigma = pen_diag
+ * (CF.R:207). f[1]; g[nhp] may be NULL. The resident forms above (mcb_eval_mean, mcb_eval_mean_common) are the fast path
+ * of the M-step; this one serves callers that pass other data (as update_tau_i_k_VEM does, CF.R:746). */
+int mcb_gp_mod(mcb_handle* h, int n, int Z, const double* t, const double* y, const double* mean, int mean_len,
+               const double* new_cov, const double* theta, int nhp, double pen_diag, double* f, double* g);
 
 /* ---- measurement helpers ----------------------------------------------------------------------------- */
 /* Device time (ms, CUDA events on the handle's stream) of the kernels launched by the last compute call,

@@ -12,7 +12,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libmagmaclust_b200.so")
+# MCB_LIB: another BUILD of the same CUDA library (compile-time experiment variants); never a different implementation
+LIB_PATH = os.environ.get("MCB_LIB") or os.path.join(_HERE, "lib", "libmagmaclust_b200.so")
 
 c_double_p = C.POINTER(C.c_double)
 c_int_p = C.POINTER(C.c_int)
@@ -58,6 +59,7 @@ SIGNATURES = {
     "mcb_vem_iteration": (C.c_int, [H, C.c_int, C.c_int, c_double_p]),
     "mcb_vem_iteration_host": (C.c_int, [H, C.c_int, C.c_int, c_double_p, c_double_p, c_double_p, c_double_p]),
     "mcb_posterior_mu_k": (C.c_int, [H, C.c_int, c_double_p, c_double_p, c_double_p, c_double_p]),
+    "mcb_set_pred_posterior": (C.c_int, [H, C.c_int, C.c_int, c_double_p, c_double_p, c_double_p, c_double_p]),
     "mcb_predict": (C.c_int, [H, C.c_int, c_int_p, c_int_p, c_double_p, c_double_p, c_double_p, C.c_int, c_int_p,
                               c_double_p, c_double_p, c_double_p]),
     "mcb_new_indiv_logl": (C.c_int, [H, C.c_int, c_int_p, c_int_p, c_double_p, C.c_int, c_int_p, c_double_p, c_double_p]),
@@ -68,6 +70,8 @@ SIGNATURES = {
     "mcb_kern_to_cov": (C.c_int, [H, C.c_int, c_double_p, c_double_p, C.c_double, c_double_p]),
     "mcb_kern_to_inv": (C.c_int, [H, C.c_int, c_double_p, c_double_p, C.c_double, c_double_p, c_double_p]),
     "mcb_dmvnorm": (C.c_int, [H, C.c_int, c_double_p, c_double_p, c_double_p, C.c_int, c_double_p]),
+    "mcb_gp_mod": (C.c_int, [H, C.c_int, C.c_int, c_double_p, c_double_p, c_double_p, C.c_int, c_double_p, c_double_p,
+                             C.c_int, C.c_double, c_double_p, c_double_p]),
     "mcb_last_timings": (C.c_int, [H, c_float_p, c_ll_p]),
     "mcb_last_mstep_stats": (C.c_int, [H, c_ll_p]),
     "mcb_pin_host": (C.c_int, [C.c_void_p, C.c_size_t]),

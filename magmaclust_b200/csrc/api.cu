@@ -122,14 +122,16 @@ extern "C" void mcb_destroy(mcb_handle* h) {
                                 &h->pvec, &h->yWy, &h->logdet_i, &h->c1, &h->c2, &h->Fi, &h->Fnew, &h->kscr, &h->fi_tmp, &h->gi_tmp,
                                 &h->theta_g, &h->Kinv, &h->cov, &h->wk, &h->mean, &h->rvec, &h->pz, &h->logdetK,
                                 &h->logdetA, &h->eK, &h->eD1, &h->eD2, &h->eCsum, &h->eX, &h->etheta, &h->ered,
-                                &h->elogdet, &h->ws.Pbuf, &h->ws.Cold, &h->ws.red, &h->ws.slabV, &h->ws.slabP, &h->ws.slabL, &h->scal, &h->pgrid, &h->pKinv,
-                                &h->pcov, &h->pwk, &h->pmean, &h->plogdet};
+                                &h->elogdet, &h->ws.Pbuf, &h->ws.Cold, &h->ws.red, &h->ws.slabV, &h->ws.slabP, &h->ws.slabL,
+                                &h->ws_aux.Pbuf, &h->ws_aux.Cold, &h->ws_aux.red, &h->ws_aux.slabV, &h->ws_aux.slabP, &h->ws_aux.slabL, &h->scal, &h->pgrid, &h->pKinv,
+                                &h->pcov, &h->pwk, &h->pmean, &h->plogdet, &h->gscr};
   for (auto* b : dbl) b->release();
   mcb::DevBuf<int>* ints[] = {&h->off, &h->gidx, &h->nfev_i, &h->niter_i, &h->status_i, &h->gmap_d, &h->egmap,
-                              &h->info, &h->pmapidx};
+                              &h->info, &h->pmapidx, &h->gscr_i};
   for (auto* b : ints) b->release();
   h->woff.release();
   h->ws.bar.release();
+  h->ws_aux.bar.release();
   h->flush.release();
   if (h->tm0) { cudaEventDestroy(h->tm0); cudaEventDestroy(h->tm1); }
   if (h->hbuf) cudaFreeHost(h->hbuf);
@@ -1442,9 +1444,8 @@ extern "C" int mcb_kern_to_inv(mcb_handle* h, int n, const double* x, const doub
   double *mat, *small;
   int ld;
   MCB_TRY(kern_build(h, n, x, theta2, sigma, &mat, &ld, &small));
-  h->ws.max_ctas = 0;
   H_CUDA(cudaMemsetAsync(h->info.p, 0, sizeof(int), h->st));
-  H_CUDA(spd_inverse(h->st, mat, n, ld, (long long)n * ld, 1, small + 4, h->info.p, h->ws, &h->launches));
+  H_CUDA(spd_inverse(h->st, mat, n, ld, (long long)n * ld, 1, small + 4, h->info.p, h->ws_aux, &h->launches));
   H_CUDA(cudaMemcpy2DAsync(out, sizeof(double) * n, mat, sizeof(double) * ld, sizeof(double) * n, n,
                            cudaMemcpyDeviceToHost, h->st));
   H_CUDA(cudaMemcpyAsync(h->hbuf + 640, small + 4, sizeof(double), cudaMemcpyDeviceToHost, h->st));
@@ -1491,14 +1492,96 @@ extern "C" int mcb_dmvnorm(mcb_handle* h, int n, const double* x, const double* 
   quad_form_kernel<<<1, 256, 0, h->st>>>(n, ld, mat2, vec, vec + ld, small + 5);
   ++h->launches;
   // log det of the precision matrix from the pivots of its factorisation (the inverse itself is not used)
-  h->ws.max_ctas = 0;
   H_CUDA(cudaMemsetAsync(h->info.p, 0, sizeof(int), h->st));
-  H_CUDA(spd_inverse(h->st, mat, n, ld, (long long)n * ld, 1, small + 4, h->info.p, h->ws, &h->launches));
+  H_CUDA(spd_inverse(h->st, mat, n, ld, (long long)n * ld, 1, small + 4, h->info.p, h->ws_aux, &h->launches));
   H_CUDA(cudaMemcpyAsync(h->hbuf + 640, small + 4, sizeof(double) * 2, cudaMemcpyDeviceToHost, h->st));
   MCB_TRY(check_info(h, "dmvnorm"));
   const double logdet_prec = h->hbuf[640], ssq = h->hbuf[641];
   const double ll = -0.5 * ((double)n * kLog2Pi - logdet_prec + ssq);
   *out = want_log ? ll : exp(ll);
+  return MCB_OK;
+}
+
+// logL_GP_mod / gr_GP_mod (CF.R:194-216, 448-475; Z = 1) and logL_GP_mod_common_hp_k / gr_GP_mod_common_hp_k (CF.R:250-278,
+// 510-537; Z clusters sharing one theta) on EXPLICIT arguments: the reference's callbacks take (hp, db, mean, kern, new_cov,
+// pen_diag) and are also called on sub-problems that are not the resident hyper-posterior (update_tau_i_k_VEM evaluates
+// logL_GP_mod per individual and cluster, CF.R:746). Same device code as the resident evaluators, own scratch buffers.
+//   t[n] sorted timestamps, y[Z][n] outputs (db$Output per cluster), mean: Z values (scalar prior means) or [Z][n],
+//   new_cov[Z][n][n]; theta[nhp] with sigma = theta[2] (nhp == 3) or pen_diag (nhp == 2); g (nhp entries) may be NULL.
+extern "C" int mcb_gp_mod(mcb_handle* h, int n, int Z, const double* t, const double* y, const double* mean, int mean_len,
+                          const double* new_cov, const double* theta, int nhp, double pen_diag, double* f, double* g) {
+  if (!h) return MCB_EINVAL;
+  H_CHECK(n >= 1 && Z >= 1 && t && y && mean && new_cov && theta && f, MCB_EINVAL, "mcb_gp_mod: bad argument");
+  H_CHECK(nhp == 2 || nhp == 3, MCB_EINVAL, "mcb_gp_mod: nhp must be 2 or 3");
+  H_CHECK(Z <= 256, MCB_EINVAL, "mcb_gp_mod: at most 256 clusters per call");
+  H_CHECK(mean_len == Z || mean_len == Z * n, MCB_EINVAL, "mcb_gp_mod: mean must have Z or Z*n entries");
+  for (int a = 1; a < n; ++a) H_CHECK(t[a] > t[a - 1], MCB_EINVAL, "mcb_gp_mod: timestamps must be sorted and unique");
+  H_CUDA(cudaSetDevice(h->device));
+  spans_reset(h);
+  const int ld = (n + 15) & ~15;
+  const long long sN = (long long)n * ld;
+  // scratch: Kmat, D1, D2, Csum, X (n x ld each), cov[Z] (n x ld each), r[Z][ld], p[Z][ld], grid[ld], theta[3], logdet[1], red[12 Z]
+  const size_t need = (5 + (size_t)Z) * sN + (2 * (size_t)Z + 1) * ld + 8 + 12 * (size_t)Z;
+  H_CUDA(h->gscr.ensure(need));
+  H_CUDA(h->gscr_i.ensure(Z));
+  double* Kmat = h->gscr.p;
+  double* D1 = Kmat + sN;
+  double* D2 = D1 + sN;
+  double* Csum = D2 + sN;
+  double* X = Csum + sN;
+  double* covz = X + sN;
+  double* r = covz + (size_t)Z * sN;
+  double* pz = r + (size_t)Z * ld;
+  double* grid = pz + (size_t)Z * ld;
+  double* th_d = grid + ld;
+  double* logdet = th_d + 4;
+  double* red = logdet + 4;
+  H_CUDA(cudaMemsetAsync(h->gscr.p, 0, sizeof(double) * need, h->st));   // zero pads (contract of the dense toolkit)
+  H_CUDA(cudaMemsetAsync(h->gscr_i.p, 0, sizeof(int) * Z, h->st));       // every cluster in group 0
+  const double th[3] = {theta[0], theta[1], nhp == 3 ? theta[2] : pen_diag};
+  std::vector<double> rh((size_t)Z * ld, 0.0);
+  for (int z = 0; z < Z; ++z)
+    for (int a = 0; a < n; ++a)
+      rh[(size_t)z * ld + a] = y[(size_t)z * n + a] - (mean_len == Z ? mean[z] : mean[(size_t)z * n + a]);
+  H_CUDA(cudaMemcpyAsync(grid, t, sizeof(double) * n, cudaMemcpyHostToDevice, h->st));
+  H_CUDA(cudaMemcpyAsync(th_d, th, sizeof th, cudaMemcpyHostToDevice, h->st));
+  H_CUDA(cudaMemcpyAsync(r, rh.data(), sizeof(double) * Z * ld, cudaMemcpyHostToDevice, h->st));
+  for (int z = 0; z < Z; ++z)
+    H_CUDA(cudaMemcpy2DAsync(covz + z * sN, sizeof(double) * ld, new_cov + (size_t)z * n * n, sizeof(double) * n,
+                             sizeof(double) * n, n, cudaMemcpyHostToDevice, h->st));
+  const bool want_grad = g != nullptr;
+  {
+    PhaseScope ps(h, PH_MSTEP_K);
+    se_build(h->st, Kmat, want_grad ? D1 : nullptr, want_grad ? D2 : nullptr, n, ld, sN, grid, th_d, 3, 1, &h->launches);
+    H_CUDA(cudaMemsetAsync(h->info.p, 0, sizeof(int), h->st));
+    H_CUDA(spd_inverse(h->st, Kmat, n, ld, sN, 1, logdet, h->info.p, h->ws_aux, &h->launches));
+    sum_groups(h->st, n, ld, sN, covz, h->gscr_i.p, Z, Csum, 1, &h->launches);
+    symv_mapped(h->st, n, ld, sN, Kmat, h->gscr_i.p, r, pz, Z, &h->launches);
+    double* redg = red;            // [1][4]
+    double* redz = red + 4 * Z;    // [Z][4]
+    double* redt = redz + 4 * Z;   // [1][4]
+    group_reduce(h->st, n, ld, sN, Kmat, Csum, sN, want_grad ? D1 : nullptr, want_grad ? D2 : nullptr, redg, 1, &h->launches);
+    cluster_reduce(h->st, n, ld, sN, r, pz, want_grad ? D1 : nullptr, want_grad ? D2 : nullptr, h->gscr_i.p, redz, Z,
+                   &h->launches);
+    if (want_grad) {
+      gemm_nt(h->st, n, n, n, Kmat, ld, sN, Csum, ld, sN, X, ld, sN, 1.0, 0.0, 1, &h->launches);
+      gemm_nt_trace(h->st, n, X, ld, sN, Kmat, ld, sN, D1, D2, ld, sN, redt, 4, 1, &h->launches);
+    }
+  }
+  double* hr = h->hbuf + 4096;
+  H_CUDA(cudaMemcpyAsync(hr, red, sizeof(double) * 12 * Z, cudaMemcpyDeviceToHost, h->st));
+  H_CUDA(cudaMemcpyAsync(hr + 12 * Z, logdet, sizeof(double), cudaMemcpyDeviceToHost, h->st));
+  MCB_TRY(check_info(h, "logL_GP_mod"));
+  const double* hg = hr;
+  const double* hz = hr + 4 * Z;
+  const double* ht = hr + 8 * Z;
+  double q = 0, pp = 0, d1 = 0, d2 = 0;
+  for (int z = 0; z < Z; ++z) { q += hz[4 * z]; pp += hz[4 * z + 1]; d1 += hz[4 * z + 2]; d2 += hz[4 * z + 3]; }
+  *f = 0.5 * Z * ((double)n * kLog2Pi + hr[12 * Z]) + 0.5 * q + 0.5 * hg[0];
+  if (want_grad) {
+    const double go[3] = {-0.5 * (d1 + ht[0] - Z * hg[1]), -0.5 * (d2 + ht[1] - Z * hg[2]), -th[2] * (pp + ht[2] - Z * hg[3])};
+    for (int j = 0; j < nhp; ++j) g[j] = go[j];
+  }
   return MCB_OK;
 }
 

@@ -41,6 +41,8 @@ struct mcb_handle {
   mcb::DevBuf<double> Winv, pvec, yWy, logdet_i, c1, c2, Fi, fi_tmp, gi_tmp;
   mcb::DevBuf<int> nfev_i, niter_i, status_i, order_i;
   mcb::DevBuf<double> kscr;   // scratch of the stand-alone kern_to_cov / kern_to_inv / dmvnorm entry points
+  mcb::DevBuf<double> gscr;   // scratch of mcb_gp_mod (explicit-argument logL_GP_mod / gr_GP_mod)
+  mcb::DevBuf<int> gscr_i;
   mcb::DevBuf<double> Fnew;   // F_i at theta_i_new as left by the per-individual M-step kernel
   bool fnew_valid = false;
   bool nfev_valid = false;   // nfev_i holds the counts of a previous per-individual M-step on this data set
@@ -65,13 +67,14 @@ struct mcb_handle {
   long long mopt_pre = 0, mopt_body = 0;  // kernels before the loop / per evaluation
   mcb::DevBuf<double> mopt_state;         // the L-BFGS state (Lbfgs struct) + result slots
   cudaStream_t st_cap = nullptr;          // capture-only stream for conditional-node bodies
-  mcb::DenseWs ws;
+  mcb::DenseWs ws;       // training path only: its buffers are baked into the captured graphs (sized by alloc_state, never grown later)
+  mcb::DenseWs ws_aux;   // posterior_mu_k on another grid and the stand-alone kern_to_inv / dmvnorm: may grow at any time
   mcb::DevBuf<int> info;
   mcb::DevBuf<double> scal;        // small device scalars
 
   // ---- prediction posterior ----
   bool has_pred = false;
-  int T = 0, ldT = 0;
+  int T = 0, ldT = 0, Kp = 0;      // Kp: clusters of the prediction posterior (== K after mcb_posterior_mu_k)
   mcb::DevBuf<double> pgrid, pKinv, pcov, pwk, pmean, plogdet;
   std::vector<double> h_pi_pred;   // pi_k = mean_i tau_ik of the frozen tau (MC.R:141)
   mcb::DevBuf<int> pmapidx;        // training row -> index in the prediction grid

@@ -282,12 +282,11 @@ extern "C" int mcb_posterior_mu_k(mcb_handle* h, int T, const double* timestamps
     H_CHECK(constant || T == N, MCB_EINVAL, "mcb_posterior_mu_k: vector prior means need T == N");
     for (int j = 0; j < T; ++j) mkT[(size_t)k * ldT + j] = constant ? mk[(size_t)k * h->ld] : mk[(size_t)k * h->ld + j];
   }
-  H_CUDA(h->eX.ensure(std::max((size_t)K * ldT, h->eX.cap)));
   double* mkT_d = h->pmean.p;  // staged here, overwritten by the result below
   H_CUDA(sync_copy(h, mkT_d, mkT.data(), sizeof(double) * K * ldT, cudaMemcpyHostToDevice));
   {
     se_build(h->st, h->pKinv.p, nullptr, nullptr, T, ldT, sT, h->pgrid.p, h->etheta.p, 3, G, &h->launches);
-    H_CUDA(spd_inverse(h->st, h->pKinv.p, T, ldT, sT, G, h->plogdet.p, h->info.p, h->ws, &h->launches));
+    H_CUDA(spd_inverse(h->st, h->pKinv.p, T, ldT, sT, G, h->plogdet.p, h->info.p, h->ws_aux, &h->launches));
     copy_mapped(h->st, T, ldT, sT, h->pKinv.p, h->egmap.p, h->pcov.p, K, h->rank == 0 ? 1.0 : 0.0, &h->launches);
     if (h->rank == 0) symv_mapped(h->st, T, ldT, sT, h->pKinv.p, h->egmap.p, mkT_d, h->pwk.p, K, &h->launches);
     else H_CUDA(cudaMemsetAsync(h->pwk.p, 0, sizeof(double) * K * ldT, h->st));
@@ -298,7 +297,7 @@ extern "C" int mcb_posterior_mu_k(mcb_handle* h, int T, const double* timestamps
     ++h->launches;
     MCB_TRY(comm_allreduce_sum(h, h->pcov.p, (size_t)K * sT));
     MCB_TRY(comm_allreduce_sum(h, h->pwk.p, (size_t)K * ldT));
-    H_CUDA(spd_inverse(h->st, h->pcov.p, T, ldT, sT, K, h->plogdet.p + K, h->info.p, h->ws, &h->launches));
+    H_CUDA(spd_inverse(h->st, h->pcov.p, T, ldT, sT, K, h->plogdet.p + K, h->info.p, h->ws_aux, &h->launches));
     symv(h->st, T, h->pcov.p, ldT, sT, h->pwk.p, ldT, h->pmean.p, ldT, K, &h->launches);
   }
   int flag = 0;
@@ -315,13 +314,44 @@ extern "C" int mcb_posterior_mu_k(mcb_handle* h, int T, const double* timestamps
   h->h_pi_pred.resize(K);
   H_CUDA(sync_copy(h, h->h_pi_pred.data(), h->plogdet.p, sizeof(double) * K, cudaMemcpyDeviceToHost));
   for (auto& v : h->h_pi_pred) v /= (double)h->M_total;
-  h->T = T; h->ldT = ldT; h->has_pred = true;
+  h->T = T; h->ldT = ldT; h->Kp = K; h->has_pred = true;
   if (out_mean)
     H_CUDA(sync_copy2d(h, out_mean, sizeof(double) * T, h->pmean.p, sizeof(double) * ldT, sizeof(double) * T, K, cudaMemcpyDeviceToHost));
   if (out_cov)
     for (int k = 0; k < K; ++k)
       H_CUDA(sync_copy2d(h, out_cov + (size_t)k * T * T, sizeof(double) * T, h->pcov.p + k * sT, sizeof(double) * ldT,
                           sizeof(double) * T, T, cudaMemcpyDeviceToHost));
+  return MCB_OK;
+}
+
+// Install an explicit prediction posterior: the `list_mu` of pred_gp_clust (MC.R:235) / `mean_k`, `cov_k` of
+// update_tau_star_k_EM (CF.R:764) when the caller supplies one (full_algo_clust(mu_k = ...), a model loaded from disk, a
+// posterior computed by another handle) instead of the result of this handle's last mcb_posterior_mu_k.
+extern "C" int mcb_set_pred_posterior(mcb_handle* h, int K, int T, const double* timestamps, const double* mean,
+                                      const double* cov, const double* pi_k) {
+  if (!h || !timestamps || !mean || !cov) return MCB_EINVAL;
+  H_CHECK(K >= 1 && T >= 1, MCB_EINVAL, "mcb_set_pred_posterior: bad shape");
+  for (int j = 1; j < T; ++j)
+    H_CHECK(timestamps[j] > timestamps[j - 1], MCB_EINVAL, "mcb_set_pred_posterior: timestamps must be sorted and unique");
+  H_CUDA(cudaSetDevice(h->device));
+  const int ldT = (T + 15) & ~15;
+  const long long sT = (long long)T * ldT;
+  h->has_pred = false;
+  H_CUDA(h->pgrid.ensure(T));
+  H_CUDA(h->pKinv.ensure((size_t)K * sT)); H_CUDA(h->pcov.ensure((size_t)K * sT));
+  H_CUDA(h->pwk.ensure((size_t)K * ldT)); H_CUDA(h->pmean.ensure((size_t)K * ldT)); H_CUDA(h->plogdet.ensure(2 * K));
+  H_CUDA(cudaMemsetAsync(h->pcov.p, 0, sizeof(double) * h->pcov.cap, h->st));   // zero row padding (ld % 16 == 0)
+  H_CUDA(cudaMemsetAsync(h->pmean.p, 0, sizeof(double) * h->pmean.cap, h->st));
+  H_CUDA(cudaMemcpyAsync(h->pgrid.p, timestamps, sizeof(double) * T, cudaMemcpyHostToDevice, h->st));
+  H_CUDA(cudaMemcpy2DAsync(h->pmean.p, sizeof(double) * ldT, mean, sizeof(double) * T, sizeof(double) * T, K,
+                           cudaMemcpyHostToDevice, h->st));
+  for (int k = 0; k < K; ++k)
+    H_CUDA(cudaMemcpy2DAsync(h->pcov.p + k * sT, sizeof(double) * ldT, cov + (size_t)k * T * T, sizeof(double) * T,
+                             sizeof(double) * T, T, cudaMemcpyHostToDevice, h->st));
+  H_CUDA(cudaStreamSynchronize(h->st));
+  h->h_pi_pred.assign(K, 1.0 / K);
+  if (pi_k) h->h_pi_pred.assign(pi_k, pi_k + K);
+  h->T = T; h->ldT = ldT; h->Kp = K; h->has_pred = true;
   return MCB_OK;
 }
 
@@ -333,7 +363,7 @@ extern "C" int mcb_predict(mcb_handle* h, int B, const int* offsets, const int* 
   H_CHECK(B >= 1 && offsets[0] == 0, MCB_EINVAL, "mcb_predict: bad offsets");
   H_CHECK((out_mean == nullptr) == (out_var == nullptr), MCB_EINVAL, "mcb_predict: pass both out_mean and out_var or neither");
   H_CHECK(out_mean == nullptr || (Tp >= 1 && pred_idx), MCB_EINVAL, "mcb_predict: prediction targets missing");
-  const int K = h->K, T = h->T;
+  const int K = h->Kp, T = h->T;
   const long long Pn = offsets[B];
   int nmax = 0;
   for (int b = 0; b < B; ++b) {
@@ -470,7 +500,7 @@ int new_indiv_upload(mcb_handle* h, NewIndivDev& d, int B, const int* offsets, c
 int new_indiv_eval(void* ctx, int npts, const int* pt_ind, const double* pt_theta, double* out) {
   NewIndivDev& d = *static_cast<NewIndivDev*>(ctx);
   mcb_handle* h = d.h;
-  const int K = h->K;
+  const int K = h->Kp;
   cudaError_t e = cudaSuccess;
   if ((e = d.pt_ind.ensure(npts)) || (e = d.pt_theta.ensure(3 * (size_t)npts)) || (e = d.out.ensure((size_t)npts * K))) {
     h->err = std::string("new-individual objective: ") + cudaGetErrorString(e);
@@ -513,7 +543,7 @@ extern "C" int mcb_train_new_indiv(mcb_handle* h, int B, const int* offsets, con
   MCB_TRY(new_indiv_upload(h, d, B, offsets, obs_idx, y, "mcb_train_new_indiv"));
   h->launches = 0;
   const double* pi = pi_k ? pi_k : h->h_pi_pred.data();
-  const int rc = mcb_new_indiv_em(B, h->K, theta0, theta0_per_indiv, pi, n_loop_max, new_indiv_eval, &d, out_theta,
+  const int rc = mcb_new_indiv_em(B, h->Kp, theta0, theta0_per_indiv, pi, n_loop_max, new_indiv_eval, &d, out_theta,
                                   out_tau, out_loops);
   d.release();
   if (rc != MCB_OK && h->err.empty()) h->err = "mcb_train_new_indiv: the EM driver failed";

@@ -28,6 +28,7 @@ class Engine:
         self.h = h
         self.M = self.N = self.K = 0
         self.T = 0
+        self.Kp = 0   # clusters of the resident prediction posterior
 
     # ------------------------------------------------------------------------------------------
     def close(self):
@@ -250,12 +251,36 @@ class Engine:
         t = f64(tau) if tau is not None else None
         self._ck(self.lib.mcb_posterior_mu_k(self.h, T, dptr(ts), dptr(t), dptr(mean), dptr(cov)))
         self.T = T
+        self.Kp = self.K
         return mean, cov
+
+    def set_pred_posterior(self, timestamps, mean, cov, pi_k=None):
+        """install an explicit prediction posterior (list_mu of pred_gp_clust, MC.R:235) instead of the result of
+        posterior_mu_k: timestamps [T] sorted, mean [K][T], cov [K][T][T], pi_k [K] (None: 1/K)"""
+        ts, mean, cov = f64(timestamps), f64(mean), f64(cov)
+        K, T = mean.shape
+        assert ts.shape == (T,) and cov.shape == (K, T, T)
+        pi = f64(pi_k) if pi_k is not None else None
+        self._ck(self.lib.mcb_set_pred_posterior(self.h, K, T, dptr(ts), dptr(mean), dptr(cov), dptr(pi)))
+        self.T, self.Kp = T, K
+
+    def gp_mod(self, t, y, mean, new_cov, theta, pen_diag=0.0, grad=True):
+        """logL_GP_mod / gr_GP_mod (Z = 1) or the common_hp_k forms (Z clusters) on explicit arguments (CF.R:194-216, 250-278,
+        448-475, 510-537): t [n], y [Z][n], mean [Z] or [Z][n], new_cov [Z][n][n], theta [2 or 3] -> (f, g or None)"""
+        t, y, mean, new_cov, theta = f64(t), f64(np.atleast_2d(y)), f64(mean).ravel(), f64(new_cov), f64(theta)
+        Z, n = y.shape
+        new_cov = new_cov.reshape(Z, n, n)
+        nhp = theta.shape[0]
+        f = np.empty(1)
+        g = np.empty(nhp) if grad else None
+        self._ck(self.lib.mcb_gp_mod(self.h, n, Z, dptr(t), dptr(y), dptr(mean), mean.shape[0], dptr(new_cov), dptr(theta),
+                                     nhp, float(pen_diag), dptr(f), dptr(g)))
+        return float(f[0]), g
 
     def predict(self, offsets, obs_idx, y, theta_new, pred_idx=None, pi_k=None):
         offsets, obs_idx, y, theta_new = i32(offsets), i32(obs_idx), f64(y), f64(theta_new)
         B = offsets.shape[0] - 1
-        tau = np.empty((B, self.K))
+        tau = np.empty((B, self.Kp))
         pi = f64(pi_k) if pi_k is not None else None
         if pred_idx is None:
             self._ck(self.lib.mcb_predict(self.h, B, iptr(offsets), iptr(obs_idx), dptr(y), dptr(theta_new), dptr(pi), 0,
@@ -263,8 +288,8 @@ class Engine:
             return tau, None, None
         pred_idx = i32(pred_idx)
         Tp = pred_idx.shape[0]
-        mean = np.empty((B, self.K, Tp))
-        var = np.empty((B, self.K, Tp))
+        mean = np.empty((B, self.Kp, Tp))
+        var = np.empty((B, self.Kp, Tp))
         self._ck(self.lib.mcb_predict(self.h, B, iptr(offsets), iptr(obs_idx), dptr(y), dptr(theta_new), dptr(pi), Tp,
                                       iptr(pred_idx), dptr(tau), dptr(mean), dptr(var)))
         return tau, mean, var
@@ -275,7 +300,7 @@ class Engine:
         offsets, obs_idx, y = i32(offsets), i32(obs_idx), f64(y)
         pt_ind, pt_theta = i32(pt_ind), f64(pt_theta).reshape(-1, 3)
         assert pt_ind.shape[0] == pt_theta.shape[0]
-        out = np.empty((pt_ind.shape[0], self.K))
+        out = np.empty((pt_ind.shape[0], self.Kp))
         self._ck(self.lib.mcb_new_indiv_logl(self.h, offsets.shape[0] - 1, iptr(offsets), iptr(obs_idx), dptr(y),
                                              pt_ind.shape[0], iptr(pt_ind), dptr(pt_theta), dptr(out)))
         return out
@@ -287,7 +312,7 @@ class Engine:
         per = theta0.ndim == 2
         assert theta0.shape == ((B, 3) if per else (3,))
         pi = f64(pi_k) if pi_k is not None else None
-        th, tau, loops = np.empty((B, 3)), np.empty((B, self.K)), np.empty(B, dtype=np.int32)
+        th, tau, loops = np.empty((B, 3)), np.empty((B, self.Kp)), np.empty(B, dtype=np.int32)
         self._ck(self.lib.mcb_train_new_indiv(self.h, B, iptr(offsets), iptr(obs_idx), dptr(y), dptr(theta0), int(per),
                                               dptr(pi), int(n_loop_max), dptr(th), dptr(tau), iptr(loops)))
         return th, tau, loops

@@ -17,6 +17,7 @@ R itself is not available in the build image; the `.Call` shim that exposes the 
 """
 from __future__ import annotations
 
+import hashlib
 import time
 
 import numpy as np
@@ -41,6 +42,20 @@ def _check_kernels(*kerns):
         if k is not kernel and k is not kernel_mu:
             raise ValueError("only the reference's squared-exponential kernels (kernel, kernel_mu) are "
                              "implemented on the GPU path; other closures are rejected (no fallback)")
+
+
+def _db_digest(db):
+    """content hash of a `db` (ID, Timestamp, Output columns in row order): decides whether the resident CSR copy of the
+    training set is still the caller's data. O(P) host work, negligible next to an upload."""
+    ids = np.asarray(db["ID"])
+    h = hashlib.blake2b(digest_size=16)
+    if ids.dtype.kind in "iufb":
+        h.update(ids.dtype.str.encode()); h.update(np.ascontiguousarray(ids).tobytes())
+    else:
+        h.update("\x00".join(str(v) for v in ids.tolist()).encode())
+    h.update(np.ascontiguousarray(db["Timestamp"], dtype=np.float64).tobytes())
+    h.update(np.ascontiguousarray(db["Output"], dtype=np.float64).tobytes())
+    return h.digest()
 
 
 class NamedMat:
@@ -87,7 +102,7 @@ class Canon:
                 raise ValueError(f"rows of individual {self.ids[a]!r} must be sorted by Timestamp and unique "
                                  "(the reference assumes it, SURVEY.md §8.0 Q2)")
         self.M, self.N = len(self.ids), self.grid.shape[0]
-        self.fingerprint = (ids.shape[0], float(ts.sum()), float(ys.sum()), self.M)
+        self.fingerprint = _db_digest(db)
 
 
 class Session:
@@ -96,20 +111,32 @@ class Session:
     def __init__(self, device: int = 0):
         self.eng = Engine(device)
         self.canon = None
-        self._post_token = None
+        self._token = None
+        self._post_ref = None   # (mean dict, cov dict) objects of the resident hyper-posterior (strong references)
         self._epoch = 0
+        self._pred_ref = None   # (mean dict, cov dict) objects of the resident PREDICTION posterior
+        self._mk = None
 
     def close(self):
         self.eng.close()
 
+    @property
+    def _post_token(self):
+        return self._token
+
+    @_post_token.setter
+    def _post_token(self, v):
+        self._token = v
+        if v is None:
+            self._post_ref = None   # the resident hyper-posterior no longer is the one those objects describe
+
+    def set_state(self, theta_k, theta_i, pi, mk, tau):
+        self.eng.set_state(theta_k, theta_i, pi, mk, tau)
+        self._mk = np.asarray(mk, dtype=np.float64).ravel().copy()   # resident prior means (K or K*N values)
+
     # -- data ------------------------------------------------------------------------------------
     def ensure_data(self, db):
-        fp = None
-        if self.canon is not None:
-            ids = np.asarray(db["ID"])
-            fp = (ids.shape[0], float(np.asarray(db["Timestamp"], dtype=np.float64).sum()),
-                  float(np.asarray(db["Output"], dtype=np.float64).sum()), self.canon.M)
-        if self.canon is None or fp != self.canon.fingerprint:
+        if self.canon is None or _db_digest(db) != self.canon.fingerprint:
             c = Canon(db)
             self.eng.set_data(c.offsets, c.grid_idx, c.y, c.grid)
             self.canon = c
@@ -148,7 +175,22 @@ class Session:
         self._epoch += 1
         self._post_token = (id(self), self._epoch)
         out["_token"] = self._post_token
+        self._post_ref = (out["mean"], out.get("cov"))
         return out
+
+    def ensure_pred(self, mean_k, cov_k, pi_k=None):
+        """make (mean_k, cov_k) the resident prediction posterior. No copies when they are the very objects the last
+        posterior_mu_k of this session returned (identity, held by strong reference); anything else -- a mu_k supplied by
+        the caller, read from disk, or computed by another session / an earlier call -- is uploaded."""
+        ref = self._pred_ref
+        if ref is not None and mean_k is ref[0] and cov_k is ref[1]:
+            return
+        names_k = list(mean_k.keys())
+        ts = np.asarray(mean_k[names_k[0]]["Timestamp"], dtype=np.float64)
+        mean = np.array([np.asarray(mean_k[k]["Output"], dtype=np.float64) for k in names_k])
+        cov = np.array([np.asarray(getattr(cov_k[k], "m", cov_k[k]), dtype=np.float64) for k in names_k])
+        self.eng.set_pred_posterior(ts, mean, cov, pi_k)
+        self._pred_ref = (mean_k, cov_k)
 
     def ensure_posterior(self, hp, m_k, param):
         """make (hp, param) the resident state; no copies when `param` is what the last E-step left"""
@@ -159,7 +201,7 @@ class Session:
         theta_k, theta_i = self.pack_hp(hp, names_k)
         tau = self.pack_tau(param["tau_i_k"], names_k)
         pi = np.asarray(hp.get("pi_k", np.full(len(names_k), 1.0 / len(names_k))), dtype=np.float64)
-        self.eng.set_state(theta_k, theta_i, pi, self.pack_mk(m_k, names_k), tau)
+        self.set_state(theta_k, theta_i, pi, self.pack_mk(m_k, names_k), tau)
         mean = np.array([np.asarray(param["mean"][k]["Output"], dtype=np.float64) for k in names_k])
         cov = np.array([param["cov"][k].m for k in names_k])
         self.eng.set_posterior(mean, cov, tau)
@@ -263,7 +305,7 @@ def e_step_VEM(db, m_k, kern_0, kern_i, hp, old_tau_i_k, session=None, want_cov=
     s.ensure_data(db)
     names_k = list(m_k.keys())
     theta_k, theta_i = s.pack_hp(hp, names_k)
-    s.eng.set_state(theta_k, theta_i, np.asarray(hp["pi_k"], dtype=np.float64), s.pack_mk(m_k, names_k),
+    s.set_state(theta_k, theta_i, np.asarray(hp["pi_k"], dtype=np.float64), s.pack_mk(m_k, names_k),
                     s.pack_tau(old_tau_i_k, names_k))
     s.eng.e_step()
     out = s.param_from_device(names_k, s.eng.get_tau_new(), want_cov)
@@ -281,7 +323,7 @@ def update_tau_i_k_VEM(db, m_k, mean_k, cov_k, kern_i, hp, pi_k, session=None):
     hp_full = hp if "theta_k" in hp else dict(hp, theta_k={k: np.array([1.0, 1.0, 0.2]) for k in names_k})  # unused here
     theta_k, theta_i = s.pack_hp(hp_full, names_k)
     M = theta_i.shape[0]
-    s.eng.set_state(theta_k, theta_i, np.asarray(pi_k, dtype=np.float64), s.pack_mk(m_k, names_k),
+    s.set_state(theta_k, theta_i, np.asarray(pi_k, dtype=np.float64), s.pack_mk(m_k, names_k),
                     np.full((M, len(names_k)), 1.0 / len(names_k)))
     mean = np.array([np.asarray(mean_k[k]["Output"], dtype=np.float64) for k in names_k])
     cov = np.array([np.asarray(getattr(cov_k[k], "m", cov_k[k]), dtype=np.float64) for k in names_k])
@@ -360,29 +402,82 @@ def gr_clust_multi_GP_common_hp_i(hp, db, mu_k_param, kern, session=None):
     return s.eng.eval_indiv_common(np.asarray(hp, dtype=np.float64)[:3], grad=True)[1]
 
 
-def logL_GP_mod(hp, k, pen_diag=None, session=None):
-    """CF.R:194-216 for mean process number `k` of the resident hyper-posterior (db = mean_k, mean = m_k,
-    new_cov = cov_k are the resident ones)."""
+def _mat(x):
+    return np.asarray(getattr(x, "m", x), dtype=np.float64)
+
+
+def _resident_cluster(s, db, mean, new_cov):
+    """position of the cluster whose resident hyper-posterior mean / covariance ARE `db` / `new_cov` (object identity with
+    what the last e_step_VEM / training_VEM of this session returned) and whose resident prior mean equals `mean`;
+    None otherwise (the evaluation then runs on the explicit arguments)"""
+    ref = s._post_ref
+    if ref is None or s._post_token is None or ref[1] is None or s._mk is None:
+        return None
+    for ck, k in enumerate(ref[0]):
+        if db is ref[0][k] and new_cov is ref[1][k]:
+            mk = s._mk[ck] if s._mk.shape[0] == len(ref[0]) else s._mk[ck * s.canon.N:(ck + 1) * s.canon.N]
+            m = np.atleast_1d(np.asarray(mean, dtype=np.float64))
+            return ck if (m.shape[0] in (1, np.size(mk)) and np.all(m == mk)) else None
+    return None
+
+
+def _gp_mod(hp, db, mean, kern, new_cov, pen_diag, grad, session):
+    _check_kernels(kern)
     s = session or default_session()
-    return s.eng.eval_mean(k, np.asarray(hp, dtype=np.float64), 0.0 if pen_diag is None else pen_diag, grad=False)[0]
+    hp = np.asarray(hp, dtype=np.float64).ravel()[:3]
+    pen = 0.0 if pen_diag is None else float(pen_diag)
+    k = _resident_cluster(s, db, mean, new_cov)
+    if k is not None:
+        return s.eng.eval_mean(k, hp, pen, grad=grad)
+    t = np.asarray(db["Timestamp"], dtype=np.float64)
+    y = np.asarray(db["Output"], dtype=np.float64)
+    m = np.atleast_1d(np.asarray(mean, dtype=np.float64))
+    if t.shape[0] == 1 and grad:
+        # CF.R:460-463: one timestamp only -- the reference takes a branch of its own; same arithmetic on 1 x 1 matrices
+        pass
+    return s.eng.gp_mod(t, y[None, :], m, _mat(new_cov)[None], hp, pen, grad=grad)
 
 
-def gr_GP_mod(hp, k, pen_diag=None, session=None):
-    """CF.R:448-475."""
+def logL_GP_mod(hp, db, mean, kern, new_cov, pen_diag=None, session=None):
+    """CF.R:194-216 with the reference's argument list: hp (a, b[, sigma]), db = {'Timestamp', 'Output'}, mean (scalar or
+    vector), kern, new_cov (n x n), pen_diag. When (db, new_cov) are a mean process of the resident hyper-posterior the
+    evaluation runs against the device-resident copies (what m_step_VEM does, CF.R:675); otherwise the arguments are
+    uploaded (`mcb_gp_mod`)."""
+    return _gp_mod(hp, db, mean, kern, new_cov, pen_diag, False, session)[0]
+
+
+def gr_GP_mod(hp, db, mean, kern, new_cov, pen_diag=None, session=None):
+    """CF.R:448-475 -> numeric[length(hp)]."""
+    return _gp_mod(hp, db, mean, kern, new_cov, pen_diag, True, session)[1]
+
+
+def _gp_mod_common(hp, db, mean, kern, new_cov, pen_diag, grad, session):
+    _check_kernels(kern)
     s = session or default_session()
-    return s.eng.eval_mean(k, np.asarray(hp, dtype=np.float64), 0.0 if pen_diag is None else pen_diag, grad=True)[1]
+    hp = np.asarray(hp, dtype=np.float64).ravel()[:3]
+    pen = 0.0 if pen_diag is None else float(pen_diag)
+    names_k = list(db.keys())
+    ref = s._post_ref
+    if ref is not None and s._post_token is not None and db is ref[0] and new_cov is ref[1] and s._mk is not None and \
+            all(_resident_cluster(s, db[k], mean[k], new_cov[k]) == ck for ck, k in enumerate(names_k)):
+        return s.eng.eval_mean_common(hp, pen, grad=grad)
+    t = np.asarray(db[names_k[0]]["Timestamp"], dtype=np.float64)       # t_k = db[[1]]$Timestamp, CF.R:264
+    y = np.array([np.asarray(db[k]["Output"], dtype=np.float64) for k in names_k])
+    ms = [np.atleast_1d(np.asarray(mean[k], dtype=np.float64)) for k in names_k]
+    m = np.array([v[0] for v in ms]) if all(v.shape[0] == 1 for v in ms) else \
+        np.concatenate([np.repeat(v, t.shape[0]) if v.shape[0] == 1 else v for v in ms])
+    cov = np.array([_mat(new_cov[k]) for k in names_k])
+    return s.eng.gp_mod(t, y, m, cov, hp, pen, grad=grad)
 
 
-def logL_GP_mod_common_hp_k(hp, pen_diag=None, session=None):
-    """CF.R:250-278."""
-    s = session or default_session()
-    return s.eng.eval_mean_common(np.asarray(hp, dtype=np.float64), 0.0 if pen_diag is None else pen_diag, grad=False)[0]
+def logL_GP_mod_common_hp_k(hp, db, mean, kern, new_cov, pen_diag=None, session=None):
+    """CF.R:250-278: db = {k: {'Timestamp', 'Output'}} (the K mean processes), mean = {k: m_k}, new_cov = {k: cov_k}."""
+    return _gp_mod_common(hp, db, mean, kern, new_cov, pen_diag, False, session)[0]
 
 
-def gr_GP_mod_common_hp_k(hp, pen_diag=None, session=None):
+def gr_GP_mod_common_hp_k(hp, db, mean, kern, new_cov, pen_diag=None, session=None):
     """CF.R:510-537."""
-    s = session or default_session()
-    return s.eng.eval_mean_common(np.asarray(hp, dtype=np.float64), 0.0 if pen_diag is None else pen_diag, grad=True)[1]
+    return _gp_mod_common(hp, db, mean, kern, new_cov, pen_diag, True, session)[1]
 
 
 def logL_monitoring_VEM(hp, db, kern_i, kern_0, mu_k_param, m_k, session=None):
@@ -408,7 +503,7 @@ def BIC(hp, db, kern_0, kern_i, m_k, mu_k_param, clust=True, session=None):
     # evaluate at (hp, mu_k_param): install both (mat_logL is recomputed at these hp with tau frozen)
     theta_k, theta_i = s.pack_hp(hp, names_k)
     tau = s.pack_tau(mu_k_param["tau_i_k"], names_k)
-    s.eng.set_state(theta_k, theta_i, np.asarray(hp["pi_k"], dtype=np.float64), s.pack_mk(m_k, names_k), tau)
+    s.set_state(theta_k, theta_i, np.asarray(hp["pi_k"], dtype=np.float64), s.pack_mk(m_k, names_k), tau)
     mean = np.array([np.asarray(mu_k_param["mean"][k]["Output"], dtype=np.float64) for k in names_k])
     cov = np.array([mu_k_param["cov"][k].m for k in names_k])
     s.eng.set_posterior(mean, cov, tau)
@@ -459,12 +554,18 @@ def training_VEM(db, prior_mean_k, ini_hp=None, kern_0=kernel_mu, kern_i=kernel,
     c = s.ensure_data(db)
     names_k = list(prior_mean_k.keys())
     K = len(names_k)
+    missing = [k for k in names_k if k not in ini_tau_i_k]
+    if missing or len(ini_tau_i_k) != K:
+        raise ValueError(f"ini_tau_i_k must hold one entry per cluster of prior_mean_k {names_k}; got {list(ini_tau_i_k)} "
+                         "(a k-means initialisation that found fewer than K clusters cannot start the VEM)")
     tau0 = s.pack_tau(ini_tau_i_k, names_k)
     theta_k = np.tile(np.asarray(ini_hp["theta_k"], dtype=np.float64)[:3], (K, 1))
     theta_i = np.tile(np.asarray(ini_hp["theta_i"], dtype=np.float64)[:3], (c.M, 1))
-    pi = tau0.mean(axis=0)  # MC.R:39
+    # MC.R:39: sapply(tau_i_k, mean) runs in the LIST order of ini_tau_i_k (first appearance of the k-means labels,
+    # MC.R:603) while update_tau_i_k_VEM multiplies pi_k positionally (CF.R:757): quirk Q3, kept
+    pi = np.array([np.mean([float(v) for v in ini_tau_i_k[k].values()]) for k in ini_tau_i_k])
     t1 = time.time()
-    s.eng.set_state(theta_k, theta_i, pi, s.pack_mk(prior_mean_k, names_k), tau0)
+    s.set_state(theta_k, theta_i, pi, s.pack_mk(prior_mean_k, names_k), tau0)
     seq_logL = []
     cv = False
     for it in range(n_loop_max):
@@ -496,13 +597,15 @@ def posterior_mu_k(db, timestamps, m_k, kern_0, kern_i, list_hp, session=None):
     pi = np.asarray(list_hp["hp"].get("pi_k", tau.mean(axis=0)), dtype=np.float64)
     tk, ti, _ = (s.eng.get_hp() if s.eng.K == len(names_k) else (None, None, None))
     if tk is None or not (np.array_equal(tk, theta_k) and np.array_equal(ti, theta_i)):
-        s.eng.set_state(theta_k, theta_i, pi, s.pack_mk(m_k, names_k), tau)
+        s.set_state(theta_k, theta_i, pi, s.pack_mk(m_k, names_k), tau)
         s._post_token = None
     ts = np.asarray(timestamps, dtype=np.float64)
     mean, cov = s.eng.posterior_mu_k(ts, tau)
-    return {"mean": {k: {"Timestamp": ts, "Output": mean[ck]} for ck, k in enumerate(names_k)},
-            "cov": {k: NamedMat(cov[ck], ts) for ck, k in enumerate(names_k)},
-            "tau_i_k": list_hp["param"]["tau_i_k"], "_pred_session": id(s)}
+    out = {"mean": {k: {"Timestamp": ts, "Output": mean[ck]} for ck, k in enumerate(names_k)},
+           "cov": {k: NamedMat(cov[ck], ts) for ck, k in enumerate(names_k)},
+           "tau_i_k": list_hp["param"]["tau_i_k"]}
+    s._pred_ref = (out["mean"], out["cov"])   # these very objects describe the resident prediction posterior
+    return out
 
 
 def _csr_new(new_dbs, ts):
@@ -519,9 +622,11 @@ def _csr_new(new_dbs, ts):
 
 
 def update_tau_star_k_EM(db, mean_k, cov_k, kern, hp, pi_k, session=None):
-    """CF.R:764-786 against the resident prediction posterior (the one `posterior_mu_k` just produced)."""
+    """CF.R:764-786. (mean_k, cov_k) are used as given: when they are the objects the last posterior_mu_k of this session
+    returned they are already resident, otherwise they are uploaded first."""
     _check_kernels(kern)
     s = session or default_session()
+    s.ensure_pred(mean_k, cov_k)
     names_k = list(mean_k.keys())
     ts = np.asarray(mean_k[names_k[0]]["Timestamp"], dtype=np.float64)
     off, idx, y = _csr_new([db], ts)
@@ -540,6 +645,7 @@ def train_new_gp_EM(db, param_mu_k, ini_hp=None, kern_i=kernel, hp_i=None, sessi
     if hp_i is None:
         _check_kernels(kern_i)
         s = session or default_session()
+        s.ensure_pred(param_mu_k["mean"], param_mu_k["cov"])
         names_k = list(param_mu_k["mean"].keys())
         ts = np.asarray(param_mu_k["mean"][names_k[0]]["Timestamp"], dtype=np.float64)
         many = isinstance(db, (list, tuple))
@@ -560,9 +666,9 @@ def pred_gp_clust(db, timestamps, list_mu, kern, hp, session=None):
     """MC.R:235-274 -> {k: {'Timestamp', 'Mean', 'Var', 'tau_k'}}."""
     _check_kernels(kern)
     s = session or default_session()
+    s.ensure_pred(list_mu["mean"], list_mu["cov"])
     names_k = list(list_mu["mean"].keys())
     ts = np.asarray(list_mu["mean"][names_k[0]]["Timestamp"], dtype=np.float64)
-    tn = np.asarray(db["Timestamp"], dtype=np.float64)
     if timestamps is None:
         raise ValueError("timestamps must be given (and belong to the grid of list_mu)")
     tp = np.asarray(timestamps, dtype=np.float64)
