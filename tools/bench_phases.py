@@ -3,7 +3,7 @@ import json
 import subprocess
 import sys
 
-out = subprocess.run([sys.executable, "bench.py", "--skip-cpu-baseline"] + sys.argv[1:], capture_output=True, text=True)
+out = subprocess.run([sys.executable, "bench.py", "--skip-cpu-baseline", "--no-extras"] + sys.argv[1:], capture_output=True, text=True)
 if out.returncode != 0:
     print("bench failed:", out.stderr[-2000:])
     sys.exit(1)
