@@ -242,6 +242,134 @@ __global__ void __launch_bounds__(kT) indiv_tau_kernel(IndivData dd, int K, cons
   }
 }
 
+// Second version of the responsibilities kernel (round 2). The first one gathers C_k[idx, idx] twice from L2 (once for
+// sum(W o C_k), once for corr2), both triangles, one cluster at a time with a CTA reduction and two barriers per cluster:
+// ncu at C3 (profiles/r02_estep_ncu.txt): 5.6 long-scoreboard stall cycles per issue, 1.14 G L1 sectors per launch.
+// Here every entry of the LOWER triangle of G_k = (m_k m_k' + C_k)[idx, idx] is gathered ONCE, for all clusters back to back
+// (K independent L2 requests in flight per element and thread), reduced on the fly against W, and parked in shared memory;
+// after ONE reduction over the CTA the new responsibilities are known and corr2 = sum_k tau_k G_k comes out of shared memory.
+//   smem: G[K][L] (L = n (n + 1) / 2), mu[K][n], p[n], idx[n], small.   KB = compile-time bound on K (8).
+constexpr int kTauKB = 8;
+size_t tau2_smem_bytes(int nmax, int K) {
+  const size_t L = (size_t)nmax * (nmax + 1) / 2;
+  return sizeof(double) * (K * L + (size_t)K * nmax + nmax + 4 * kTauKB + 2 * kTauKB * (kT / 32) + 8) + sizeof(int) * (size_t)nmax + 16;
+}
+
+__global__ void __launch_bounds__(kT) indiv_tau2_kernel(IndivData dd, int K, const double* __restrict__ mean,
+                                                        const double* __restrict__ cov, int ldN, long long strideC,
+                                                        const double* __restrict__ pi, IndivWork w,
+                                                        double* __restrict__ tau_new, double* __restrict__ logL,
+                                                        int fixed_tau, int nmax) {
+  extern __shared__ __align__(16) double sm[];
+  const int i = blockIdx.x;
+  const int o0 = dd.off[i], n = dd.off[i + 1] - o0;
+  const int L = n * (n + 1) / 2;
+  const size_t Lmax = (size_t)nmax * (nmax + 1) / 2;
+  double* G = sm;                          // [K][Lmax]
+  double* mu = G + (size_t)K * Lmax;       // [K][nmax]
+  double* p = mu + (size_t)K * nmax;       // [nmax]
+  double* lk = p + nmax;                   // [KB] tau_k
+  double* red = lk + 4 * kTauKB;           // [2 KB][kT / 32]
+  int* idx = (int*)(red + 2 * kTauKB * (kT / 32) + 8);
+  const int tid = threadIdx.x;
+  for (int a = tid; a < n; a += kT) {
+    p[a] = w.pvec[o0 + a];
+    idx[a] = dd.gidx[o0 + a];
+  }
+  __syncthreads();
+  for (int e = tid; e < K * n; e += kT) {
+    const int k = e / n, a = e - k * n;
+    mu[(size_t)k * nmax + a] = mean[(size_t)k * ldN + idx[a]];
+  }
+  __syncthreads();
+  const double* Wg = w.Winv + dd.woff[i];
+  double acc[2 * kTauKB];                  // [k]: sum W o G_k (both triangles)   [KB + k]: p' mu_k
+#pragma unroll
+  for (int k = 0; k < 2 * kTauKB; ++k) acc[k] = 0.0;
+  for (int e = tid; e < L; e += kT) {
+    int a = (int)((sqrtf(8.0f * e + 1.0f) - 1.0f) * 0.5f);
+    while ((a + 1) * (a + 2) / 2 <= e) ++a;
+    while (a * (a + 1) / 2 > e) --a;
+    const int b = e - a * (a + 1) / 2;
+    const double wab = ((a == b) ? 1.0 : 2.0) * Wg[(size_t)a * n + b];
+    const size_t gofs = (size_t)idx[a] * ldN + idx[b];
+    double c[kTauKB];
+#pragma unroll
+    for (int k = 0; k < kTauKB; ++k) c[k] = (k < K) ? __ldg(cov + k * strideC + gofs) : 0.0;
+#pragma unroll
+    for (int k = 0; k < kTauKB; ++k) {
+      if (k < K) {
+        const double g = fma(mu[(size_t)k * nmax + a], mu[(size_t)k * nmax + b], c[k]);
+        G[(size_t)k * Lmax + e] = g;
+        acc[k] = fma(wab, g, acc[k]);
+      }
+    }
+  }
+  for (int a = tid; a < n; a += kT) {
+#pragma unroll
+    for (int k = 0; k < kTauKB; ++k)
+      if (k < K) acc[kTauKB + k] = fma(p[a], mu[(size_t)k * nmax + a], acc[kTauKB + k]);
+  }
+  cta_sum_v<2 * kTauKB, kT>(acc, red);     // barriers inside: G is complete for every thread afterwards
+  const double base = (double)n * kLog2Pi + w.logdet[i] + w.yWy[i];
+  if (tid == 0) {
+    double l[kTauKB];
+    double mx = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < kTauKB; ++k) {
+      if (k < K) {
+        // l_ik = -( 0.5 (n log 2pi + log|Psi| + z'Wz) + 0.5 sum(W o C_k) ),  z = y - mu   (CF.R:212-215, 746)
+        l[k] = -0.5 * (base - 2.0 * acc[kTauKB + k] + acc[k]);
+        logL[(size_t)i * K + k] = l[k];
+        mx = fmax(mx, l[k]);
+      }
+    }
+    double den = 0.0;
+#pragma unroll
+    for (int k = 0; k < kTauKB; ++k) {
+      if (k < K) {
+        l[k] = pi[k] * exp(l[k] - mx);      // CF.R:755-757: max over l only, pi multiplied after
+        den += l[k];
+      }
+    }
+    double Fi = 0.5 * base;
+#pragma unroll
+    for (int k = 0; k < kTauKB; ++k) {
+      if (k < K) {
+        // fixed_tau: the caller supplied mu_k_param$tau_i_k (M-step callbacks on an explicit posterior)
+        const double tk = fixed_tau ? tau_new[(size_t)i * K + k] : l[k] / den;
+        lk[k] = tk;
+        if (!fixed_tau) tau_new[(size_t)i * K + k] = tk;
+        Fi += tk * (0.5 * acc[k] - acc[kTauKB + k]);
+      }
+    }
+    w.Fi[i] = Fi;
+  }
+  __syncthreads();
+  // corr1 / corr2 with the NEW tau (they feed the M-step, CF.R:236-245)
+  double tk[kTauKB];
+#pragma unroll
+  for (int k = 0; k < kTauKB; ++k) tk[k] = (k < K) ? lk[k] : 0.0;
+  double* c2 = w.c2 + dd.woff[i];
+  for (int e = tid; e < n * n; e += kT) {
+    const int a = e / n, b = e - a * n;
+    const int hi = a > b ? a : b, lo = a > b ? b : a;
+    const int le = hi * (hi + 1) / 2 + lo;
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < kTauKB; ++k)
+      if (k < K) s = fma(tk[k], G[(size_t)k * Lmax + le], s);
+    c2[e] = s;
+  }
+  for (int a = tid; a < n; a += kT) {
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < kTauKB; ++k)
+      if (k < K) s = fma(tk[k], mu[(size_t)k * nmax + a], s);
+    w.c1[o0 + a] = s;
+  }
+}
+
 // -------------------------------------------------------------------------------------------------
 // M-step objective + gradient kernels (device function in indiv_eval.cuh)
 // -------------------------------------------------------------------------------------------------
@@ -557,6 +685,14 @@ static cudaError_t set_smem(const void* fn, size_t bytes) {
 cudaError_t launch_tau(cudaStream_t s, const IndivData& dd, int M, int nmax, int K, const double* mean,
                        const double* cov, int ldN, long long strideC, const double* pi, const IndivWork& w,
                        double* tau_new, double* logL, int fixed_tau) {
+  static const bool v1 = getenv("MCB_TAU_V1") != nullptr;
+  const size_t sm2 = tau2_smem_bytes(nmax, K);
+  if (!v1 && K <= kTauKB && sm2 <= 200 * 1024) {
+    cudaError_t e2 = set_smem((const void*)indiv_tau2_kernel, sm2);
+    if (e2 != cudaSuccess) return e2;
+    indiv_tau2_kernel<<<M, kT, sm2, s>>>(dd, K, mean, cov, ldN, strideC, pi, w, tau_new, logL, fixed_tau, nmax);
+    return cudaGetLastError();
+  }
   const size_t sm = tau_smem_bytes(nmax, K);
   cudaError_t e = set_smem((const void*)indiv_tau_kernel, sm);
   if (e != cudaSuccess) return e;

@@ -1,9 +1,10 @@
 /* mcb_shim.c — thin .Call marshalling between R and libmagmaclust_b200.so (include/mcb.h).
  *
- * SOURCE ONLY: R and its headers are not installed in the build image nor on the GPU box, so this file has
- * never been compiled or run. It contains no arithmetic: every entry point copies
- * pointers/lengths out of SEXPs, calls one mcb_* function and wraps the result. The executable tests of the
- * same C ABI go through Python ctypes (tests/).
+ * R and its headers are not installed in the build image nor on the GPU box. The file is compiled in CI against a
+ * stand-in for R's C API (tests/r_stub/include: ~100 lines implementing exactly the entry points used here) and
+ * driven by tests/r_stub/drive_shim.c: tests/test_r_shim.py (CPU: every mcbR_* symbol links, error path; GPU: e_step_VEM,
+ * one loop body of training_VEM and the callbacks through the shim against the ctypes path). It contains no arithmetic: every entry
+ * point copies pointers/lengths out of SEXPs, calls one mcb_* function and wraps the result.
  *
  * Build (where R exists):  R CMD SHLIB mcb_shim.c -I../../include -L../../magmaclust_b200/lib -lmagmaclust_b200
  */
@@ -254,3 +255,84 @@ SEXP mcbR_update_tau(SEXP hp, SEXP mean, SEXP cov, SEXP K_, SEXP M_) {
   return tau;
 }
 
+
+/* ---- round 2: the rest of the reference's interface -------------------------------------------------------------------- */
+
+/* Content hash of a column (numeric, integer or character): decides on the R side whether the resident copy of `db` is
+ * still the caller's data (FNV-1a, 64 bit, returned as 16 hex digits; R has no 64-bit integer type). */
+SEXP mcbR_hash(SEXP x) {
+  unsigned long long hsh = 1469598103934665603ULL;
+  const unsigned char* p = NULL;
+  size_t nb = 0;
+  if (TYPEOF(x) == REALSXP) { p = (const unsigned char*)REAL(x); nb = sizeof(double) * (size_t)Rf_xlength(x); }
+  else if (TYPEOF(x) == INTSXP || TYPEOF(x) == LGLSXP) { p = (const unsigned char*)INTEGER(x); nb = sizeof(int) * (size_t)Rf_xlength(x); }
+  if (p) {
+    for (size_t i = 0; i < nb; ++i) { hsh ^= p[i]; hsh *= 1099511628211ULL; }
+  } else if (TYPEOF(x) == STRSXP) {
+    for (R_xlen_t j = 0; j < Rf_xlength(x); ++j) {
+      const char* c = CHAR(STRING_ELT(x, j));
+      for (; *c; ++c) { hsh ^= (unsigned char)*c; hsh *= 1099511628211ULL; }
+      hsh ^= 0xffu; hsh *= 1099511628211ULL;   /* element separator */
+    }
+  } else {
+    Rf_error("mcbR_hash: unsupported column type");
+  }
+  char buf[17];
+  snprintf(buf, sizeof buf, "%016llx", hsh);
+  return Rf_mkString(buf);
+}
+
+/* mu_k_param / list_mu_param given explicitly (CF.R:218, 280, 327, 631): mean N x K, cov N x N x K, tau K x M or NULL */
+SEXP mcbR_set_posterior(SEXP hp, SEXP mean, SEXP cov, SEXP tau) {
+  mcb_handle* h = get_handle(hp);
+  check(h, mcb_set_posterior(h, REAL(mean), REAL(cov), Rf_isNull(tau) ? NULL : REAL(tau)), 0);
+  return R_NilValue;
+}
+
+/* list_mu of pred_gp_clust / mean_k, cov_k of update_tau_star_k_EM given explicitly: mean T x K, cov T x T x K */
+SEXP mcbR_set_pred_posterior(SEXP hp, SEXP timestamps, SEXP mean, SEXP cov, SEXP pi_k) {
+  mcb_handle* h = get_handle(hp);
+  int T = Rf_length(timestamps), K = Rf_length(mean) / (T > 0 ? T : 1);
+  check(h, mcb_set_pred_posterior(h, K, T, REAL(timestamps), REAL(mean), REAL(cov), Rf_isNull(pi_k) ? NULL : REAL(pi_k)), 0);
+  return R_NilValue;
+}
+
+/* logL_GP_mod / gr_GP_mod (Z = 1) and the common_hp_k forms on explicit arguments: t[n], y n x Z, mean (Z or n x Z values),
+ * new_cov n x n x Z, theta (2 or 3), pen_diag; returns c(f, g...) */
+SEXP mcbR_gp_mod(SEXP hp, SEXP t, SEXP y, SEXP mean, SEXP new_cov, SEXP theta, SEXP pen_diag, SEXP want_grad) {
+  mcb_handle* h = get_handle(hp);
+  int n = Rf_length(t), Z = Rf_length(y) / (n > 0 ? n : 1), nhp = Rf_length(theta);
+  SEXP out = PROTECT(Rf_allocVector(REALSXP, 1 + nhp));
+  double* o = REAL(out);
+  check(h, mcb_gp_mod(h, n, Z, REAL(t), REAL(y), REAL(mean), Rf_length(mean), REAL(new_cov), REAL(theta), nhp,
+                      Rf_asReal(pen_diag), o, Rf_asLogical(want_grad) ? o + 1 : NULL), 1);
+  UNPROTECT(1);
+  return out;
+}
+
+/* hp = new_hp of the last M-step (training_VEM returns it even when it was not accepted, MC.R:95) */
+SEXP mcbR_get_new_hp(SEXP hp, SEXP K_, SEXP M_) {
+  mcb_handle* h = get_handle(hp);
+  int K = Rf_asInteger(K_), M = Rf_asInteger(M_);
+  SEXP tk = PROTECT(Rf_allocMatrix(REALSXP, 3, K));
+  SEXP ti = PROTECT(Rf_allocMatrix(REALSXP, 3, M));
+  SEXP pi = PROTECT(Rf_allocVector(REALSXP, K));
+  check(h, mcb_get_new_hp(h, REAL(tk), REAL(ti), REAL(pi)), 3);
+  SEXP out = PROTECT(Rf_allocVector(VECSXP, 3));
+  SET_VECTOR_ELT(out, 0, tk);
+  SET_VECTOR_ELT(out, 1, ti);
+  SET_VECTOR_ELT(out, 2, pi);
+  UNPROTECT(4);
+  return out;
+}
+
+/* terms of BIC (CF.R:354-432) at the resident hp / hyper-posterior */
+SEXP mcbR_bic_terms(SEXP hp) {
+  mcb_handle* h = get_handle(hp);
+  SEXP out = PROTECT(Rf_allocVector(REALSXP, 3));
+  check(h, mcb_bic_terms(h, REAL(out)), 1);
+  UNPROTECT(1);
+  return out;
+}
+
+SEXP mcbR_version(void) { return Rf_ScalarInteger(mcb_version()); }

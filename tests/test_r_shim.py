@@ -1,0 +1,110 @@
+"""The R `.Call` shim (r/src/mcb_shim.c) compiled against a stand-in for R's C API (tests/r_stub/include) and driven like R
+would drive it (tests/r_stub/drive_shim.c). R itself is not installed in the image."""
+import os
+import re
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "build", "r_stub", "drive_shim")
+
+
+@pytest.fixture(scope="module")
+def drive():
+    subprocess.run(["make", "-C", os.path.join(ROOT, "tests", "r_stub")], check=True, capture_output=True)
+    assert os.path.exists(EXE)
+    return EXE
+
+
+def test_shim_compiles_links_and_reports_errors_through_rf_error(drive):
+    """CPU: the shim links against every mcb_* symbol it uses; without a CUDA device mcbR_create raises through Rf_error with
+    the library's message (nothing is left on the PROTECT stack)"""
+    out = subprocess.run([drive, "abi"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "abi ok" in out.stdout
+
+
+def test_every_call_of_the_r_wrappers_has_a_shim_entry_point():
+    """each .Call('mcbR_*') in r/R/magmaclust_b200.R names a function defined in r/src/mcb_shim.c with the same arity"""
+    rsrc = open(os.path.join(ROOT, "r", "R", "magmaclust_b200.R")).read()
+    csrc = open(os.path.join(ROOT, "r", "src", "mcb_shim.c")).read()
+    defs = {m.group(1): (0 if m.group(2).strip() in ("", "void") else m.group(2).count(",") + 1)
+            for m in re.finditer(r"^SEXP (mcbR_\w+)\(([^)]*)\)\s*\{", csrc, re.M)}
+    calls = re.findall(r"\.Call\('(mcbR_\w+)'", rsrc)
+    assert len(calls) >= 20
+    for name in set(calls):
+        assert name in defs, name
+    # arity: count the top-level arguments of each .Call
+    for m in re.finditer(r"\.Call\('(mcbR_\w+)'", rsrc):
+        i, depth, n, seen = m.end(), 1, 0, False
+        while depth > 0:
+            c = rsrc[i]
+            if c in "([{":
+                depth += 1
+            elif c in ")]}":
+                depth -= 1
+            elif c == "," and depth == 1:
+                n += 1
+            elif not c.isspace():
+                seen = True
+            i += 1
+        assert n == defs[m.group(1)], (m.group(1), n, defs[m.group(1)])
+
+
+@pytest.mark.gpu
+def test_e_step_and_loop_body_through_the_shim_match_the_ctypes_path(drive, tmp_path):
+    from helpers import RTOL_LL, RTOL_POST, rel_err, small_problem
+    from magmaclust_b200 import magma
+    from magmaclust_b200.engine import Engine
+    from oracle import magma_oracle as O
+    db, hp, tau, m_k = small_problem(M=14, K=3, n=(7, 15), n_grid=45, seed=21, common_hp_i=True)
+    names = list(m_k.keys())
+    c = magma.Canon(db)
+    M, N, K, P = c.M, c.N, len(names), c.y.shape[0]
+    theta_k = np.array([hp["theta_k"][k] for k in names])
+    theta_i = np.array([hp["theta_i"][i] for i in c.ids])
+    tau_a = np.array([[tau[k][i] for k in names] for i in c.ids])
+    mk = np.array([m_k[k] for k in names])
+    pin, pout = str(tmp_path / "in.bin"), str(tmp_path / "out.bin")
+    with open(pin, "wb") as f:
+        f.write(struct.pack("4i", M, N, K, P))
+        for a, dt in ((c.offsets, np.int32), (c.grid_idx, np.int32), (c.y, np.float64), (c.grid, np.float64),
+                      (theta_k, np.float64), (theta_i, np.float64), (hp["pi_k"], np.float64), (mk, np.float64),
+                      (tau_a, np.float64)):
+            f.write(np.ascontiguousarray(a, dtype=dt).tobytes())
+    out = subprocess.run([drive, "estep", pin, pout], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    r = np.fromfile(pout)
+    o = 0
+    mean = r[o:o + K * N].reshape(K, N); o += K * N
+    cov = r[o:o + K * N * N].reshape(K, N, N); o += K * N * N
+    tau_s = r[o:o + M * K].reshape(M, K); o += M * K
+    ei, em, it = r[o:o + 4], r[o + 4:o + 8], r[o + 8:o + 11]; o += 11
+    vmean = r[o:o + K * N].reshape(K, N); o += K * N
+    new_tk = r[o:o + 3 * K].reshape(K, 3)
+    ref = O.e_step_VEM(db, m_k, O.kernel_mu, O.kernel, hp, tau)
+    for ck, k in enumerate(names):
+        assert rel_err(mean[ck], ref["mean"][k]["Output"]) < RTOL_POST
+        assert rel_err(cov[ck], ref["cov"][k].m) < RTOL_POST
+    assert np.abs(tau_s - O.tau_to_array(ref["tau_i_k"])).max() < RTOL_LL
+    th3 = np.array([0.9, 0.7, 0.3])
+    fr = O.logL_clust_multi_GP_common_hp_i(th3, db, ref, O.kernel)
+    gr = O.gr_clust_multi_GP_common_hp_i(th3, db, ref, O.kernel)
+    assert abs(ei[0] - fr) <= RTOL_LL * abs(fr) and np.abs(ei[1:] - gr).max() <= RTOL_LL * max(1.0, np.abs(gr).max())
+    fk = O.logL_GP_mod_common_hp_k(th3, ref["mean"], m_k, O.kernel_mu, ref["cov"])
+    gk = O.gr_GP_mod_common_hp_k(th3, ref["mean"], m_k, O.kernel_mu, ref["cov"])
+    assert abs(em[0] - fk) <= RTOL_LL * abs(fk) and np.abs(em[1:] - gk).max() <= RTOL_LL * max(1.0, np.abs(gk).max())
+    # the loop body through the shim == the same call through ctypes
+    e = Engine(0)
+    try:
+        e.set_data(c.offsets, c.grid_idx, c.y, c.grid)
+        e.set_state(theta_k, theta_i, hp["pi_k"], mk, tau_a)
+        got = e.vem_iteration(True, True)
+        assert abs(got[0] - it[0]) <= 1e-9 * abs(got[0]) and bool(it[2]) == got[2]
+        assert rel_err(vmean, e.get_mean()) < 1e-10
+        assert np.abs(new_tk - e.get_new_hp()[0]).max() < 1e-6
+    finally:
+        e.close()
