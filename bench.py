@@ -72,6 +72,8 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=200, help="individuals in the CPU baseline sample")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--individuals", type=int, default=0, help="override the individuals per GPU of the workload")
+    ap.add_argument("--data", default="", help="directory written by data/gen.py for --workload: read the dataset from its files "
+                    "(the bytes baseline/run_reference.R reads) instead of generating it in memory; N = 1 only")
     return ap.parse_args()
 
 
@@ -141,9 +143,18 @@ class Clocks:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+DATA_DIR = ""
+
+
 def workload_data(name, nranks, individuals=0, strong=False):
     """the synthetic dataset of a BASELINE config. Weak scaling: M individuals PER rank; strong: M in total."""
     from magmaclust_b200 import synth
+    if DATA_DIR and nranks == 1 and not individuals and not strong:
+        from data import gen
+        ds, c = gen.load(DATA_DIR)
+        if c.get("name") != name:
+            raise SystemExit(f"--data {DATA_DIR} holds {c.get('name')}, not {name}")
+        return ds, c
     c = dict(synth.CONFIGS[name])
     if individuals:
         c["M"] = individuals
@@ -688,4 +699,6 @@ def run_ours(args):
 
 if __name__ == "__main__":
     a = parse()
+    if a.data:
+        globals()["DATA_DIR"] = a.data
     sys.exit(run_reference(a) if a.impl == "reference" else run_ours(a))

@@ -190,8 +190,10 @@ SEXP mcbR_predict(SEXP hp, SEXP offsets, SEXP obs_idx, SEXP y, SEXP theta_new, S
   SEXP tau = PROTECT(Rf_allocMatrix(REALSXP, K, B));
   SEXP mean = PROTECT(Rf_alloc3DArray(REALSXP, Tp, K, B));
   SEXP var = PROTECT(Rf_alloc3DArray(REALSXP, Tp, K, B));
+  /* no targets (update_tau_star_k_EM, CF.R:764-786): responsibilities only */
   check(h, mcb_predict(h, B, INTEGER(offsets), INTEGER(obs_idx), REAL(y), REAL(theta_new),
-                       Rf_isNull(pi_k) ? NULL : REAL(pi_k), Tp, INTEGER(pred_idx), REAL(tau), REAL(mean), REAL(var)), 3);
+                       Rf_isNull(pi_k) ? NULL : REAL(pi_k), Tp, INTEGER(pred_idx), REAL(tau), Tp > 0 ? REAL(mean) : NULL,
+                       Tp > 0 ? REAL(var) : NULL), 3);
   SEXP out = PROTECT(Rf_allocVector(VECSXP, 3));
   SET_VECTOR_ELT(out, 0, tau);
   SET_VECTOR_ELT(out, 1, mean);

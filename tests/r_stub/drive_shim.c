@@ -6,7 +6,9 @@
  * in.bin : int32 M, N, K, P | int32 offsets[M+1] | int32 grid_idx[P] | f64 y[P] | f64 grid[N] | f64 theta_k[K][3] |
  *          f64 theta_i[M][3] | f64 pi[K] | f64 m_k[K] | f64 tau[M][K]
  * out.bin: f64 mean[K][N] | cov[K][N][N] | tau[M][K] | eval_indiv_common (4) | eval_mean common (4) | vem stats (3) |
- *          vem mean[K][N] | new theta_k[K][3]
+ *          vem mean[K][N] | new theta_k[K][3] | elbo (2) | bic terms (3) | posterior_mu_k mean[K][N] on the training grid |
+ *          tau_star[K] of individual 0 (no targets) | pred mean[K][N] | pred var[K][N] | gp_mod (4) on cluster 0 of the E-step |
+ *          the same prediction after set_pred_posterior with the arrays just read: tau[K] | free-hp EM: theta[3], tau[K]
  */
 #include <R.h>
 #include <Rinternals.h>
@@ -23,6 +25,12 @@ SEXP mcbR_eval_mean(SEXP, SEXP, SEXP, SEXP, SEXP);
 SEXP mcbR_set_state(SEXP, SEXP, SEXP, SEXP, SEXP, SEXP);
 SEXP mcbR_vem_iteration_host(SEXP, SEXP, SEXP, SEXP, SEXP, SEXP);
 SEXP mcbR_get_new_hp(SEXP, SEXP, SEXP);
+SEXP mcbR_elbo(SEXP, SEXP, SEXP), mcbR_bic_terms(SEXP);
+SEXP mcbR_posterior_mu_k(SEXP, SEXP, SEXP, SEXP);
+SEXP mcbR_predict(SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP);
+SEXP mcbR_gp_mod(SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP);
+SEXP mcbR_set_pred_posterior(SEXP, SEXP, SEXP, SEXP, SEXP);
+SEXP mcbR_train_new_indiv(SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP);
 
 static SEXP reals(const double* p, long n) { SEXP s = Rf_allocVector(REALSXP, n); memcpy(REAL(s), p, sizeof(double) * n); return s; }
 static SEXP ints(const int* p, long n) { SEXP s = Rf_allocVector(INTSXP, n); memcpy(INTEGER(s), p, sizeof(int) * n); return s; }
@@ -95,6 +103,35 @@ static int estep(const char* in, const char* outp) {
   fwrite(REAL(VECTOR_ELT(it, 1)), sizeof(double), (size_t)K * N, o);
   SEXP nh = mcbR_get_new_hp(h, Rf_ScalarInteger(K), Rf_ScalarInteger(M));
   fwrite(REAL(VECTOR_ELT(nh, 0)), sizeof(double), 3 * (size_t)K, o);
+  /* logL_monitoring_VEM and BIC terms at the resident state (CF.R:327-352, 354-432) */
+  fwrite(REAL(mcbR_elbo(h, R_NilValue, R_NilValue)), sizeof(double), 2, o);
+  fwrite(REAL(mcbR_bic_terms(h)), sizeof(double), 3, o);
+  /* posterior_mu_k -> update_tau_star_k_EM -> pred_gp_clust for individual 0 as the new individual (MC.R:196-274) */
+  SEXP pm = mcbR_posterior_mu_k(h, reals(grid, N), R_NilValue, Rf_ScalarInteger(K));
+  fwrite(REAL(VECTOR_ELT(pm, 0)), sizeof(double), (size_t)K * N, o);
+  const int n0 = off[1];
+  int o2[2] = {0, n0};
+  int* all = malloc(sizeof(int) * N);
+  for (int j = 0; j < N; ++j) all[j] = j;
+  SEXP t0 = mcbR_predict(h, ints(o2, 2), ints(gi, n0), reals(y, n0), reals(th3, 3), R_NilValue, ints(all, 0), Rf_ScalarInteger(K));
+  fwrite(REAL(VECTOR_ELT(t0, 0)), sizeof(double), K, o);
+  SEXP p1 = mcbR_predict(h, ints(o2, 2), ints(gi, n0), reals(y, n0), reals(th3, 3), R_NilValue, ints(all, N), Rf_ScalarInteger(K));
+  /* Tp x K x B column-major = [B][K][Tp] */
+  fwrite(REAL(VECTOR_ELT(p1, 1)), sizeof(double), (size_t)K * N, o);
+  fwrite(REAL(VECTOR_ELT(p1, 2)), sizeof(double), (size_t)K * N, o);
+  /* logL_GP_mod / gr_GP_mod on explicit arguments: mean process 0 of the E-step, prior mean m_k[0] */
+  SEXP gm = mcbR_gp_mod(h, reals(grid, N), reals(REAL(VECTOR_ELT(res, 0)), N), reals(mk, 1), reals(REAL(VECTOR_ELT(res, 1)), (long)N * N),
+                        reals(th3, 3), Rf_ScalarReal(0.0), Rf_ScalarLogical(1));
+  fwrite(REAL(gm), sizeof(double), 4, o);
+  /* a list_mu that does not come from this handle's posterior_mu_k (MC.R:305): upload, then the same responsibilities */
+  mcbR_set_pred_posterior(h, reals(grid, N), VECTOR_ELT(pm, 0), VECTOR_ELT(pm, 1), reals(pi, K));
+  SEXP t1 = mcbR_predict(h, ints(o2, 2), ints(gi, n0), reals(y, n0), reals(th3, 3), reals(pi, K), ints(all, 0), Rf_ScalarInteger(K));
+  fwrite(REAL(VECTOR_ELT(t1, 0)), sizeof(double), K, o);
+  /* train_new_gp_EM with hp_i = NULL (MC.R:142-186) */
+  SEXP tn = mcbR_train_new_indiv(h, ints(o2, 2), ints(gi, n0), reals(y, n0), reals(th3, 3), reals(pi, K), Rf_ScalarInteger(25));
+  fwrite(REAL(VECTOR_ELT(tn, 0)), sizeof(double), 3, o);
+  fwrite(REAL(VECTOR_ELT(tn, 1)), sizeof(double), K, o);
+  free(all);
   fclose(o);
   if (h->finalizer) h->finalizer(h);
   if (mcb_stub_protect_depth != 0) return 15;

@@ -84,7 +84,16 @@ def test_e_step_and_loop_body_through_the_shim_match_the_ctypes_path(drive, tmp_
     tau_s = r[o:o + M * K].reshape(M, K); o += M * K
     ei, em, it = r[o:o + 4], r[o + 4:o + 8], r[o + 8:o + 11]; o += 11
     vmean = r[o:o + K * N].reshape(K, N); o += K * N
-    new_tk = r[o:o + 3 * K].reshape(K, 3)
+    new_tk = r[o:o + 3 * K].reshape(K, 3); o += 3 * K
+    elbo2, bic3 = r[o:o + 2], r[o + 2:o + 5]; o += 5
+    pmean = r[o:o + K * N].reshape(K, N); o += K * N
+    tstar = r[o:o + K]; o += K
+    prmean = r[o:o + K * N].reshape(K, N); o += K * N
+    prvar = r[o:o + K * N].reshape(K, N); o += K * N
+    gm = r[o:o + 4]; o += 4
+    tstar2 = r[o:o + K]; o += K
+    em_theta, em_tau = r[o:o + 3], r[o + 3:o + 3 + K]; o += 3 + K
+    assert o == r.shape[0]
     ref = O.e_step_VEM(db, m_k, O.kernel_mu, O.kernel, hp, tau)
     for ck, k in enumerate(names):
         assert rel_err(mean[ck], ref["mean"][k]["Output"]) < RTOL_POST
@@ -106,5 +115,21 @@ def test_e_step_and_loop_body_through_the_shim_match_the_ctypes_path(drive, tmp_
         assert abs(got[0] - it[0]) <= 1e-9 * abs(got[0]) and bool(it[2]) == got[2]
         assert rel_err(vmean, e.get_mean()) < 1e-10
         assert np.abs(new_tk - e.get_new_hp()[0]).max() < 1e-6
+        # the rest of the interface through the shim == the same C ABI through ctypes, from the same resident state
+        assert np.allclose(elbo2, e.elbo(), rtol=1e-12) and np.allclose(bic3, e.bic_terms(), rtol=1e-12)
+        pm, pc = e.posterior_mu_k(c.grid)
+        assert rel_err(pmean, pm) < 1e-12
+        n0 = int(c.offsets[1])
+        off2, gi0, y0 = np.array([0, n0], np.int32), c.grid_idx[:n0], c.y[:n0]
+        tau_c, mean_c, var_c = e.predict(off2, gi0, y0, th3, pred_idx=np.arange(N, dtype=np.int32))
+        assert np.abs(tstar - tau_c[0]).max() < 1e-12 and np.abs(tstar2 - e.predict(off2, gi0, y0, th3, pi_k=hp["pi_k"])[0][0]).max() < 1e-12
+        assert rel_err(prmean, mean_c[0]) < 1e-12 and rel_err(prvar, var_c[0]) < 1e-12
+        # logL_GP_mod / gr_GP_mod on explicit arguments against the oracle (CF.R:194-216, 448-475)
+        k0 = names[0]
+        f0 = O.logL_GP_mod(th3, ref["mean"][k0], m_k[k0], O.kernel_mu, ref["cov"][k0].m)
+        g0 = O.gr_GP_mod(th3, ref["mean"][k0], m_k[k0], O.kernel_mu, ref["cov"][k0].m)
+        assert abs(gm[0] - f0) <= RTOL_LL * abs(f0) and np.abs(gm[1:] - g0).max() <= RTOL_LL * max(1.0, np.abs(g0).max())
+        th_c, tau_e, _ = e.train_new_indiv(off2, gi0, y0, th3, pi_k=hp["pi_k"])
+        assert np.abs(em_theta - th_c[0]).max() < 1e-9 and np.abs(em_tau - tau_e[0]).max() < 1e-9
     finally:
         e.close()
