@@ -167,7 +167,7 @@ int mcb_set_pred_posterior(mcb_handle* h, int K, int T, const double* timestamps
  * new individuals in CSR (offsets[B+1], obs_idx = positions in the prediction grid, y), shared theta_new[3]
  * (train_new_gp_EM fixed-hp branch, MC.R:187-191), targets pred_idx[Tp] = positions in the prediction grid.
  * pi_k[K]: mixing proportions (NULL: mean_i tau_ik of the tau frozen in mcb_posterior_mu_k, MC.R:141).
- * out_mean/out_var may both be NULL (tau only). At most 64 observations per new individual. */
+ * out_mean/out_var may both be NULL (tau only). Any number of observations per new individual (above 64, or above the shared-memory budget, a global-memory version of the kernel runs). */
 int mcb_predict(mcb_handle* h, int B, const int* offsets, const int* obs_idx, const double* y,
                 const double* theta_new, const double* pi_k, int Tp, const int* pred_idx, double* out_tau,
                 double* out_mean, double* out_var);
@@ -197,6 +197,17 @@ int mcb_train_new_indiv(mcb_handle* h, int B, const int* offsets, const int* obs
                         double* out_theta, double* out_tau, int* out_loops);
 int mcb_new_indiv_em(int B, int K, const double* theta0, int theta0_per_indiv, const double* pi_k, int n_loop_max,
                      mcb_logl_fn fn, void* ctx, double* out_theta, double* out_tau, int* out_loops);
+
+/* ---- initialisation -------------------------------------------------------------------------------------- */
+/* ini_kmeans (MAGMAclust.R:562-598): k-means of the feature rows feat[M][D] (one per individual: the outputs on a common
+ * grid, or (min, mean, max), MAGMAclust.R:569-580) from `nstart` starts, start s taking the rows start_rows[s][0..K) as
+ * initial centres (kmeans(centers = k) draws k distinct rows). Lloyd iterations (at most max_iter assignment passes) to a
+ * fixed point, all starts side by side on the device; the start with the smallest total within-cluster sum of squares wins
+ * (the first one on ties). out_labels[M] in [0, K); out_centers[K][D], out_cost, out_iters may be NULL. Every floating-point
+ * operation has a prescribed order (csrc/kmeans.cu), so the result is reproducible bit for bit (stats::kmeans itself is
+ * Hartigan-Wong on R's RNG: unpinned). Needs no training set on the handle. */
+int mcb_kmeans(mcb_handle* h, int M, int D, const double* feat, int K, int nstart, const int* start_rows, int max_iter,
+               int* out_labels, double* out_centers, double* out_cost, int* out_iters);
 
 /* ---- stand-alone building blocks (the vector branches the reference also calls directly, e.g. MC.R:261-264) ------------ */
 /* kern_to_cov(x, kern, theta, sigma), vector branch CF.R:68-86: SE covariance of the SORTED timestamps x[n] (the reference
@@ -229,6 +240,11 @@ int mcb_last_timings(mcb_handle* h, float ms[8], long long* launches);
  * theta_k optimiser(s), out[2], out[3] the iteration counts, out[4] total individual objective+gradient
  * evaluations on this rank, out[5] number of local individuals. */
 int mcb_last_mstep_stats(mcb_handle* h, long long out[6]);
+/* Per-individual outcome of the last M-step with individual-specific theta_i (one optimisation per individual, CF.R:653-659):
+ * nfev[M] objective + gradient evaluations, niter[M] iterations, status[M] = 1 converged (optim: 0), 2 iteration limit
+ * (optim: 1), 3 abnormal line search (optim: 52), 4 zero gradient, 5 objective not finite at the start point (the start
+ * point is returned). Any pointer may be NULL. */
+int mcb_last_mstep_indiv(mcb_handle* h, int* nfev, int* niter, int* status);
 /* Page-lock / release a host buffer (cudaHostRegister) so that the copies of the host-buffer entry points run
  * from pinned memory. */
 int mcb_pin_host(void* ptr, size_t bytes);

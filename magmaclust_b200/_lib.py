@@ -67,6 +67,8 @@ SIGNATURES = {
                                       c_double_p, c_double_p, c_int_p]),
     "mcb_new_indiv_em": (C.c_int, [C.c_int, C.c_int, c_double_p, C.c_int, c_double_p, C.c_int, LOGL_FN, C.c_void_p,
                                    c_double_p, c_double_p, c_int_p]),
+    "mcb_kmeans": (C.c_int, [H, C.c_int, C.c_int, c_double_p, C.c_int, C.c_int, c_int_p, C.c_int, c_int_p, c_double_p,
+                             c_double_p, c_int_p]),
     "mcb_kern_to_cov": (C.c_int, [H, C.c_int, c_double_p, c_double_p, C.c_double, c_double_p]),
     "mcb_kern_to_inv": (C.c_int, [H, C.c_int, c_double_p, c_double_p, C.c_double, c_double_p, c_double_p]),
     "mcb_dmvnorm": (C.c_int, [H, C.c_int, c_double_p, c_double_p, c_double_p, C.c_int, c_double_p]),
@@ -74,6 +76,7 @@ SIGNATURES = {
                              C.c_int, C.c_double, c_double_p, c_double_p]),
     "mcb_last_timings": (C.c_int, [H, c_float_p, c_ll_p]),
     "mcb_last_mstep_stats": (C.c_int, [H, c_ll_p]),
+    "mcb_last_mstep_indiv": (C.c_int, [H, c_int_p, c_int_p, c_int_p]),
     "mcb_pin_host": (C.c_int, [C.c_void_p, C.c_size_t]),
     "mcb_unpin_host": (C.c_int, [C.c_void_p]),
     "mcb_timer_start": (C.c_int, [H]),

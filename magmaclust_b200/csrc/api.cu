@@ -156,11 +156,21 @@ extern "C" int mcb_set_data(mcb_handle* h, int M, int N, long long P, const int*
   for (int j = 1; j < N; ++j) H_CHECK(grid[j] > grid[j - 1], MCB_EINVAL, "mcb_set_data: grid must be sorted and unique");
   std::vector<long long> woff(M + 1, 0);
   std::vector<double> t((size_t)P);
-  int nmax = 0;
+  int nmax = 0, nmax_all = 0;
+  std::vector<int> big_ids;
+  std::vector<long long> big_wsoff(1, 0);
   for (int i = 0; i < M; ++i) {
     const int n = offsets[i + 1] - offsets[i];
     H_CHECK(n >= 1, MCB_EINVAL, "mcb_set_data: empty individual");
-    nmax = std::max(nmax, n);
+    nmax_all = std::max(nmax_all, n);
+    if (n <= mcb::kSmallMax) {
+      nmax = std::max(nmax, n);
+    } else {
+      // no size limit in the reference (CF.R:153-190): above the tile buckets of the shared-memory kernels an individual
+      // takes the global-memory kernels of indiv_big.cu
+      big_ids.push_back(i);
+      big_wsoff.push_back(big_wsoff.back() + (long long)(n + 2) * (n + 2) + (long long)n * n);
+    }
     woff[i + 1] = woff[i] + (long long)n * n;
     for (int a = offsets[i]; a < offsets[i + 1]; ++a) {
       H_CHECK(grid_idx[a] >= 0 && grid_idx[a] < N, MCB_EINVAL, "mcb_set_data: grid_idx out of range");
@@ -169,14 +179,23 @@ extern "C" int mcb_set_data(mcb_handle* h, int M, int N, long long P, const int*
       t[a] = grid[grid_idx[a]];
     }
   }
-  H_CHECK(eval_smem_bytes(nmax) <= 227 * 1024, MCB_EINVAL,
-          "mcb_set_data: an individual has too many observations for the shared-memory path (n_i <= 80)");
+  if (nmax == 0) nmax = 1;   // every individual is on the global-memory path: the shared-memory kernels are not launched
+  H_CHECK(eval_smem_bytes(nmax) <= 227 * 1024, MCB_EINVAL, "mcb_set_data: shared-memory budget of the evaluators exceeded");
   H_CUDA(cudaSetDevice(h->device));
   // a dataset of another shape forces the state buffers to be re-sized and the captured graphs (which hold M, N, P and
   // the buffer addresses) to be rebuilt; re-uploading a dataset of the SAME shape (the host-buffer loop) keeps both
-  const bool same_shape = M == h->M && N == h->N && P == h->P && nmax == h->nmax && M_total == h->M_total;
+  const bool same_shape = M == h->M && N == h->N && P == h->P && nmax == h->nmax && M_total == h->M_total &&
+                          big_ids == h->h_big_ids && nmax_all == h->nmax_all;
   if (!same_shape) h->K = 0;
   h->M = M; h->N = N; h->ld = (N + 15) & ~15; h->P = P; h->nmax = nmax; h->M_total = M_total; h->W2 = woff[M];
+  h->nmax_all = nmax_all; h->nbig = (int)big_ids.size(); h->h_big_ids = big_ids;
+  if (h->nbig > 0) {
+    const size_t nb = big_ids.size();
+    H_CUDA(h->big_ids.ensure(nb)); H_CUDA(h->big_wsoff.ensure(nb + 1)); H_CUDA(h->big_ws.ensure((size_t)big_wsoff.back()));
+    H_CUDA(h->big_active.ensure(nb)); H_CUDA(h->big_theta.ensure(3 * nb)); H_CUDA(h->big_f.ensure(nb)); H_CUDA(h->big_g.ensure(3 * nb));
+    H_CUDA(cudaMemcpyAsync(h->big_ids.p, big_ids.data(), sizeof(int) * nb, cudaMemcpyHostToDevice, h->st));
+    H_CUDA(cudaMemcpyAsync(h->big_wsoff.p, big_wsoff.data(), sizeof(long long) * (nb + 1), cudaMemcpyHostToDevice, h->st));
+  }
   H_CUDA(h->off.ensure(M + 1)); H_CUDA(h->gidx.ensure(P)); H_CUDA(h->woff.ensure(M + 1));
   H_CUDA(h->t.ensure(P)); H_CUDA(h->y.ensure(P)); H_CUDA(h->grid.ensure(N));
   H_CUDA(cudaMemcpyAsync(h->off.p, offsets, sizeof(int) * (M + 1), cudaMemcpyHostToDevice, h->st));
@@ -1070,6 +1089,48 @@ static int compute_pen_diag(mcb_handle* h, double* pen_diag) {
   return MCB_OK;
 }
 
+// The per-individual optimiser loop of m_step_VEM (CF.R:653-659) for the individuals of the global-memory path: the same
+// L-BFGS state machine as the in-kernel one (lbfgs.h), advanced in lock step on the host, one batched objective + gradient
+// launch over the still-active individuals per round (big_eval_kernel, indexed by position in big_ids).
+static int mstep_big_individuals(mcb_handle* h) {
+  const int nb = h->nbig;
+  std::vector<Lbfgs> opt(nb);
+  std::vector<int> st(nb, LB_EVAL), active(nb, 1);
+  std::vector<double> th0(3 * (size_t)h->M), x(3 * (size_t)nb), f(nb), g(3 * (size_t)nb);
+  H_CUDA(sync_copy(h, th0.data(), h->theta_i.p, sizeof(double) * 3 * h->M, cudaMemcpyDeviceToHost));
+  for (int j = 0; j < nb; ++j) lb_init(opt[j], 3, &th0[3 * (size_t)h->h_big_ids[j]], 100);
+  int left = nb;
+  while (left > 0) {
+    for (int j = 0; j < nb; ++j) for (int q = 0; q < 3; ++q) x[3 * (size_t)j + q] = opt[j].x[q];
+    H_CUDA(cudaMemcpyAsync(h->big_theta.p, x.data(), sizeof(double) * 3 * nb, cudaMemcpyHostToDevice, h->st));
+    H_CUDA(cudaMemcpyAsync(h->big_active.p, active.data(), sizeof(int) * nb, cudaMemcpyHostToDevice, h->st));
+    H_CUDA(cudaMemsetAsync(h->info.p, 0, sizeof(int), h->st));
+    H_CUDA(launch_big_eval(h->st, h->idata(), h->iwork(), h->big_theta.p, 3, 1, h->big_active.p, 1, h->big_f.p, h->big_g.p,
+                           nullptr, h->info.p));
+    ++h->launches;
+    H_CUDA(cudaMemcpyAsync(f.data(), h->big_f.p, sizeof(double) * nb, cudaMemcpyDeviceToHost, h->st));
+    H_CUDA(cudaMemcpyAsync(g.data(), h->big_g.p, sizeof(double) * 3 * nb, cudaMemcpyDeviceToHost, h->st));
+    H_CUDA(cudaStreamSynchronize(h->st));
+    for (int j = 0; j < nb; ++j) {
+      if (!active[j]) continue;
+      // a trial point where Psi_i is not positive definite (f = NaN) is a failed line-search step, as in the kernel
+      st[j] = lb_advance(opt[j], f[j], &g[3 * (size_t)j]);
+      if (st[j] != LB_EVAL) { active[j] = 0; --left; }
+    }
+  }
+  H_CUDA(cudaMemsetAsync(h->info.p, 0, sizeof(int), h->st));
+  for (int j = 0; j < nb; ++j) {
+    const int i = h->h_big_ids[j];
+    const int iv[3] = {opt[j].nfev, opt[j].iter, st[j]};
+    H_CUDA(cudaMemcpyAsync(h->theta_i_new.p + 3 * (size_t)i, opt[j].x, sizeof(double) * 3, cudaMemcpyHostToDevice, h->st));
+    H_CUDA(cudaMemcpyAsync(h->nfev_i.p + i, iv, sizeof(int), cudaMemcpyHostToDevice, h->st));
+    H_CUDA(cudaMemcpyAsync(h->niter_i.p + i, iv + 1, sizeof(int), cudaMemcpyHostToDevice, h->st));
+    H_CUDA(cudaMemcpyAsync(h->status_i.p + i, iv + 2, sizeof(int), cudaMemcpyHostToDevice, h->st));
+    H_CUDA(cudaStreamSynchronize(h->st));   // pageable sources on the stack
+  }
+  return MCB_OK;
+}
+
 // ---- M-step ------------------------------------------------------------------------------------------
 static int m_step_impl(mcb_handle* h, int common_hp_k, int common_hp_i, int* stats) {
   const int M = h->M, K = h->K;
@@ -1079,7 +1140,8 @@ static int m_step_impl(mcb_handle* h, int common_hp_k, int common_hp_i, int* sta
   // With individual-specific theta_i and a shared theta_k the two optimisations are independent (pen_diag only
   // replaces the third entry of theta_k afterwards, CF.R:666-668): run them concurrently.
   static const bool no_overlap = getenv("MCB_NO_OVERLAP") != nullptr;
-  const bool overlap = !no_overlap && !common_hp_i && common_hp_k && spd_inverse_slab_ok(h->N, h->ld);
+  // (individuals on the global-memory path are optimised by a host loop after the kernel: no overlap then)
+  const bool overlap = !no_overlap && !common_hp_i && common_hp_k && spd_inverse_slab_ok(h->N, h->ld) && h->nbig == 0;
   // Shared theta_i (one host-driven optimiser over sum_i F_i, one batched kernel per evaluation) and shared theta_k:
   // the two optimisations are independent here too. The device-side theta_k loop goes to a high-priority stream, so
   // its kernels (a few CTAs each) are placed as soon as CTAs of the batched theta_i evaluation retire.
@@ -1148,6 +1210,10 @@ static int m_step_impl(mcb_handle* h, int common_hp_k, int common_hp_i, int* sta
       h->fnew_valid = fw != 0;
       h->nfev_valid = true;
       ++h->launches;
+      if (h->nbig > 0) {
+        MCB_TRY(mstep_big_individuals(h));
+        h->fnew_valid = false;   // F_i at the new theta_i is recomputed by the ELBO for everybody
+      }
     }
   }
   if (overlap) {
@@ -1604,6 +1670,19 @@ extern "C" int mcb_last_mstep_stats(mcb_handle* h, long long out[6]) {
   }
   out[4] = h->ms_stats[4];
   out[5] = h->M;
+  return MCB_OK;
+}
+
+// per-individual outcome of the last M-step with individual-specific theta_i (CF.R:653-659 runs one opm() per individual
+// and keeps only its par; optim's counts and convergence code are what these are)
+extern "C" int mcb_last_mstep_indiv(mcb_handle* h, int* nfev, int* niter, int* status) {
+  if (!h) return MCB_EINVAL;
+  H_CHECK(h->has_cand && h->nfev_valid, MCB_ESTATE,
+          "mcb_last_mstep_indiv: the last M-step did not optimise theta_i per individual");
+  H_CUDA(cudaSetDevice(h->device));
+  if (nfev) H_CUDA(sync_copy(h, nfev, h->nfev_i.p, sizeof(int) * h->M, cudaMemcpyDeviceToHost));
+  if (niter) H_CUDA(sync_copy(h, niter, h->niter_i.p, sizeof(int) * h->M, cudaMemcpyDeviceToHost));
+  if (status) H_CUDA(sync_copy(h, status, h->status_i.p, sizeof(int) * h->M, cudaMemcpyDeviceToHost));
   return MCB_OK;
 }
 

@@ -23,7 +23,12 @@ struct mcb_handle {
 
   // ---- training set (local shard) ----
   bool has_data = false;
-  int M = 0, N = 0, ld = 0, nmax = 0;
+  int M = 0, N = 0, ld = 0, nmax = 0;       // nmax: most observations among the individuals of the shared-memory kernels
+  int nmax_all = 0, nbig = 0;               // individuals above mcb::kSmallMax observations take the global-memory kernels
+  std::vector<int> h_big_ids;
+  mcb::DevBuf<int> big_ids, big_active;
+  mcb::DevBuf<long long> big_wsoff;
+  mcb::DevBuf<double> big_ws, big_theta, big_f, big_g;
   long long P = 0, M_total = 0, W2 = 0;
   mcb::DevBuf<int> off, gidx;
   mcb::DevBuf<long long> woff;
@@ -93,7 +98,7 @@ struct mcb_handle {
   int flush_byte = 0;
 
   mcb::IndivData idata() const {
-    return mcb::IndivData{off.p, woff.p, gidx.p, t.p, y.p};
+    return mcb::IndivData{off.p, woff.p, gidx.p, t.p, y.p, big_ids.p, big_wsoff.p, big_ws.p, nbig, mcb::kSmallMax};
   }
   mcb::IndivWork iwork() const {
     return mcb::IndivWork{Winv.p, pvec.p, yWy.p, logdet_i.p, c1.p, c2.p, Fi.p};

@@ -116,6 +116,7 @@ __global__ void __launch_bounds__(kT) indiv_factor_scatter_kernel(IndivData dd, 
   extern __shared__ double sm[];
   const int i = blockIdx.x;
   const int o0 = dd.off[i], n = dd.off[i + 1] - o0;
+  if (n > dd.small_max) return;   // global-memory path (indiv_big.cu)
   const int ntot = n + 1, ld = ntot | 1;
   double* A = sm;
   double* t = A + (size_t)ntot * ld;
@@ -166,6 +167,7 @@ __global__ void __launch_bounds__(kT) indiv_tau_kernel(IndivData dd, int K, cons
   __shared__ double red[3 * (kT / 32)];
   const int i = blockIdx.x;
   const int o0 = dd.off[i], n = dd.off[i + 1] - o0;
+  if (n > dd.small_max) return;   // global-memory path (indiv_big.cu)
   double* W = sm;                 // n*n
   double* mu = W + (size_t)n * n;  // n
   double* p = mu + n;             // n
@@ -244,7 +246,7 @@ __global__ void __launch_bounds__(kT) indiv_tau_kernel(IndivData dd, int K, cons
 
 // Second version of the responsibilities kernel (round 2). The first one gathers C_k[idx, idx] twice from L2 (once for
 // sum(W o C_k), once for corr2), both triangles, one cluster at a time with a CTA reduction and two barriers per cluster:
-// ncu at C3 (profiles/r02_estep_ncu.txt): 5.6 long-scoreboard stall cycles per issue, 1.14 G L1 sectors per launch.
+// ncu at C3 (profiles/r02_estep_ncu.txt, profiles/r02s2_tau2_ncu.txt): 5.6 long-scoreboard stall cycles per issue, 1.14 G L1 sectors per launch.
 // Here every entry of the LOWER triangle of G_k = (m_k m_k' + C_k)[idx, idx] is gathered ONCE, for all clusters back to back
 // (K independent L2 requests in flight per element and thread), reduced on the fly against W, and parked in shared memory;
 // after ONE reduction over the CTA the new responsibilities are known and corr2 = sum_k tau_k G_k comes out of shared memory.
@@ -263,6 +265,7 @@ __global__ void __launch_bounds__(kT) indiv_tau2_kernel(IndivData dd, int K, con
   extern __shared__ __align__(16) double sm[];
   const int i = blockIdx.x;
   const int o0 = dd.off[i], n = dd.off[i + 1] - o0;
+  if (n > dd.small_max) return;   // global-memory path (indiv_big.cu)
   const int L = n * (n + 1) / 2;
   const size_t Lmax = (size_t)nmax * (nmax + 1) / 2;
   double* G = sm;                          // [K][Lmax]
@@ -387,6 +390,7 @@ __global__ void __launch_bounds__(TT) indiv_eval_kernel(IndivData dd, IndivWork 
   __shared__ double out[4];
   const int i = blockIdx.x;
   const int o0 = dd.off[i], n = dd.off[i + 1] - o0;
+  if (n > dd.small_max) return;   // global-memory path (indiv_big.cu)
   EvalSm s = eval_carve(sm, nmax);
   eval_load<TT>(s, n, dd.t + o0, dd.y + o0, w.c1 + o0, w.c2 + dd.woff[i]);
   const double* th = theta + (size_t)i * theta_stride;
@@ -450,6 +454,7 @@ __global__ void __launch_bounds__(TT) indiv_mstep_kernel(IndivData dd, IndivWork
     if (cur >= M) break;
     const int i = order ? order[cur] : cur;  // longest-expected-first order when the previous M-step's counts exist
     const int o0 = dd.off[i], n = dd.off[i + 1] - o0;
+    if (n > dd.small_max) continue;   // optimised by the host loop over dd.big_ids (api.cu)
     eval_load<TT>(s, n, dd.t + o0, dd.y + o0, w.c1 + o0, w.c2 + dd.woff[i]);
     if (threadIdx.x == 0) {
       lb_init(opt, 3, theta0 + 3 * (size_t)i, maxit);
@@ -490,6 +495,7 @@ __global__ void __launch_bounds__(TT, ((E > 1 || NT > 8) ? 256 : 512) / TT) indi
   __shared__ double out[4];
   const int i = blockIdx.x;
   const int o0 = dd.off[i], n = dd.off[i + 1] - o0;
+  if (n > dd.small_max) return;   // global-memory path (indiv_big.cu)
   EvalSm2<NT> s = eval2_carve<NT>(sm);
   eval2_load<TT, NT>(s, n, dd.t + o0, dd.y + o0, w.c1 + o0, w.c2 + dd.woff[i]);
   const double* th = theta + (size_t)i * theta_stride;
@@ -526,7 +532,8 @@ __global__ void __launch_bounds__(TT, ((E > 1 || NT > 8) ? 256 : 512) / TT) indi
                                                                     int* __restrict__ nfev, int* __restrict__ niter,
                                                                     int* __restrict__ status, int* __restrict__ ctl,
                                                                     int reserve, const int* __restrict__ order,
-                                                                    int solo, int solo_items, double* __restrict__ f_out) {
+                                                                    int solo, int solo_items, double* __restrict__ f_out,
+                                                                    int solo_ctas) {
   extern __shared__ __align__(16) double sm[];
   __shared__ double out[4];
   __shared__ Lbfgs opt;
@@ -548,7 +555,7 @@ __global__ void __launch_bounds__(TT, ((E > 1 || NT > 8) ? 256 : 512) / TT) indi
         role = old;
         while (role == 3) role = *((volatile int*)flag);
       }
-      if (role == 4 && atomicAdd(ctl + 1027 + smid, 1) > 0) role = 2;   // a solo SM keeps its first CTA only
+      if (role == 4 && atomicAdd(ctl + 1027 + smid, 1) >= solo_ctas) role = 2;   // a solo SM keeps its first solo_ctas CTAs only
     }
     my_role = role;
     cur = (role == 2) ? -1 : 0;
@@ -576,6 +583,7 @@ __global__ void __launch_bounds__(TT, ((E > 1 || NT > 8) ? 256 : 512) / TT) indi
     const int slot = cur;
     const int i = order ? order[slot] : slot;  // longest-expected-first order when the previous M-step's counts exist
     const int o0 = dd.off[i], n = dd.off[i + 1] - o0;
+    if (n > dd.small_max) continue;   // optimised by the host loop over dd.big_ids (api.cu)
     eval2_load<TT, NT>(s, n, dd.t + o0, dd.y + o0, w.c1 + o0, w.c2 + dd.woff[i]);
     int bI[E], bJ[E];
     if constexpr (VER != 3) eval2_decode<E, TT>(n, bI, bJ);
@@ -619,6 +627,7 @@ __global__ void __launch_bounds__(TT, ((E > 1 || NT > 8) ? 256 : 512) / TT) indi
   __shared__ double out[4];
   const int i = blockIdx.x;
   const int o0 = dd.off[i], n = dd.off[i + 1] - o0;
+  if (n > dd.small_max) return;   // global-memory path (indiv_big.cu)
   EvalSm2<NT> s = eval2_carve<NT>(sm);
   {
     double2* z = reinterpret_cast<double2*>(s.W);
@@ -685,6 +694,10 @@ static cudaError_t set_smem(const void* fn, size_t bytes) {
 cudaError_t launch_tau(cudaStream_t s, const IndivData& dd, int M, int nmax, int K, const double* mean,
                        const double* cov, int ldN, long long strideC, const double* pi, const IndivWork& w,
                        double* tau_new, double* logL, int fixed_tau) {
+  if (dd.nbig > 0) {
+    cudaError_t eb = launch_big_tau(s, dd, K, mean, cov, ldN, strideC, pi, w, tau_new, logL, fixed_tau);
+    if (eb != cudaSuccess || dd.nbig == M) return eb;
+  }
   static const bool v1 = getenv("MCB_TAU_V1") != nullptr;
   const size_t sm2 = tau2_smem_bytes(nmax, K);
   if (!v1 && K <= kTauKB && sm2 <= 200 * 1024) {
@@ -780,6 +793,10 @@ static size_t eval2_smem_bytes(int NT) {
 cudaError_t launch_factor_scatter(cudaStream_t s, const IndivData& dd, int M, int nmax, const double* theta_i,
                                   const double* tau, int K, double* acc, int ldN, long long strideA, double* wk,
                                   const IndivWork& w, int* info) {
+  if (dd.nbig > 0) {
+    cudaError_t eb = launch_big_factor(s, dd, theta_i, tau, K, acc, ldN, strideA, wk, w, info);
+    if (eb != cudaSuccess || dd.nbig == M) return eb;
+  }
   {
     int TT, E, NT;
     static const bool old_path = getenv("MCB_FACTOR_V1") != nullptr;
@@ -806,6 +823,10 @@ cudaError_t launch_factor_scatter(cudaStream_t s, const IndivData& dd, int M, in
 cudaError_t launch_indiv_eval(cudaStream_t s, const IndivData& dd, int M, int nmax, const IndivWork& w,
                               const double* theta, int theta_stride, int want_grad, double* f, double* g,
                               double* sum4, int* info) {
+  if (dd.nbig > 0) {
+    cudaError_t eb = launch_big_eval(s, dd, w, theta, theta_stride, 0, nullptr, want_grad, f, g, sum4, info);
+    if (eb != cudaSuccess || dd.nbig == M) return eb;
+  }
   {
     int TT, E, NT;
     if (eval2_shape(nmax, &TT, &E, &NT)) {
@@ -855,6 +876,7 @@ cudaError_t launch_indiv_mstep(cudaStream_t s, const IndivData& dd, int M, int n
       static const int cap_per_sm = getenv("MCB_MSTEP_CTAS") ? atoi(getenv("MCB_MSTEP_CTAS")) : 0;
       static const int solo_sms = getenv("MCB_SOLO_SMS") ? atoi(getenv("MCB_SOLO_SMS")) : -1;
       static const int solo_mult = getenv("MCB_SOLO_MULT") ? atoi(getenv("MCB_SOLO_MULT")) : 1;
+      static const int solo_ctas = getenv("MCB_SOLO_CTAS") ? std::max(1, atoi(getenv("MCB_SOLO_CTAS"))) : 1;
 #define MCB_LAUNCH_MSTEP2(EE, T_, N_, V_)                                                                              \
   do {                                                                                                                 \
     if ((e = set_smem_t(indiv_mstep2_kernel<EE, T_, N_, V_>, sm2)) != cudaSuccess) return e;                           \
@@ -868,11 +890,12 @@ cudaError_t launch_indiv_mstep(cudaStream_t s, const IndivData& dd, int M, int n
       /* solo SMs pay off while the optimisations outnumber the CTA slots only a few times (tail-bound regime) */      \
       solo = solo_sms >= 0 ? solo_sms : ((long long)M < 8LL * per_sm * sms ? (sms - reserve_sms) / 8 : 0);            \
       if (solo > sms - reserve_sms - 1) solo = sms - reserve_sms - 1;                                                  \
-      solo_items = solo_mult * solo;                                                                                   \
+      solo_items = solo_mult * solo * solo_ctas;                                                                       \
     }                                                                                                                  \
     if (grid > M && reserve_sms == 0 && solo == 0) grid = M;                                                           \
     indiv_mstep2_kernel<EE, T_, N_, V_><<<grid, T_, sm2, s>>>(dd, w, nmax, M, theta0, theta_out, maxit, nfev, niter,   \
-                                                          status, ctl, reserve_sms, order, solo, solo_items, f_out);   \
+                                                          status, ctl, reserve_sms, order, solo, solo_items, f_out,    \
+                                                          solo_ctas);                                                  \
     if (f_out_written) *f_out_written = f_out ? 1 : 0;                                                                 \
   } while (0)
       MCB_DISPATCH_EVAL2(MCB_LAUNCH_MSTEP2);

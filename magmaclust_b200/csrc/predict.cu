@@ -86,6 +86,11 @@ __global__ void kc_build_kernel(int K, int T, int ldT, const double* __restrict_
   for (int k = 0; k < K; ++k) KC[k * sT + (size_t)i * ldT + j] = e + pcov[k * sT + (size_t)i * ldT + j];
 }
 
+// BIG: more observations than the shared-memory version holds (n* > kMaxObs, or (n* + 1)^2 doubles above the shared-memory
+// budget): the same layout lives in a global-memory workspace block per CTA (ws + blockIdx.x * wsstride) and the
+// per-target quadratic form is done by one warp per target without a per-thread copy of the cross-covariance column.
+// The reference has no size limit (MC.R:255-262).
+template <bool BIG>
 __global__ void __launch_bounds__(kTP) predict_kernel(int K, int T, int ldT, const double* __restrict__ pgrid,
                                                       const double* __restrict__ pmean,
                                                       const double* __restrict__ pcov, const int* __restrict__ off,
@@ -93,12 +98,13 @@ __global__ void __launch_bounds__(kTP) predict_kernel(int K, int T, int ldT, con
                                                       const double* __restrict__ theta, const double* __restrict__ pik,
                                                       int Tp, const int* __restrict__ pidx, int nmax,
                                                       double* __restrict__ out_tau, double* __restrict__ out_mean,
-                                                      double* __restrict__ out_var, int* __restrict__ info) {
+                                                      double* __restrict__ out_var, int* __restrict__ info,
+                                                      double* ws, long long wsstride) {
   extern __shared__ double sm[];
   const int b = blockIdx.x;
   const int o0 = off[b], n = off[b + 1] - o0;
   const int ntot = n + 1, ld = ntot | 1;
-  double* A = sm;                               // (nmax+1) x ld
+  double* A = BIG ? ws + (size_t)blockIdx.x * wsstride : sm;   // (nmax+1) x ld
   double* ts = A + (size_t)(nmax + 1) * ((nmax + 1) | 1);
   double* lk = ts + nmax;                       // K
   int* idx = (int*)(lk + K);
@@ -129,7 +135,30 @@ __global__ void __launch_bounds__(kTP) predict_kernel(int K, int T, int ldT, con
     }
     const double logdet = sweep_p(A, n, ntot, ld, info);
     if (threadIdx.x == 0) lk[k] = -0.5 * ((double)n * kLog2Pi + logdet - A[n * ld + n]);  // dmvnorm, CF.R:780
-    if (out_mean) {
+    if (out_mean && BIG) {
+      const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+      for (int j = warp; j < Tp; j += kTP / 32) {
+        const int gj = pidx[j];
+        double mean = 0.0, quad = 0.0;
+        for (int a = lane; a < n; a += 32) {
+          const double ga = Ck[(size_t)idx[a] * ldT + gj];
+          mean += ga * A[a * ld + n];
+          double row = 0.0;
+          for (int c = 0; c < n; ++c) row -= A[a * ld + c] * Ck[(size_t)idx[c] * ldT + gj];   // A block = -S^-1
+          quad += ga * row;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          mean += __shfl_xor_sync(0xffffffffu, mean, o);
+          quad += __shfl_xor_sync(0xffffffffu, quad, o);
+        }
+        if (lane == 0) {
+          const size_t o = ((size_t)b * K + k) * Tp + j;
+          out_mean[o] = mk[gj] + mean;
+          out_var[o] = sg * sg + Ck[(size_t)gj * ldT + gj] - quad;
+        }
+      }
+    } else if (out_mean) {
       // Mean_k = m_k[tp] + Gamma' S^-1 z ; Var_k = diag(Sigma(tp) + C_k[tp,tp] - Gamma' S^-1 Gamma)  (MC.R:261-268)
       for (int j = threadIdx.x; j < Tp; j += kTP) {
         const int gj = pidx[j];
@@ -170,20 +199,21 @@ __global__ void __launch_bounds__(kTP) predict_kernel(int K, int T, int ldT, con
 // train_new_gp_EM (MC.R:151-166). The kernel matrix cannot be shared over the grid here (theta differs per point), so it is
 // evaluated n*^2 times per cluster in place. A trial theta that makes a covariance numerically singular yields NaN for
 // that term (the line search treats it as a failed step), not an error.
+template <bool BIG>
 __global__ void __launch_bounds__(kTP) new_indiv_logl_kernel(int K, int T, int ldT, const double* __restrict__ pgrid,
                                                              const double* __restrict__ pmean,
                                                              const double* __restrict__ pcov, const int* __restrict__ off,
                                                              const int* __restrict__ oidx, const double* __restrict__ yv,
                                                              const int* __restrict__ pt_ind,
                                                              const double* __restrict__ pt_theta, int nmax,
-                                                             double* __restrict__ out) {
+                                                             double* __restrict__ out, double* ws, long long wsstride) {
   extern __shared__ double sm[];
   __shared__ int bad;
   const int p = blockIdx.x;
   const int b = pt_ind[p];
   const int o0 = off[b], n = off[b + 1] - o0;
   const int ntot = n + 1, ld = ntot | 1;
-  double* A = sm;                               // (nmax+1) x ld
+  double* A = BIG ? ws + (size_t)blockIdx.x * wsstride : sm;   // (nmax+1) x ld
   double* ts = A + (size_t)(nmax + 1) * ((nmax + 1) | 1);
   int* idx = (int*)(ts + nmax);
   const double th1 = pt_theta[3 * p], th2 = pt_theta[3 * p + 1], sg = pt_theta[3 * p + 2];
@@ -377,21 +407,23 @@ extern "C" int mcb_predict(mcb_handle* h, int B, const int* offsets, const int* 
   }
   if (out_mean) for (int j = 0; j < Tp; ++j) H_CHECK(pred_idx[j] >= 0 && pred_idx[j] < T, MCB_EINVAL, "mcb_predict: pred_idx out of range");
   const size_t smem = sizeof(double) * ((size_t)(nmax + 1) * ((nmax + 1) | 1) + nmax + K) + sizeof(int) * nmax + 16;
-  H_CHECK(nmax <= kMaxObs && smem <= 227 * 1024, MCB_EINVAL,
-          "mcb_predict: more than 64 observations for one new individual is not supported yet");
+  // above the shared-memory version's limits the same kernel runs on a global-memory workspace block per new individual
+  const bool big = nmax > kMaxObs || smem > 227 * 1024;
+  const long long wsstride = (long long)((smem + 7) / 8);
+  mcb::DevBuf<double> d_ws;
   H_CUDA(cudaSetDevice(h->device));
   h->spans.clear(); h->ev_next = 0; h->launches = 0;
   mcb::DevBuf<int> d_off, d_idx, d_pidx;
   mcb::DevBuf<double> d_y, d_small, d_tau, d_mean, d_var;
   auto cleanup = [&]() {
     d_off.release(); d_idx.release(); d_pidx.release(); d_y.release(); d_small.release(); d_tau.release();
-    d_mean.release(); d_var.release();
+    d_mean.release(); d_var.release(); d_ws.release();
   };
   cudaError_t e = cudaSuccess;
   const size_t nout = out_mean ? (size_t)B * K * Tp : 0;
   if ((e = d_off.ensure(B + 1)) || (e = d_idx.ensure(Pn)) || (e = d_y.ensure(Pn)) || (e = d_small.ensure(3 + K)) ||
       (e = d_tau.ensure((size_t)B * K)) || (e = d_pidx.ensure(std::max(Tp, 1))) ||
-      (nout && ((e = d_mean.ensure(nout)) || (e = d_var.ensure(nout))))) {
+      (nout && ((e = d_mean.ensure(nout)) || (e = d_var.ensure(nout)))) || (big && (e = d_ws.ensure((size_t)B * wsstride)))) {
     cleanup();
     h->err = std::string("mcb_predict: ") + cudaGetErrorString(e);
     return MCB_ENOMEM;
@@ -404,7 +436,7 @@ extern "C" int mcb_predict(mcb_handle* h, int B, const int* offsets, const int* 
   cudaMemcpyAsync(d_y.p, y, sizeof(double) * Pn, cudaMemcpyHostToDevice, h->st);
   cudaMemcpyAsync(d_small.p, small.data(), sizeof(double) * (3 + K), cudaMemcpyHostToDevice, h->st);
   if (out_mean) cudaMemcpyAsync(d_pidx.p, pred_idx, sizeof(int) * Tp, cudaMemcpyHostToDevice, h->st);
-  if (smem > 48 * 1024) cudaFuncSetAttribute(predict_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (!big && smem > 48 * 1024) cudaFuncSetAttribute(predict_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   {
     int e0 = (int)h->evpool.size();
     cudaEvent_t a, b2;
@@ -414,9 +446,16 @@ extern "C" int mcb_predict(mcb_handle* h, int B, const int* offsets, const int* 
     kc_build_kernel<<<dim3((T + 31) / 32, (T + 7) / 8), dim3(32, 8), 0, h->st>>>(K, T, h->ldT, h->pgrid.p, h->pcov.p,
                                                                                  d_small.p, h->pKinv.p);
     ++h->launches;
-    predict_kernel<<<B, kTP, smem, h->st>>>(K, T, h->ldT, h->pgrid.p, h->pmean.p, h->pKinv.p, d_off.p, d_idx.p, d_y.p,
-                                            d_small.p, d_small.p + 3, Tp, d_pidx.p, nmax, d_tau.p,
-                                            out_mean ? d_mean.p : nullptr, out_mean ? d_var.p : nullptr, h->info.p);
+    if (big)
+      predict_kernel<true><<<B, kTP, 0, h->st>>>(K, T, h->ldT, h->pgrid.p, h->pmean.p, h->pKinv.p, d_off.p, d_idx.p, d_y.p,
+                                                 d_small.p, d_small.p + 3, Tp, d_pidx.p, nmax, d_tau.p,
+                                                 out_mean ? d_mean.p : nullptr, out_mean ? d_var.p : nullptr, h->info.p,
+                                                 d_ws.p, wsstride);
+    else
+      predict_kernel<false><<<B, kTP, smem, h->st>>>(K, T, h->ldT, h->pgrid.p, h->pmean.p, h->pKinv.p, d_off.p, d_idx.p, d_y.p,
+                                                     d_small.p, d_small.p + 3, Tp, d_pidx.p, nmax, d_tau.p,
+                                                     out_mean ? d_mean.p : nullptr, out_mean ? d_var.p : nullptr, h->info.p,
+                                                     nullptr, 0);
     cudaEventRecord(b2, h->st);
     h->spans.push_back({PH_PRED, e0, e0 + 1});
     ++h->launches;
@@ -450,9 +489,10 @@ struct NewIndivDev {
   mcb_handle* h;
   int B = 0, nmax = 0;
   size_t smem = 0;
+  bool big = false;
   mcb::DevBuf<int> off, idx, pt_ind;
-  mcb::DevBuf<double> y, pt_theta, out;
-  void release() { off.release(); idx.release(); pt_ind.release(); y.release(); pt_theta.release(); out.release(); }
+  mcb::DevBuf<double> y, pt_theta, out, ws;
+  void release() { off.release(); idx.release(); pt_ind.release(); y.release(); pt_theta.release(); out.release(); ws.release(); }
 };
 
 int new_indiv_upload(mcb_handle* h, NewIndivDev& d, int B, const int* offsets, const int* obs_idx, const double* y,
@@ -473,8 +513,7 @@ int new_indiv_upload(mcb_handle* h, NewIndivDev& d, int B, const int* offsets, c
   }
   d.h = h; d.B = B; d.nmax = nmax;
   d.smem = sizeof(double) * ((size_t)(nmax + 1) * ((nmax + 1) | 1) + nmax) + sizeof(int) * nmax + 16;
-  H_CHECK(nmax <= mcb::kMaxObs && d.smem <= 227 * 1024, MCB_EINVAL,
-          std::string(who) + ": more than 64 observations for one new individual is not supported yet");
+  d.big = d.smem > 227 * 1024;   // beyond the shared-memory budget: global-memory workspace block per evaluation point
   H_CUDA(cudaSetDevice(h->device));
   const long long Pn = offsets[B];
   cudaError_t e = cudaSuccess;
@@ -486,8 +525,8 @@ int new_indiv_upload(mcb_handle* h, NewIndivDev& d, int B, const int* offsets, c
   cudaMemcpyAsync(d.off.p, offsets, sizeof(int) * (B + 1), cudaMemcpyHostToDevice, h->st);
   cudaMemcpyAsync(d.idx.p, obs_idx, sizeof(int) * Pn, cudaMemcpyHostToDevice, h->st);
   cudaMemcpyAsync(d.y.p, y, sizeof(double) * Pn, cudaMemcpyHostToDevice, h->st);
-  if (d.smem > 48 * 1024)
-    cudaFuncSetAttribute(mcb::new_indiv_logl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d.smem);
+  if (!d.big && d.smem > 48 * 1024)
+    cudaFuncSetAttribute(mcb::new_indiv_logl_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d.smem);
   if ((e = cudaStreamSynchronize(h->st)) != cudaSuccess) {
     d.release();
     h->err = std::string(who) + ": " + cudaGetErrorString(e);
@@ -502,14 +541,22 @@ int new_indiv_eval(void* ctx, int npts, const int* pt_ind, const double* pt_thet
   mcb_handle* h = d.h;
   const int K = h->Kp;
   cudaError_t e = cudaSuccess;
-  if ((e = d.pt_ind.ensure(npts)) || (e = d.pt_theta.ensure(3 * (size_t)npts)) || (e = d.out.ensure((size_t)npts * K))) {
+  const long long wsstride = (long long)((d.smem + 7) / 8);
+  if ((e = d.pt_ind.ensure(npts)) || (e = d.pt_theta.ensure(3 * (size_t)npts)) || (e = d.out.ensure((size_t)npts * K)) ||
+      (d.big && (e = d.ws.ensure((size_t)npts * wsstride)))) {
     h->err = std::string("new-individual objective: ") + cudaGetErrorString(e);
     return MCB_ENOMEM;
   }
   cudaMemcpyAsync(d.pt_ind.p, pt_ind, sizeof(int) * npts, cudaMemcpyHostToDevice, h->st);
   cudaMemcpyAsync(d.pt_theta.p, pt_theta, sizeof(double) * 3 * npts, cudaMemcpyHostToDevice, h->st);
-  mcb::new_indiv_logl_kernel<<<npts, mcb::kTP, d.smem, h->st>>>(K, h->T, h->ldT, h->pgrid.p, h->pmean.p, h->pcov.p, d.off.p,
-                                                                d.idx.p, d.y.p, d.pt_ind.p, d.pt_theta.p, d.nmax, d.out.p);
+  if (d.big)
+    mcb::new_indiv_logl_kernel<true><<<npts, mcb::kTP, 0, h->st>>>(K, h->T, h->ldT, h->pgrid.p, h->pmean.p, h->pcov.p, d.off.p,
+                                                                   d.idx.p, d.y.p, d.pt_ind.p, d.pt_theta.p, d.nmax, d.out.p,
+                                                                   d.ws.p, wsstride);
+  else
+    mcb::new_indiv_logl_kernel<false><<<npts, mcb::kTP, d.smem, h->st>>>(K, h->T, h->ldT, h->pgrid.p, h->pmean.p, h->pcov.p,
+                                                                         d.off.p, d.idx.p, d.y.p, d.pt_ind.p, d.pt_theta.p,
+                                                                         d.nmax, d.out.p, nullptr, 0);
   ++h->launches;
   cudaMemcpyAsync(out, d.out.p, sizeof(double) * (size_t)npts * K, cudaMemcpyDeviceToHost, h->st);
   if ((e = cudaGetLastError()) != cudaSuccess || (e = cudaStreamSynchronize(h->st)) != cudaSuccess) {

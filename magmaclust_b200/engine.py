@@ -318,6 +318,19 @@ class Engine:
         return th, tau, loops
 
     # ------------------------------------------------------------------------------------------
+    def kmeans(self, feat, K, start_rows, max_iter=100):
+        """ini_kmeans' clustering step (MAGMAclust.R:585) on the device: feat [M][D], start_rows [nstart][K] (initial centres
+        = those rows) -> (labels [M] in [0, K), centres [K][D], total within-cluster SS, assignment passes)"""
+        feat, start_rows = f64(feat), i32(start_rows)
+        M, D = feat.shape
+        nstart = start_rows.shape[0]
+        assert start_rows.shape == (nstart, K)
+        lab, cent = np.empty(M, dtype=np.int32), np.empty((K, D))
+        cost, iters = C.c_double(0.0), C.c_int(0)
+        self._ck(self.lib.mcb_kmeans(self.h, M, D, dptr(feat), K, nstart, iptr(start_rows), int(max_iter), iptr(lab),
+                                     dptr(cent), C.byref(cost), C.byref(iters)))
+        return lab, cent, float(cost.value), int(iters.value)
+
     def last_timings(self):
         ms = (C.c_float * 8)()
         n = C.c_longlong(0)
@@ -329,6 +342,13 @@ class Engine:
         self._ck(self.lib.mcb_last_mstep_stats(self.h, out))
         return {"nfev_i_max": out[0], "nfev_k": out[1], "nit_i": out[2], "nit_k": out[3], "nfev_i_sum": out[4],
                 "M_local": out[5]}
+
+    def last_mstep_indiv(self):
+        """(nfev [M], niter [M], status [M]) of the last per-individual M-step (status: 1 converged, 2 maxit, 3 abnormal line
+        search, 4 zero gradient, 5 not finite at the start)"""
+        a, b, c = (np.empty(self.M, dtype=np.int32) for _ in range(3))
+        self._ck(self.lib.mcb_last_mstep_indiv(self.h, iptr(a), iptr(b), iptr(c)))
+        return a, b, c
 
     def pin(self, arr):
         """page-lock a numpy array in place (cudaHostRegister); returns True on success"""

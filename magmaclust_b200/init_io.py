@@ -1,7 +1,8 @@
 """Callers and data formats either side of the hot path: the k-means initialisation of the
 responsibilities (`ini_kmeans`, `ini_tau_i_k`, MAGMAclust.R:562-603) and the `db` table formats the study scripts use
-(CSV with ID, Timestamp, Output columns, Simulation_study.R:554-582). Host side, numpy only: none of this is on the
-timed path and nothing here touches the GPU.
+(CSV with ID, Timestamp, Output columns, Simulation_study.R:554-582). The feature rows and the random choice of the
+starts are host work; the clustering itself (`nstart` Lloyd runs side by side) runs on the GPU (`mcb_kmeans`,
+csrc/kmeans.cu) -- there is no host k-means in the product.
 
 Parity note: the reference clusters with `stats::kmeans(centers = k, nstart = 50)` (Hartigan-Wong, R's
 RNG): there is no artefact that pins its partitions, so parity is at the level of the contract, which the tests check:
@@ -41,48 +42,35 @@ def kmeans_features(db):
     return uid, feat
 
 
-def _lloyd(feat, cent, n_iter):
-    lab = None
-    for _ in range(n_iter):
-        d2 = ((feat[:, None, :] - cent[None, :, :]) ** 2).sum(-1)
-        new_lab = np.argmin(d2, axis=1)
-        if lab is not None and np.array_equal(new_lab, lab):
-            break
-        lab = new_lab
-        for k in range(cent.shape[0]):
-            if np.any(lab == k):
-                cent[k] = feat[lab == k].mean(0)
-    return lab, cent
+def kmeans_starts(M, k, nstart, seed):
+    """start_rows [nstart][k]: k distinct individuals per start as initial centres, like kmeans(centers = k); `seed`
+    replaces R's global RNG state"""
+    rng = np.random.default_rng(seed)
+    return np.array([rng.choice(M, size=k, replace=False) for _ in range(max(1, int(nstart)))], dtype=np.int32)
 
 
-def ini_kmeans(db, k, nstart=50, summary=False, seed=0, n_iter=100):
+def ini_kmeans(db, k, nstart=50, summary=False, seed=0, n_iter=100, session=None):
     """`ini_kmeans(db, k, nstart, summary)` (MAGMAclust.R:562-598): returns {"ID": [...], "Cluster_ini": ["K2", ...]}.
-    `nstart` random starts (k distinct rows as centres, like kmeans(centers = k)), Lloyd iterations to a fixed point, the
-    start with the smallest total within-cluster sum of squares wins. `seed` replaces R's global RNG state."""
+    `nstart` random starts (k distinct rows as centres), Lloyd iterations to a fixed point on the GPU (all starts in the
+    same launches), the start with the smallest total within-cluster sum of squares wins."""
+    from . import magma
     uid, feat = kmeans_features(db)
     M = feat.shape[0]
     if not (1 <= k <= M):
         raise ValueError("ini_kmeans: need 1 <= k <= number of individuals")
-    rng = np.random.default_rng(seed)
-    best = None
-    for _ in range(max(1, int(nstart))):
-        cent = feat[rng.choice(M, size=k, replace=False)].astype(np.float64).copy()
-        lab, cent = _lloyd(feat, cent, n_iter)
-        cost = float(((feat - cent[lab]) ** 2).sum())
-        if best is None or cost < best[0]:
-            best = (cost, lab.copy(), cent.copy())
-    cost, lab, cent = best
+    s = session or magma.default_session()
+    lab, cent, cost, _ = s.eng.kmeans(feat, k, kmeans_starts(M, k, nstart, seed), n_iter)
     if summary:
         print(f"K-means clustering with {k} clusters of sizes {', '.join(str(int((lab == j).sum())) for j in range(k))}; "
               f"total within-cluster sum of squares {cost:.6g}")
     return {"ID": uid, "Cluster_ini": [f"K{int(j) + 1}" for j in lab], "centers": cent, "tot_withinss": cost}
 
 
-def ini_tau_i_k(db, k, nstart=50, seed=0):
+def ini_tau_i_k(db, k, nstart=50, seed=0, session=None):
     """`ini_tau_i_k(db, k, nstart)` (MAGMAclust.R:600-607): {cluster name: {ID: 0/1}}; the clusters appear in the order
     in which their labels first occur over the individuals (pivot_wider), which is NOT K1, K2, ... in general: the first
     E-step multiplies pi_k positionally against this order (quirk Q3, CF.R:757)."""
-    res = ini_kmeans(db, k, nstart, seed=seed)
+    res = ini_kmeans(db, k, nstart, seed=seed, session=session)
     names = _unique_in_order(np.asarray(res["Cluster_ini"]))
     return {name: {i: (1.0 if c == name else 0.0) for i, c in zip(res["ID"], res["Cluster_ini"])} for name in names}
 

@@ -51,12 +51,83 @@ def test_other_evaluator_designs_agree_with_the_oracle(var):
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
 
 
-def test_more_than_80_observations_is_rejected(session):
-    from magmaclust_b200._lib import McbError
+def _mixed_problem(M, K, sizes, n_grid, seed, common_hp_i=False):
+    """a small problem whose individual r has sizes[r % len(sizes)] observations"""
+    db, hp, tau, m_k = small_problem(M=M, K=K, n=(max(sizes), max(sizes)), n_grid=n_grid, seed=seed, ragged=False,
+                                     common_hp_i=common_hp_i)
+    keep = np.zeros(db["ID"].shape[0], dtype=bool)
+    rng = np.random.default_rng(seed + 1)
+    for r, i in enumerate(np.unique(db["ID"])):
+        rows = np.nonzero(db["ID"] == i)[0]
+        keep[np.sort(rng.choice(rows, sizes[r % len(sizes)], replace=False))] = True
+    return {c: v[keep] for c, v in db.items()}, hp, tau, m_k
+
+
+@pytest.mark.parametrize("sizes", [(81, 12, 130, 40), (96, 100), (200, 7)])
+def test_more_than_80_observations_take_the_global_memory_kernels(session, sizes):
+    """the reference has no limit on n_i (CF.R:153-190); above the tile buckets of the shared-memory kernels an individual
+    runs on indiv_big.cu. Mixed with small individuals, all big, and n_i = 200: E-step, objective and gradient vs the oracle"""
+    db, hp, tau, m_k = _mixed_problem(M=6, K=2, sizes=sizes, n_grid=260, seed=17)
+    _check_eval(session, db, hp, tau, m_k)
+
+
+@pytest.mark.parametrize("common_hp_i", [True, False])
+def test_m_step_with_big_individuals_reaches_the_oracles_optimum(session, common_hp_i):
+    """m_step_VEM (CF.R:631-687) on a data set with individuals on both paths: the optimiser (in-kernel for the small ones,
+    the same state machine in lock step on the host for the big ones) ends at scipy's minimiser of the oracle's objective"""
     from magmaclust_b200 import magma
-    db, hp, tau, m_k = small_problem(M=3, K=2, n=(81, 81), n_grid=100, seed=1, ragged=False)
-    with pytest.raises(McbError):
-        magma.e_step_VEM(db, m_k, magma.kernel_mu, magma.kernel, hp, tau, session=session)
+    db, hp, tau, m_k = _mixed_problem(M=5, K=2, sizes=(90, 14, 110), n_grid=160, seed=23, common_hp_i=common_hp_i)
+    got = magma.e_step_VEM(db, m_k, magma.kernel_mu, magma.kernel, hp, tau, session=session)
+    ref = O.e_step_VEM(db, m_k, O.kernel_mu, O.kernel, hp, tau)
+    new = magma.m_step_VEM(db, hp, got, magma.kernel_mu, magma.kernel, m_k, True, common_hp_i, session=session)
+    want = O.m_step_VEM(db, hp, ref, O.kernel_mu, O.kernel, m_k, True, common_hp_i)
+    per = O.split_db(db)
+    for i in per:
+        a, b = np.asarray(new["theta_i"][i]), np.asarray(want["theta_i"][i])
+        if common_hp_i:
+            fa = O.logL_clust_multi_GP_common_hp_i(a, db, ref, O.kernel)
+            fb = O.logL_clust_multi_GP_common_hp_i(b, db, ref, O.kernel)
+        else:
+            fa, fb = O.logL_clust_multi_GP(a, per[i], ref, O.kernel), O.logL_clust_multi_GP(b, per[i], ref, O.kernel)
+        # same objective value at the end point (flat directions make theta itself loose), never worse than scipy's
+        assert fa <= fb + 1e-6 * max(1.0, abs(fb)), (i, fa, fb)
+        assert abs(fa - fb) <= 1e-4 * max(1.0, abs(fb)), (i, fa, fb)
+    elbo_g = magma.logL_monitoring_VEM(new, db, magma.kernel, magma.kernel_mu, got, m_k, session=session)
+    elbo_o = O.logL_monitoring_VEM(new, db, O.kernel, O.kernel_mu, ref, m_k)
+    assert abs(elbo_g - elbo_o) <= RTOL_LL * abs(elbo_o)
+
+
+def test_new_individual_with_more_than_64_observations(session):
+    """pred_gp_clust / update_tau_star_k_EM / the free-hp log-density for n* = 100 and n* = 180 (MC.R:255-262 has no limit):
+    the global-memory versions of the prediction kernels against the oracle"""
+    from magmaclust_b200 import magma
+    db, hp, tau, m_k = small_problem(M=10, K=2, n=(8, 14), n_grid=200, seed=29, common_hp_i=True)
+    names = list(m_k.keys())
+    param = magma.e_step_VEM(db, m_k, magma.kernel_mu, magma.kernel, hp, tau, session=session)
+    ref = O.e_step_VEM(db, m_k, O.kernel_mu, O.kernel, hp, tau)
+    list_hp = {"hp": hp, "param": param}
+    grid = np.round(np.linspace(0, 10, 200), 3)
+    mu = magma.posterior_mu_k(db, grid, m_k, magma.kernel_mu, magma.kernel, list_hp, session=session)
+    mu_o = O.posterior_mu_k(db, grid, m_k, O.kernel_mu, O.kernel, {"hp": hp, "param": ref})
+    rng = np.random.default_rng(5)
+    for nstar in (100, 180):
+        t = np.sort(rng.choice(grid, nstar, replace=False))
+        new_db = {"Timestamp": t, "Output": 1.0 + np.sin(t) + 0.3 * rng.standard_normal(nstar)}
+        th = np.array([0.7, 0.4, 0.35])
+        pi_k = {k: 1.0 / len(names) for k in names}
+        tk = magma.update_tau_star_k_EM(new_db, mu["mean"], mu["cov"], magma.kernel, th, pi_k, session=session)
+        tk_o = O.update_tau_star_k_EM(new_db, mu_o["mean"], mu_o["cov"], O.kernel, th, pi_k)
+        for k in names:
+            assert abs(tk[k] - tk_o[k]) < RTOL_LL
+        pr = magma.pred_gp_clust(new_db, grid[::4], mu, magma.kernel, {"theta_new": th, "tau_k": tk}, session=session)
+        pr_o = O.pred_gp_clust(new_db, grid[::4], mu_o, O.kernel, {"theta_new": th, "tau_k": tk_o})
+        for k in names:
+            assert rel_err(pr[k]["Mean"], pr_o[k]["Mean"]) < RTOL_POST
+            assert np.max(np.abs(np.asarray(pr[k]["Var"]) - np.asarray(pr_o[k]["Var"]))) < RTOL_POST * max(1.0, np.max(np.abs(pr_o[k]["Var"])))
+        idx = np.searchsorted(grid, t).astype(np.int32)
+        ll = session.eng.new_indiv_logl(np.array([0, nstar], np.int32), idx, new_db["Output"], np.array([0], np.int32), th[None])
+        ll_o = O.new_indiv_logl(new_db, mu_o["mean"], mu_o["cov"], O.kernel, th)
+        assert np.max(np.abs(ll[0] - ll_o)) <= RTOL_LL * max(1.0, np.max(np.abs(ll_o)))
 
 
 def test_single_cluster_and_tiny_grid(session):

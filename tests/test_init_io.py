@@ -1,4 +1,5 @@
-"""Host-side rows of SURVEY.md §8f: ini_kmeans / ini_tau_i_k (MAGMAclust.R:562-607) and the CSV form of `db`."""
+"""Rows of SURVEY.md §8f either side of the path: ini_kmeans / ini_tau_i_k (MAGMAclust.R:562-607; features and starts on the
+host, the clustering on the GPU, checked bit for bit against oracle/kmeans_oracle.py) and the CSV form of `db`."""
 import os
 
 import numpy as np
@@ -28,6 +29,41 @@ def test_features_follow_the_reference_rule():
 
 
 @pytest.mark.parametrize("regular", [True, False])
+def test_oracle_kmeans_is_a_lloyd_fixed_point(regular):
+    """CPU: the restated k-means ends where every individual sits with its nearest centre and every centre is its cluster's mean"""
+    from oracle import kmeans_oracle as KO
+    db, _ = _db(regular)
+    uid, feat = init_io.kmeans_features(db)
+    lab, cent, cost, iters = KO.kmeans(feat, 3, init_io.kmeans_starts(feat.shape[0], 3, 20, 1))
+    for k in range(3):
+        if np.any(lab == k):
+            assert np.allclose(cent[k], feat[lab == k].mean(0), rtol=1e-14)
+    d2 = ((feat[:, None, :] - cent[None, :, :]) ** 2).sum(-1)
+    assert np.array_equal(np.argmin(d2, 1), lab) and np.isclose(cost, d2[np.arange(len(lab)), lab].sum(), rtol=1e-13)
+    assert 1 <= iters <= 100
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("M,D,K,nstart", [(24, 3, 3, 20), (24, 10, 3, 7), (2500, 3, 5, 12), (1, 3, 1, 2), (40, 64, 4, 5)])
+def test_gpu_kmeans_is_bit_identical_to_the_oracle(M, D, K, nstart):
+    """mcb_kmeans vs oracle/kmeans_oracle.py on the same features and starts: identical labels, centres and cost (every
+    floating-point operation has a prescribed order), including M > one summation chunk and a single individual"""
+    from magmaclust_b200.engine import Engine
+    from oracle import kmeans_oracle as KO
+    rng = np.random.default_rng(M + D)
+    feat = rng.normal(0, 1, (M, D)) + 4.0 * rng.integers(0, K, M)[:, None]
+    starts = init_io.kmeans_starts(M, K, nstart, 3)
+    e = Engine(0)
+    try:
+        lab, cent, cost, iters = e.kmeans(feat, K, starts)
+    finally:
+        e.close()
+    lab_o, cent_o, cost_o, iters_o = KO.kmeans(feat, K, starts)
+    assert np.array_equal(lab, lab_o) and np.array_equal(cent, cent_o) and cost == cost_o and iters == iters_o
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("regular", [True, False])
 def test_ini_kmeans_is_a_local_optimum_and_labels_are_K_names(regular):
     db, _ = _db(regular)
     res = init_io.ini_kmeans(db, 3, nstart=20, seed=1)
@@ -45,6 +81,7 @@ def test_ini_kmeans_is_a_local_optimum_and_labels_are_K_names(regular):
     assert init_io.ini_kmeans(db, 3, nstart=40, seed=1)["tot_withinss"] <= res["tot_withinss"] + 1e-12
 
 
+@pytest.mark.gpu
 def test_ini_tau_i_k_is_one_hot_in_first_appearance_order():
     db, _ = _db(regular=False, seed=8)
     tau = init_io.ini_tau_i_k(db, 3, nstart=10, seed=2)
@@ -58,6 +95,7 @@ def test_ini_tau_i_k_is_one_hot_in_first_appearance_order():
         assert [tau[k][i] for k in tau] == [1.0 if k == c else 0.0 for k in tau]
 
 
+@pytest.mark.gpu
 def test_well_separated_clusters_are_recovered():
     rng = np.random.default_rng(0)
     ids, ts, ys, truth = [], [], [], []

@@ -118,7 +118,7 @@ int main() {
     CK(cudaMemcpy(dt, t.data(), P * 8, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(dy, y.data(), P * 8, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(dth, th.data(), 3 * M * 8, cudaMemcpyHostToDevice));
-    IndivData dd{doff, dw, dg, dt, dy};
+    IndivData dd{doff, dw, dg, dt, dy, nullptr, nullptr, nullptr, 0, kSmallMax};
     IndivWork w{dW, dp, dyWy, dld, nullptr, nullptr, nullptr};
     CK(launch_factor_scatter(st, dd, M, 50, dth, dtau, 0, nullptr, 0, 0, nullptr, w, info));
     CK(cudaStreamSynchronize(st));
