@@ -21,6 +21,9 @@ Next to the headline, the same line carries (every --gpus N, unless --no-extras)
                       sharded over the N GPUs: ms per VEM iteration (strong scaling), phases, and its own sharded_vs_single
   c4_owner          : configs[3]: dense grid N = 8192, K = 8 (M = 4096 x 32 obs): ms per E-step; with N > 1 cluster k is
                       owned by rank k mod N (one cluster per GPU at N = 8), A_k reduced to its owner, C_k broadcast back
+  c5_predict        : configs[4]: 10,000 new individuals x 20 obs onto a 2,000-point grid, K = 5, all targets: new individuals
+                      predicted per second through host buffers (strong scaling: B / N per rank, no exchange step)
+  c1_training       : configs[0] (the reference's CPU-runnable case, M = 50, K = 3): ms per whole training_VEM
   training_run      : one real multi-iteration training_VEM trajectory (until the reference's stopping rule, <= 15
                       iterations) of the headline workload, timed once
 
@@ -68,7 +71,7 @@ def parse():
     ap.add_argument("--no-flush", action="store_true", help="do not evict L2 between timed steps")
     ap.add_argument("--reps", type=int, default=2, help="repetitions of the timed region; the faster one is reported")
     ap.add_argument("--no-steady", action="store_true", help="skip the extra steady-state measurement of the dominant kernel")
-    ap.add_argument("--no-extras", action="store_true", help="skip c3_strong / c4_owner / training_run")
+    ap.add_argument("--no-extras", action="store_true", help="skip c3_strong / c4_owner / c5_predict / c1_training / training_run")
     ap.add_argument("--cpu-sample", type=int, default=200, help="individuals in the CPU baseline sample")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--individuals", type=int, default=0, help="override the individuals per GPU of the workload")
@@ -472,6 +475,92 @@ def run_c4_owner(D, local, args):
         eng.close()
 
 
+def run_c5_predict(D, local, args):
+    """BASELINE configs[4]: pred_magmaclust-style prediction, 10,000 new individuals (20 observations each) onto a 2,000-point
+    grid with the cluster-mixture posterior (K = 5): posterior_mu_k once, then update_tau_star_k_EM + pred_gp_clust for the
+    whole batch in one call. New individuals shard with NO exchange step: every rank holds the prediction
+    posterior and takes B / n_gpus of them (strong scaling). Host buffers in, page-locked host buffers out (reused across
+    calls); 16 B K T bytes come back per new individual."""
+    from magmaclust_b200 import synth
+    from magmaclust_b200.engine import Engine
+    B_total, T, K, nstar = 10000, 2000, 5, 20
+    ds = synth.make_dataset(M=1000, K=K, n=30, n_grid=T, common_hp_i=True, seed=synth.CONFIGS["C5"]["seed"])
+    eng = Engine(local)
+    try:
+        M = ds["M"]
+        eng.set_data(ds["offsets"], ds["grid_idx_full"], ds["y"], ds["grid_full"])
+        tk, ti, mk = start_state(M, K)
+        eng.set_state(tk, ti, np.ascontiguousarray(ds["tau0"].mean(0)), mk, np.ascontiguousarray(ds["tau0"]))
+        eng.timer_start()
+        eng.posterior_mu_k(ds["grid_full"], tau=ds["tau0"], want_mean=False, want_cov=False)
+        ms_post = eng.timer_stop()
+        rng = np.random.default_rng(7)
+        obs = np.sort(np.argsort(rng.random((B_total, T)), axis=1)[:, :nstar], axis=1).astype(np.int32)
+        mu = ds["mu_true"][rng.integers(0, K, B_total)]
+        y = np.take_along_axis(mu, obs, axis=1) + 0.3 * rng.standard_normal((B_total, nstar))
+        lo, hi = B_total * D.rank // D.world, B_total * (D.rank + 1) // D.world
+        B = hi - lo
+        offsets = (np.arange(B + 1) * nstar).astype(np.int32)
+        o_idx, o_y = np.ascontiguousarray(obs[lo:hi].ravel()), np.ascontiguousarray(y[lo:hi].ravel())
+        pred_idx = np.arange(T, dtype=np.int32)
+        theta_new = np.array([1.0, 1.0, 0.2])
+        out = (eng.pinned_empty((B, K)), eng.pinned_empty((B, K, T)), eng.pinned_empty((B, K, T)))
+        eng.predict(offsets, o_idx, o_y, theta_new, pred_idx, out=out)   # warm-up (device allocations)
+        steps, ker = 3, 0.0
+        D.barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            eng.predict(offsets, o_idx, o_y, theta_new, pred_idx, out=out)
+            ker += eng.last_timings()[0]["predict"]
+        wall = D.max((time.perf_counter() - t0) * 1e3)
+        D.barrier()
+        tau, mean, var = out
+        flop = B * K * (nstar ** 3 + 2.0 * nstar ** 2 * T + 4.0 * nstar * T)     # SURVEY 8d per (new individual, cluster)
+        return {"workload": f"C5: {B_total} new individuals (fixed) x {nstar} obs onto a {T}-point grid, K={K}, all {T} targets",
+                "new_individuals_this_rank": B, "steps": steps, "warmup": 1, "ms_per_call_e2e": wall / steps,
+                "value": B_total * steps / (wall / 1e3), "unit": "new individuals predicted/s (host buffers in, page-locked host buffers out)",
+                "scaling": "strong", "posterior_mu_k_ms": ms_post, "predict_kernels_ms_this_rank": ker / steps,
+                "predict_kernel_tflops_this_rank": flop / (ker / steps / 1e3) / 1e12 if ker > 0 else None,
+                "h2d_bytes_per_call": int(offsets.nbytes + o_idx.nbytes + o_y.nbytes + pred_idx.nbytes),
+                "d2h_bytes_per_call": int(tau.nbytes + mean.nbytes + var.nbytes),
+                "checks": {"tau_rowsum_err": float(np.abs(tau.sum(1) - 1).max()), "var_min": float(var.min())}}
+    finally:
+        eng.close()
+
+
+def run_c1(D, local, args):
+    """BASELINE configs[0] (the reference's own CPU-runnable case: M = 50, K = 3, ~30 obs, common hp): one whole training_VEM
+    on this rank (replicas only: 50 individuals do not shard usefully). The reference's stored R timing for a training of this
+    shape is 97.8 s."""
+    from magmaclust_b200 import synth
+    from magmaclust_b200.engine import Engine
+    c = synth.CONFIGS["C1"]
+    ds = synth.make_dataset(c["M"], c["K"], c["n"], c["n_grid"], c["common_hp_i"], c["seed"])
+    eng = Engine(local)
+    try:
+        tk, ti, mk = start_state(ds["M"], c["K"])
+        eng.set_data(ds["offsets"], ds["grid_idx_full"], ds["y"], np.ascontiguousarray(ds["grid_full"]))
+        best = None
+        for rep in range(3):
+            eng.set_state(tk, ti, np.ascontiguousarray(ds["tau0"].mean(0)), mk, np.ascontiguousarray(ds["tau0"]))
+            eng.timer_start()
+            trace, conv = [], False
+            for it in range(15):
+                elbo, eps, conv = eng.vem_iteration(True, True)
+                trace.append(elbo)
+                if conv:
+                    break
+            ms = eng.timer_stop()
+            if rep > 0 and (best is None or ms < best[0]):
+                best = (ms, len(trace), bool(conv), trace[-1])
+        return {"workload": "C1: M=50 individuals x K=3, n_i=30, grid of 201 points, common hp; whole training_VEM from the study's "
+                            "start state", "ms_per_training": best[0], "iterations": best[1], "converged": best[2],
+                "ms_per_iteration": best[0] / best[1], "elbo_last": best[3], "replicas": D.world,
+                "reference_stored_r_seconds_for_this_shape": 97.8}
+    finally:
+        eng.close()
+
+
 # ------------------------------------------------------------------------------------------------
 def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
@@ -648,7 +737,7 @@ def run_ours(args):
     eng.close()
 
     # ---- the other BASELINE configurations, in the same record -----------------------------------------------------------
-    c3 = c4 = None
+    c1 = c3 = c4 = c5 = None
     if not args.no_extras and args.workload == "C2" and not args.individuals:
         try:
             c3 = run_c3_strong(D, local, args)
@@ -658,6 +747,14 @@ def run_ours(args):
             c4 = run_c4_owner(D, local, args)
         except Exception as ex:
             c4 = {"error": str(ex)[:300]}
+        try:
+            c5 = run_c5_predict(D, local, args)
+        except Exception as ex:
+            c5 = {"error": str(ex)[:300]}
+        try:
+            c1 = run_c1(D, local, args)
+        except Exception as ex:
+            c1 = {"error": str(ex)[:300]}
 
     failed = False
     if rank == 0:
@@ -686,6 +783,7 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "mstep_evals_per_step": {"theta_i_total": nfev_i_sum / args.steps, "theta_k": nfev_k / args.steps},
             "training_run": training_run, "sharded_vs_single": parity, "c3_strong": c3, "c4_owner": c4,
+            "c5_predict": c5, "c1_training": c1,
         }
         for rec in (parity, (c3 or {}).get("sharded_vs_single"), (c4 or {}).get("sharded_vs_single")):
             if rec is not None and not rec.get("ok", False):

@@ -249,6 +249,9 @@ int mcb_last_mstep_indiv(mcb_handle* h, int* nfev, int* niter, int* status);
  * from pinned memory. */
 int mcb_pin_host(void* ptr, size_t bytes);
 int mcb_unpin_host(void* ptr);
+/* Page-locked host memory (cudaHostAlloc) for buffers that cross PCIe on every call, e.g. the results of mcb_predict. */
+int mcb_host_alloc(void** out, size_t bytes);
+int mcb_host_free(void* ptr);
 /* CUDA-event stopwatch on the handle's stream (the stream every kernel of this library is launched on):
  * start synchronises and records; stop records, synchronises and returns the elapsed device time. */
 int mcb_timer_start(mcb_handle* h);

@@ -79,6 +79,8 @@ SIGNATURES = {
     "mcb_last_mstep_indiv": (C.c_int, [H, c_int_p, c_int_p, c_int_p]),
     "mcb_pin_host": (C.c_int, [C.c_void_p, C.c_size_t]),
     "mcb_unpin_host": (C.c_int, [C.c_void_p]),
+    "mcb_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t]),
+    "mcb_host_free": (C.c_int, [C.c_void_p]),
     "mcb_timer_start": (C.c_int, [H]),
     "mcb_timer_stop": (C.c_int, [H, c_float_p]),
     "mcb_flush_l2": (C.c_int, [H]),

@@ -1686,6 +1686,14 @@ extern "C" int mcb_last_mstep_indiv(mcb_handle* h, int* nfev, int* niter, int* s
   return MCB_OK;
 }
 
+// page-locked host memory for buffers that cross PCIe on every call (results of mcb_predict: 1.6 GB at config C5)
+extern "C" int mcb_host_alloc(void** out, size_t bytes) {
+  if (!out || bytes == 0) return MCB_EINVAL;
+  return cudaHostAlloc(out, bytes, cudaHostAllocDefault) == cudaSuccess ? MCB_OK : MCB_ENOMEM;
+}
+
+extern "C" int mcb_host_free(void* ptr) { return cudaFreeHost(ptr) == cudaSuccess ? MCB_OK : MCB_ECUDA; }
+
 extern "C" int mcb_pin_host(void* ptr, size_t bytes) {
   return cudaHostRegister(ptr, bytes, cudaHostRegisterDefault) == cudaSuccess ? MCB_OK : MCB_ECUDA;
 }

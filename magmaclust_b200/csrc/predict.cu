@@ -99,12 +99,12 @@ __global__ void __launch_bounds__(kTP) predict_kernel(int K, int T, int ldT, con
                                                       int Tp, const int* __restrict__ pidx, int nmax,
                                                       double* __restrict__ out_tau, double* __restrict__ out_mean,
                                                       double* __restrict__ out_var, int* __restrict__ info,
-                                                      double* ws, long long wsstride) {
+                                                      double* ws, long long wsstride, int b0) {
   extern __shared__ double sm[];
-  const int b = blockIdx.x;
+  const int b = b0 + blockIdx.x;   // the batch is launched in chunks so that result copies overlap the next chunk
   const int o0 = off[b], n = off[b + 1] - o0;
   const int ntot = n + 1, ld = ntot | 1;
-  double* A = BIG ? ws + (size_t)blockIdx.x * wsstride : sm;   // (nmax+1) x ld
+  double* A = BIG ? ws + (size_t)b * wsstride : sm;   // (nmax+1) x ld
   double* ts = A + (size_t)(nmax + 1) * ((nmax + 1) | 1);
   double* lk = ts + nmax;                       // K
   int* idx = (int*)(lk + K);
@@ -446,24 +446,43 @@ extern "C" int mcb_predict(mcb_handle* h, int B, const int* offsets, const int* 
     kc_build_kernel<<<dim3((T + 31) / 32, (T + 7) / 8), dim3(32, 8), 0, h->st>>>(K, T, h->ldT, h->pgrid.p, h->pcov.p,
                                                                                  d_small.p, h->pKinv.p);
     ++h->launches;
-    if (big)
-      predict_kernel<true><<<B, kTP, 0, h->st>>>(K, T, h->ldT, h->pgrid.p, h->pmean.p, h->pKinv.p, d_off.p, d_idx.p, d_y.p,
-                                                 d_small.p, d_small.p + 3, Tp, d_pidx.p, nmax, d_tau.p,
-                                                 out_mean ? d_mean.p : nullptr, out_mean ? d_var.p : nullptr, h->info.p,
-                                                 d_ws.p, wsstride);
-    else
-      predict_kernel<false><<<B, kTP, smem, h->st>>>(K, T, h->ldT, h->pgrid.p, h->pmean.p, h->pKinv.p, d_off.p, d_idx.p, d_y.p,
-                                                     d_small.p, d_small.p + 3, Tp, d_pidx.p, nmax, d_tau.p,
-                                                     out_mean ? d_mean.p : nullptr, out_mean ? d_var.p : nullptr, h->info.p,
-                                                     nullptr, 0);
+    // Chunks of the batch: the means / variances of chunk c travel to the host (second stream) while chunk c + 1 is being
+    // computed. 16 B K Tp bytes come back (1.6 GB at C5): with page-locked destinations (mcb_host_alloc / mcb_pin_host) the
+    // call is bounded by that copy at PCIe rate; pageable destinations work but are staged by the driver.
+    const int nch = out_mean ? std::max(1, std::min(16, B / 512)) : 1;
+    if (out_mean && !h->st_copy) {
+      cudaStreamCreateWithFlags(&h->st_copy, cudaStreamNonBlocking);
+      cudaEventCreateWithFlags(&h->ev_copy0, cudaEventDisableTiming);
+      cudaEventCreateWithFlags(&h->ev_copy1, cudaEventDisableTiming);
+    }
+    std::vector<cudaEvent_t> evc(nch, nullptr);
+    for (int c = 0; c < nch; ++c) {
+      const int bs = (int)((long long)B * c / nch), be = (int)((long long)B * (c + 1) / nch);
+      if (big)
+        predict_kernel<true><<<be - bs, kTP, 0, h->st>>>(K, T, h->ldT, h->pgrid.p, h->pmean.p, h->pKinv.p, d_off.p, d_idx.p,
+                                                         d_y.p, d_small.p, d_small.p + 3, Tp, d_pidx.p, nmax, d_tau.p,
+                                                         out_mean ? d_mean.p : nullptr, out_mean ? d_var.p : nullptr,
+                                                         h->info.p, d_ws.p, wsstride, bs);
+      else
+        predict_kernel<false><<<be - bs, kTP, smem, h->st>>>(K, T, h->ldT, h->pgrid.p, h->pmean.p, h->pKinv.p, d_off.p, d_idx.p,
+                                                             d_y.p, d_small.p, d_small.p + 3, Tp, d_pidx.p, nmax, d_tau.p,
+                                                             out_mean ? d_mean.p : nullptr, out_mean ? d_var.p : nullptr,
+                                                             h->info.p, nullptr, 0, bs);
+      ++h->launches;
+      if (out_mean) {
+        cudaEventCreateWithFlags(&evc[c], cudaEventDisableTiming);
+        cudaEventRecord(evc[c], h->st);
+        cudaStreamWaitEvent(h->st_copy, evc[c], 0);
+        const size_t o = (size_t)bs * K * Tp, cnt = (size_t)(be - bs) * K * Tp;
+        cudaMemcpyAsync(out_mean + o, d_mean.p + o, sizeof(double) * cnt, cudaMemcpyDeviceToHost, h->st_copy);
+        cudaMemcpyAsync(out_var + o, d_var.p + o, sizeof(double) * cnt, cudaMemcpyDeviceToHost, h->st_copy);
+      }
+    }
     cudaEventRecord(b2, h->st);
     h->spans.push_back({PH_PRED, e0, e0 + 1});
-    ++h->launches;
-  }
-  cudaMemcpyAsync(out_tau, d_tau.p, sizeof(double) * (size_t)B * K, cudaMemcpyDeviceToHost, h->st);
-  if (out_mean) {
-    cudaMemcpyAsync(out_mean, d_mean.p, sizeof(double) * nout, cudaMemcpyDeviceToHost, h->st);
-    cudaMemcpyAsync(out_var, d_var.p, sizeof(double) * nout, cudaMemcpyDeviceToHost, h->st);
+    cudaMemcpyAsync(out_tau, d_tau.p, sizeof(double) * (size_t)B * K, cudaMemcpyDeviceToHost, h->st);
+    if (out_mean) cudaStreamSynchronize(h->st_copy);
+    for (cudaEvent_t ev : evc) if (ev) cudaEventDestroy(ev);
   }
   int flag = 0;
   cudaMemcpyAsync(&flag, h->info.p, sizeof(int), cudaMemcpyDeviceToHost, h->st);

@@ -10,7 +10,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import McbError, dptr, f64, i32, iptr
+from ._lib import McbError, c_double_p, dptr, f64, i32, iptr
 
 PHASES = ("indiv_factor_scatter", "dense_hyperpost", "indiv_tau", "mstep_indiv", "mstep_mean", "elbo",
           "predict", "collectives")
@@ -29,10 +29,14 @@ class Engine:
         self.M = self.N = self.K = 0
         self.T = 0
         self.Kp = 0   # clusters of the resident prediction posterior
+        self._pinned_allocs = []
 
     # ------------------------------------------------------------------------------------------
     def close(self):
         if getattr(self, "h", None):
+            for p in self._pinned_allocs:
+                self.lib.mcb_host_free(p)
+            self._pinned_allocs = []
             self.lib.mcb_destroy(self.h)
             self.h = None
 
@@ -277,9 +281,29 @@ class Engine:
                                      nhp, float(pen_diag), dptr(f), dptr(g)))
         return float(f[0]), g
 
-    def predict(self, offsets, obs_idx, y, theta_new, pred_idx=None, pi_k=None):
+    def pinned_empty(self, shape):
+        """float64 array in page-locked host memory (mcb_host_alloc), released with the engine: destination for results that
+        cross PCIe on every call (predict(out=...))"""
+        n = int(np.prod(shape))
+        p = C.c_void_p()
+        self._ck(self.lib.mcb_host_alloc(C.byref(p), max(8, 8 * n)))
+        self._pinned_allocs.append(p)
+        return np.ctypeslib.as_array(C.cast(p, c_double_p), shape=(max(1, n),))[:n].reshape(shape)
+
+    def predict(self, offsets, obs_idx, y, theta_new, pred_idx=None, pi_k=None, out=None):
+        """out = (tau [B][K], mean [B][K][Tp], var [B][K][Tp]): caller-owned result buffers (reuse them across calls; page-locked
+        ones from pinned_empty() make the copies run at PCIe rate)"""
         offsets, obs_idx, y, theta_new = i32(offsets), i32(obs_idx), f64(y), f64(theta_new)
         B = offsets.shape[0] - 1
+        if out is not None:
+            tau, mean, var = out
+            pred_idx = i32(pred_idx)
+            Tp = pred_idx.shape[0]
+            assert tau.shape == (B, self.Kp) and mean.shape == (B, self.Kp, Tp) and var.shape == mean.shape
+            pi = f64(pi_k) if pi_k is not None else None
+            self._ck(self.lib.mcb_predict(self.h, B, iptr(offsets), iptr(obs_idx), dptr(y), dptr(theta_new), dptr(pi), Tp,
+                                          iptr(pred_idx), dptr(tau), dptr(mean), dptr(var)))
+            return tau, mean, var
         tau = np.empty((B, self.Kp))
         pi = f64(pi_k) if pi_k is not None else None
         if pred_idx is None:

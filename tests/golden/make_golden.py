@@ -62,6 +62,28 @@ def main():
                         ini_hp_theta_i=np.asarray(settings["ini_hp_clust"][1]),
                         prior_mean=np.asarray(settings["prior_mean"]))
     print("wrote", out, os.path.getsize(out), "bytes")
+    make_pred()
+
+
+def make_pred():
+    """hoo_diff_time_pred.npz: the testing individual (ID 1) of every dataset and the numbers the reference's own study
+    stored for its MAGMAclust prediction (`loop_pred`, Simulation_study.R:672-737: first 20 timestamps observed, last 10
+    predicted, `full_algo_clust` with the stored trained model, then MSE_clust / WCIC, Simulation_study.R:262-298):
+    `Simulations/Results/res_pred_Hoo_diff_time.csv`, rows Method == "MAGMAclust" in dataset order. Re-encoded verbatim."""
+    csv = pd.read_csv(f"{REF}/Data/db_i_clust_100rep_M20_N30_diff_time_Hoo.csv")
+    res = pd.read_csv(f"{REF}/Results/res_pred_Hoo_diff_time.csv")
+    mc = res[res.Method == "MAGMAclust"].reset_index(drop=True)
+    assert len(mc) == 100
+    one = csv[csv.ID == 1]
+    ts, ys = np.zeros((100, 30)), np.zeros((100, 30))
+    for d in range(100):
+        df = one[one.ID_dataset == d + 1]
+        assert len(df) == 30
+        ts[d], ys[d] = df.Timestamp.values, df.Output.values
+    out = os.path.join(os.path.dirname(__file__), "hoo_diff_time_pred.npz")
+    np.savez_compressed(out, Timestamp=ts, Output=ys, MSE=mc.MSE.values, WCIC=mc.WCIC.values,
+                        Time_train=mc.Time_train.values, nb_obs=np.array([20]), nb_test=np.array([10]))
+    print("wrote", out, os.path.getsize(out), "bytes")
 
 
 if __name__ == "__main__":

@@ -72,3 +72,37 @@ def assert_param_close(got, ref, names_k):
     A, B = O.tau_to_array(got["tau_i_k"]), O.tau_to_array(ref["tau_i_k"])
     assert np.max(np.abs(A - B)) < RTOL_LL, "tau"
     assert np.array_equal(A.argmax(1), B.argmax(1)), "hard assignments"
+
+
+GOLD_PRED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "hoo_diff_time_pred.npz")
+
+
+def gold_prediction_case(g, gp, d):
+    """the reference's own prediction experiment on fixture dataset d (loop_pred, Simulation_study.R:672-737): the stored
+    trained model, the testing individual's first nb_obs timestamps as observations, its last nb_test as targets"""
+    db, hp, tau, m_k = gold_dataset(g, d)
+    order = np.argsort(gp["Timestamp"][d], kind="stable")
+    t, y = gp["Timestamp"][d][order], gp["Output"][d][order]
+    nb_obs, nb_test = int(gp["nb_obs"][0]), int(gp["nb_test"][0])
+    new_db = {"Timestamp": t[:nb_obs], "Output": y[:nb_obs]}
+    test = {"Timestamp": t[-nb_test:], "Output": y[-nb_test:]}
+    list_hp = {"hp": hp, "param": {"tau_i_k": tau}}
+    return db, m_k, list_hp, new_db, test
+
+
+def mse_clust(test, pred):
+    """MSE_clust (Simulation_study.R:262-276): squared error of the tau-weighted mixture of the cluster means"""
+    mix = sum(pred[k]["tau_k"] * np.asarray(pred[k]["Mean"]) for k in pred)
+    return float(np.mean((np.asarray(test["Output"]) - mix) ** 2))
+
+
+def wcic(test, pred, level=0.05):
+    """WCIC (Simulation_study.R:283-298): tau-weighted share of test values inside each cluster's credible interval"""
+    from scipy.stats import norm
+    q = norm.ppf(1 - level / 2)
+    v = np.asarray(test["Output"])
+    out = 0.0
+    for k in pred:
+        m, sd = np.asarray(pred[k]["Mean"]), np.sqrt(np.asarray(pred[k]["Var"]))
+        out += 100.0 * pred[k]["tau_k"] * np.mean((m - q * sd < v) & (v < m + q * sd))
+    return float(out)

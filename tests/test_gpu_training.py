@@ -145,3 +145,19 @@ def test_trained_model_through_an_rds_file(session, tmp_path):
         assert np.array_equal(loaded["param"]["cov"][k].m, trained["param"]["cov"][k].m)
         assert rel_err(b["mean"][k]["Output"], a["mean"][k]["Output"]) < 1e-12
         assert rel_err(b["cov"][k].m, a["cov"][k].m) < 1e-12
+
+
+@pytest.mark.parametrize("d0", [0, 40, 80])
+def test_library_reproduces_the_reference_studys_stored_prediction_mse(session, d0):
+    """full_algo_clust on the GPU with the reference's stored trained models against the MSE / coverage the REFERENCE wrote
+    for the same experiment (Simulations/Results/res_pred_Hoo_diff_time.csv via tests/golden/hoo_diff_time_pred.npz; loop_pred,
+    Simulation_study.R:672-737): not GPU-vs-oracle but GPU-vs-reference output, 12 of the 100 datasets"""
+    from helpers import GOLD_PRED, gold_prediction_case, mse_clust, wcic
+    from magmaclust_b200 import magma
+    g, gp = load_gold(), np.load(GOLD_PRED)
+    for d in range(d0, d0 + 4):
+        db, m_k, list_hp, new_db, test = gold_prediction_case(g, gp, d)
+        out = magma.full_algo_clust(db, new_db, test["Timestamp"], magma.kernel, None, True, True, m_k, magma.kernel_mu,
+                                    list_hp, None, None, None, session=session)
+        assert abs(mse_clust(test, out["Prediction"]) - gp["MSE"][d]) <= 1e-7 * gp["MSE"][d], d
+        assert abs(wcic(test, out["Prediction"]) - gp["WCIC"][d]) <= 1e-6, d
