@@ -14,6 +14,9 @@
 // b);  A[:,b] = P;  A[b,b] = -D^-1.  After the last block the matrix holds -A^-1 (the sign is flipped in the
 // last epilogue). Total N^3 FMAs in uniform rank-32 DMMA updates, 2 launches per block, log det = sum of the
 // log pivots. The un-swept part evolves exactly as in a right-looking blocked Cholesky.
+#include <algorithm>
+#include <cmath>
+
 #include "common.cuh"
 
 namespace mcb {
@@ -595,10 +598,35 @@ __global__ void panel_gather_kernel(const double* __restrict__ A, int N, int ld,
   Pn[z * sPn + e] = (r < N && c < nbw) ? A[z * stride + (size_t)r * ld + c0 + c] : 0.0;
 }
 
+// dense_tma.cu: TMA-fed persistent version of the symmetric full-matrix update (returns false when it does not apply)
+bool sweep_update_tma(cudaStream_t s, int N, int K, const double* V, int ldv, int rows, int Z, double* C, int ldc,
+                      long long sC, const double* P, int ldp, long long sP, int c0, int nb, double sign, cudaError_t* err);
+
 static void launch_sweep_update(cudaStream_t s, int M, int Ncols, int K, const double* Va, int lda, long long sA,
                                 const double* Vb, int ldb, long long sB, double* C, int ldc, long long sC,
                                 const double* P, int ldp, long long sP, int r0p, int c0, int nb, int cro, double sign,
                                 int Z, int sym = 0) {
+  static const bool verify = getenv("MCB_TMA_VERIFY") != nullptr;   // debug: run both kernels and compare
+  double* Cold = nullptr;
+  if (sym && Va == Vb && lda == ldb && sA == sB && M == Ncols && r0p == c0 && cro == 0 && sA % lda == 0) {
+    cudaError_t e;
+    if (verify) {
+      cudaMalloc(&Cold, sizeof(double) * (size_t)sC * Z);
+      cudaMemcpyAsync(Cold, C, sizeof(double) * (size_t)sC * Z, cudaMemcpyDeviceToDevice, s);
+      if (atoi(getenv("MCB_TMA_VERIFY")) >= 2) {   // evict C from L2 again: the TMA kernel then sees what it sees in the real flow
+        static void* scratch = nullptr;
+        if (!scratch) cudaMalloc(&scratch, 512u << 20);
+        cudaMemsetAsync(scratch, 1, 512u << 20, s);
+      }
+    }
+    if (sweep_update_tma(s, M, K, Va, lda, (int)(sA / lda), Z, C, ldc, sC, P, ldp, sP, c0, nb, sign, &e)) {
+      if (!verify) return;
+      std::swap(C, Cold);   // the cp.async kernel below now works on the copy of the input; compared afterwards
+    } else if (Cold) {
+      cudaFree(Cold);
+      Cold = nullptr;
+    }
+  }
   GemmParams p{};
   p.M = M; p.N = Ncols; p.K = K;
   p.A = Va; p.lda = lda; p.sA = sA;
@@ -611,6 +639,23 @@ static void launch_sweep_update(cudaStream_t s, int M, int Ncols, int K, const d
   p.sym = nosym ? 0 : sym;
   p.nofast = nofast ? 1 : 0;
   launch_gemm<EPI_SWEEP>(s, p, Z, nullptr);
+  if (Cold) {
+    // C (here: the copy) holds the cp.async result, Cold (the real matrix) the TMA result
+    cudaStreamSynchronize(s);
+    std::vector<double> a((size_t)sC * Z), b((size_t)sC * Z);
+    cudaMemcpy(a.data(), C, sizeof(double) * a.size(), cudaMemcpyDeviceToHost);
+    cudaMemcpy(b.data(), Cold, sizeof(double) * b.size(), cudaMemcpyDeviceToHost);
+    double worst = 0, scale = 0; long long bad = 0; int wi = -1, wj = -1;
+    for (int i = 0; i < M; ++i) for (int j = 0; j < Ncols; ++j) {
+      const double x = a[(size_t)i * ldc + j], y = b[(size_t)i * ldc + j];
+      scale = std::max(scale, std::fabs(x));
+      const double d = std::fabs(x - y);
+      if (!(d <= 1e-9 * (1.0 + std::fabs(x)))) { ++bad; if (!(d <= worst)) { worst = d; wi = i; wj = j; } }
+    }
+    printf("[tma verify] N %d K %d c0 %d nb %d sign %+.0f: mismatches %lld worst %.3e at (%d, %d), |C| max %.3e\n", M, K, c0, nb, sign,
+           bad, worst, wi, wj, scale);
+    cudaFree(C);   // the copy; the matrix keeps the TMA result
+  }
 }
 
 cudaError_t spd_inverse(cudaStream_t s, double* A, int N, int ld, long long stride, int Z, double* logdet,
