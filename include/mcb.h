@@ -138,7 +138,9 @@ int mcb_get_new_hp(mcb_handle* h, double* theta_k, double* theta_i, double* pi_k
 
 /* ---- one VEM iteration = the loop body of training_VEM (MC.R:44-93) ---------------------------------- */
 /* E-step, ELBO(hp), M-step, eps = (L(new_hp) - L(hp)) / |L(new_hp)|, acceptance rule of MC.R:83-90.
- * out[0] = ELBO total appended to logL_iterations (MC.R:77), out[1] = eps, out[2] = 1 if converged. */
+ * out[0] = ELBO total appended to logL_iterations (MC.R:77), out[1] = eps, out[2] = 0 go on, 1 converged (MC.R:83-87),
+ * 2 the M-step's candidate hp are unusable (a covariance at them is not positive definite; eps = -inf): the reference's
+ * M-step failure (MC.R:62-67) -- stop WITHOUT appending out[0], convergence stays FALSE, the last valid hp are kept. */
 int mcb_vem_iteration(mcb_handle* h, int common_hp_k, int common_hp_i, double out[3]);
 /* Host-buffer form of the same call (what the `.Call` shim binds for the loop body of training_VEM): additionally delivers
  * `param` of this iteration's E-step (MC.R:48) to caller-owned host buffers: out_mean[K][N], out_cov[K][N][N],

@@ -330,7 +330,26 @@ static int group_theta(const double* theta, int K, std::vector<int>& gmap, std::
   return G;
 }
 
-static int check_info(mcb_handle* h, const char* where) {
+// Multi-rank runs: the not-positive-definite flag is raised by kernels that work on rank-local individuals, so one rank could
+// return MCB_ENOTPD alone while its peers wait in their next collective. The flag therefore travels as one more double in
+// the all-reduce that precedes the check (info_to_double before it, info_from_double after it), or through its own 8-byte
+// all-reduce where there is none (synced = false): every rank then takes the same branch.
+__global__ void info_to_double_kernel(const int* info, double* d) { *d = (*info != 0) ? 1.0 : 0.0; }
+__global__ void info_from_double_kernel(const double* d, int* info) { if (*d != 0.0) *info = 1; }
+static void info_to_double(mcb_handle* h, double* d) {
+  if (h->nranks > 1) info_to_double_kernel<<<1, 1, 0, h->st>>>(h->info.p, d);
+}
+static void info_from_double(mcb_handle* h, const double* d) {
+  if (h->nranks > 1) info_from_double_kernel<<<1, 1, 0, h->st>>>(d, h->info.p);
+}
+
+static int check_info(mcb_handle* h, const char* where, bool synced = false) {
+  if (h->nranks > 1 && !synced) {
+    double* d = h->scal.p + 56;
+    info_to_double(h, d);
+    MCB_TRY(comm_allreduce_sum(h, d, 1));
+    info_from_double(h, d);
+  }
   int flag = 0;
   H_CUDA(cudaMemcpyAsync(&flag, h->info.p, sizeof(int), cudaMemcpyDeviceToHost, h->st));
   H_CUDA(cudaStreamSynchronize(h->st));
@@ -740,9 +759,11 @@ static int eval_indiv_common(mcb_handle* h, const double* theta3, bool want_grad
   H_CUDA(launch_indiv_eval(h->st, h->idata(), h->M, h->nmax, h->iwork(), dth, 0, want_grad, nullptr, nullptr, dsum,
                            h->info.p));
   ++h->launches;
-  MCB_TRY(comm_allreduce_sum(h, dsum, 4));
+  info_to_double(h, dsum + 4);
+  MCB_TRY(comm_allreduce_sum(h, dsum, h->nranks > 1 ? 5 : 4));
+  info_from_double(h, dsum + 4);
   H_CUDA(cudaMemcpyAsync(h->hbuf + 520, dsum, sizeof(double) * 4, cudaMemcpyDeviceToHost, h->st));
-  MCB_TRY(check_info(h, "logL_clust_multi_GP_common_hp_i"));
+  MCB_TRY(check_info(h, "logL_clust_multi_GP_common_hp_i", true));
   memcpy(out4, h->hbuf + 520, sizeof(double) * 4);
   return MCB_OK;
 }
@@ -787,9 +808,11 @@ static int elbo_impl(mcb_handle* h, const double* theta_k, const double* theta_i
                              h->info.p));
     ++h->launches;
   }
-  MCB_TRY(comm_allreduce_sum(h, dsum, 1));
+  info_to_double(h, dsum + 1);
+  MCB_TRY(comm_allreduce_sum(h, dsum, h->nranks > 1 ? 2 : 1));
+  info_from_double(h, dsum + 1);
   H_CUDA(cudaMemcpyAsync(h->hbuf + 600, dsum, sizeof(double), cudaMemcpyDeviceToHost, h->st));
-  MCB_TRY(check_info(h, "logL_monitoring_VEM"));
+  MCB_TRY(check_info(h, "logL_monitoring_VEM", true));
   const double sum_i = h->hbuf[600];
   if (!std::isfinite(sum_i)) { h->err = "logL_monitoring_VEM: covariance not positive definite"; return MCB_ENOTPD; }
   out[0] = -sum_k - sum_i;
@@ -1409,7 +1432,11 @@ static int vem_rest(mcb_handle* h, int common_hp_k, int common_hp_i, double out[
   const double eps = std::isfinite(e_new[0]) ? (e_new[0] - e_old[0]) / fabs(e_new[0]) : -INFINITY;
   out[0] = e_old[1];
   out[1] = eps;
-  if (eps < 1e-2) {
+  if (!std::isfinite(eps)) {
+    // the candidate hp are unusable: the reference leaves its loop BEFORE appending to logL_iterations, with convergence
+    // still FALSE and the last valid hp (MC.R:62-67)
+    out[2] = 2.0;
+  } else if (eps < 1e-2) {
     if (eps > 0) MCB_TRY(accept_hp_impl(h));
     out[2] = 1.0;
   } else {

@@ -208,6 +208,7 @@ class Engine:
     def vem_iteration(self, common_hp_k=True, common_hp_i=True):
         out = np.empty(3)
         self._ck(self.lib.mcb_vem_iteration(self.h, int(common_hp_k), int(common_hp_i), dptr(out)))
+        self.last_vem_status = int(out[2])   # 0 go on, 1 converged, 2 M-step failure (stop without appending, MC.R:62-67)
         return float(out[0]), float(out[1]), bool(out[2] != 0.0)
 
     def vem_iteration_host(self, common_hp_k, common_hp_i, out_mean=None, out_cov=None, out_tau=None):
@@ -218,6 +219,7 @@ class Engine:
             assert a is None or (a.dtype == np.float64 and a.flags.c_contiguous and a.shape == shp)
         self._ck(self.lib.mcb_vem_iteration_host(self.h, int(common_hp_k), int(common_hp_i), dptr(out), dptr(out_mean),
                                                  dptr(out_cov), dptr(out_tau)))
+        self.last_vem_status = int(out[2])
         return float(out[0]), float(out[1]), bool(out[2] != 0.0)
 
     # ------------------------------------------------------------------------------------------

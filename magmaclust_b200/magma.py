@@ -570,6 +570,11 @@ def training_VEM(db, prior_mean_k, ini_hp=None, kern_0=kernel_mu, kern_i=kernel,
     cv = False
     for it in range(n_loop_max):
         elbo, eps, conv = s.eng.vem_iteration(common_hp_k, common_hp_i)
+        if s.eng.last_vem_status == 2:
+            # MC.R:62-67: the M-step failed -- leave the loop before logL_iterations grows, convergence stays FALSE
+            if verbose:
+                print(f"The M-step encountered an error at iteration : {it + 1}")
+            break
         seq_logL.append(elbo)
         if verbose:
             print(it + 1, elbo, "eps", eps)
