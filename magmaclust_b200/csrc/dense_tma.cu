@@ -156,6 +156,17 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_update_tma_kernel(const __g
     for (int i = 0; i < 8; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    {
+      // This warp's 64 x 32 patch of C (64 rows of 256 bytes) is requested into L2 now, so that the read-modify-write after the
+      // contraction (33 us later at full DMMA rate) does not wait for HBM and the C reads of all SMs do not arrive in one burst
+      const double* cp = p.C + z * p.sC + (size_t)(m0 + wm) * p.ldc + n0 + wn;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int r = 16 * q + (lane >> 1);
+        if (m0 + wm + r < p.N && n0 + wn + 16 * (lane & 1) < p.N)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(cp + (size_t)r * p.ldc + 16 * (lane & 1)));
+      }
+    }
     for (int k = 0; k < nk; ++k) {
       mbar_wait(full + stage, phase);
       // Release of the PREVIOUS stage, one stage late: an mbarrier arrive does not wait for this warp's outstanding shared
@@ -191,21 +202,30 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_update_tma_kernel(const __g
     const bool clean = (m0 + kTile <= p.c0 || m0 >= p.c0 + p.nb) && (n0 + kTile <= p.c0 || n0 >= p.c0 + p.nb) &&
                        m0 + kTile <= p.N && n0 + kTile <= p.N && ti != tj && (p.ldc % 2 == 0);
     if (clean) {
-      // away from the pivot block, the diagonal and the edge: batches of independent 16-byte loads, then stores + mirror
+      // away from the pivot block, the diagonal and the edge: two batches of 16 independent 16-byte loads (they hit L2: the
+      // tile was prefetched at the start of the contraction), then stores + mirror
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int gi = m0 + wm + 8 * i + g;
-        double2 cv[4];
+      for (int half = 0; half < 2; ++half) {
+        double2 cv[4][4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) cv[j] = *reinterpret_cast<const double2*>(Cz + (size_t)gi * p.ldc + n0 + wn + 8 * j + 2 * c);
+        for (int ii = 0; ii < 4; ++ii) {
+          const int gi = m0 + wm + 8 * (4 * half + ii) + g;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int gj = n0 + wn + 8 * j + 2 * c;
-          const double r0 = p.sign * (cv[j].x - acc[i][j][0]);
-          const double r1 = p.sign * (cv[j].y - acc[i][j][1]);
-          *reinterpret_cast<double2*>(Cz + (size_t)gi * p.ldc + gj) = make_double2(r0, r1);
-          Cz[(size_t)gj * p.ldc + gi] = r0;
-          Cz[(size_t)(gj + 1) * p.ldc + gi] = r1;
+          for (int j = 0; j < 4; ++j) cv[ii][j] = *reinterpret_cast<const double2*>(Cz + (size_t)gi * p.ldc + n0 + wn + 8 * j + 2 * c);
+        }
+#pragma unroll
+        for (int ii = 0; ii < 4; ++ii) {
+          const int i = 4 * half + ii;
+          const int gi = m0 + wm + 8 * i + g;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int gj = n0 + wn + 8 * j + 2 * c;
+            const double r0 = p.sign * (cv[ii][j].x - acc[i][j][0]);
+            const double r1 = p.sign * (cv[ii][j].y - acc[i][j][1]);
+            *reinterpret_cast<double2*>(Cz + (size_t)gi * p.ldc + gj) = make_double2(r0, r1);
+            Cz[(size_t)gj * p.ldc + gi] = r0;
+            Cz[(size_t)(gj + 1) * p.ldc + gi] = r1;
+          }
         }
       }
     } else {
@@ -261,8 +281,9 @@ bool sweep_update_tma(cudaStream_t s, int N, int K, const double* V, int ldv, in
   static const bool off = getenv("MCB_NO_TMA") != nullptr;
   *err = cudaSuccess;
   // 128 x 128 tiles on 148 persistent CTAs: below ~8 tiles per CTA the last, partly filled round costs more than the
-  // pipelining saves (measured at N = 4096: 8.27 ms per inversion against 7.90 ms with the 64 x 64 cp.async kernel; N = 8192:
-  // 34.97 against 34.74 ms, i.e. equal: both kernels keep the DMMA pipe ~75 % busy and pay the same C traffic)
+  // pipelining saves (measured at N = 4096: 8.13 ms per inversion against 7.90 ms with the 64 x 64 cp.async kernel; N = 8192:
+  // 33.68 against 34.77 ms, C4 E-step 253 against 263 ms; before the L2 prefetch of the C tile and the deeper epilogue
+  // batches the two kernels were equal at N = 8192, 34.97 / 34.74 ms)
   static const int min_n = getenv("MCB_TMA_MIN_N") ? atoi(getenv("MCB_TMA_MIN_N")) : 6144;
   if (off || K % kStageCols != 0 || ldv != K || N < 4 * kTile || N < min_n || (reinterpret_cast<unsigned long long>(V) & 15ull))
     return false;
