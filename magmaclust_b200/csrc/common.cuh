@@ -67,7 +67,7 @@ struct DevBuf {
 constexpr int kNB = 32;  // pivot block of the blocked symmetric sweep
 
 struct DenseWs {
-  DevBuf<double> Pbuf, Cold;  // [Z][Npad][kNB] panels of the blocked sweep
+  DevBuf<double> Pbuf, Pbuf2, Cold;  // panels of the blocked sweep: [Z][rows][256] P (ping-pong pair) and V
   DevBuf<double> red;         // scratch for reductions
   DevBuf<double> slabV, slabP, slabL;  // panel exchange buffers of the persistent slab inverse (V, P triple-buffered)
   DevBuf<unsigned> bar;                // its per-matrix arrival counter and published-block flag

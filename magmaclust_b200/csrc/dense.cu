@@ -18,6 +18,7 @@
 #include <cmath>
 
 #include "common.cuh"
+#include "factor32.cuh"
 
 namespace mcb {
 
@@ -577,6 +578,211 @@ __global__ void __launch_bounds__(256) sweep_panel_kernel(const double* __restri
 
 constexpr int kWide = 256;   // outer pivot block of the large-grid path (8 inner blocks of kNB)
 
+// -------------------------------------------------------------------------------------------------
+// Panel phase of the wide path, round 2: ONE kernel per inner pivot block (instead of sweep_panel_kernel + a K = 32 GEMM),
+// no dependency between CTAs inside a launch. CTA = 32 rows of the column panel, 256 threads, for inner block j:
+//   A  (j > 0) its 32 x 256 slice of the panel takes the rank-32 update of block j - 1 on DMMA (own V rows from shared
+//      memory, the V rows of the 256 pivot-panel rows streamed from L2), pivot rows / columns of block j - 1 replaced from
+//      P_{j-1}; the slice is read from the OLD panel buffer and written to the NEW one (ping-pong), so every CTA of the launch
+//      sees the same old values.   (j == 0: the slice is gathered from the matrix itself.)
+//   B  (j < nin) the 32 x 32 pivot block j is recomputed by EVERY CTA from old values (D - Vp Vp', one DMMA tile product),
+//      factorised with factor32 (two-level, register-resident 8 x 8 tiles: 6.4 k cycles against ~15 k for the 32-barrier
+//      elimination of sweep_panel_kernel), V_j = R L^-T and P_j = V_j L^-1 on DMMA for the CTA's own rows.
+// Same arithmetic as the two-kernel version (sweep_panel_kernel + gemm_nt_kernel<EPI_SWEEP>); 9 launches per outer block
+// instead of 17 and no redundant 32-step elimination. Measured (tools/dbg/dense_time, one matrix): N = 8192 33.6 -> 26.8 ms per
+// inversion, N = 4096 7.89 -> 5.65 ms, N = 2000 2.45 -> 1.74 ms; C4 E-step 253 -> 216 ms. A launch takes 20 - 27 us
+// (profiles/r02s2_panel_launches.txt): 256 CTAs are 1.7 per SM, each a chain of L2 round trips, so the panel phase is still
+// ~7 of the 26.8 ms; MCB_OLD_PANEL=1 selects the two-kernel version.
+constexpr int kPLd = kF32Ld;   // 36: row stride of the 32 x 32 shared-memory tiles
+
+__device__ __forceinline__ void pdmma(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+struct PanelStep {
+  int N, rows, ld;             // matrix size, padded rows of the panel buffers, leading dimension of the matrix
+  long long strideA;           // between the matrices of the batch
+  int c0, nbw, j, nin;         // outer block start / width, inner block index, number of inner blocks
+  const double* A;             // the matrix (j == 0: source of the panel)
+  const double* Pold;          // [Z][rows][kWide] panel before the update of block j - 1 (j > 0)
+  double* Pnew;                // [Z][rows][kWide] panel after it
+  double* Vc;                  // [Z][rows][kWide] V_0 .. V_7 side by side
+  const double* Pin_prev;      // [Z][rows][kNB] P_{j-1}
+  double* Pin;                 // [Z][rows][kNB] P_j
+  double* logdet; int* info;
+};
+
+__global__ void __launch_bounds__(256) panel_step_kernel(PanelStep p) {
+  extern __shared__ __align__(16) double psm[];
+  double* Vown = psm;                      // V_{j-1} of the CTA's rows
+  double* Vp = Vown + kNB * kPLd;          // V_{j-1} of the rows of pivot block j
+  double* Dm = Vp + kNB * kPLd;            // pivot block j (destroyed by factor32)
+  double* Li = Dm + kNB * kPLd;            // L^-1
+  double* Rs = Li + kNB * kPLd;            // the CTA's rows of the pivot columns of block j
+  double* Vs = Rs + kNB * kPLd;            // V_j of the CTA's rows
+  double* scratch = Vs + kNB * kPLd;
+  const int z = blockIdx.z, r0 = blockIdx.x * kNB;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, gr = lane >> 2, gc = lane & 3;
+  const long long sW = (long long)p.rows * kWide, sI = (long long)p.rows * kNB;
+  const double* A = p.A + z * p.strideA;
+  const double* Pold = p.Pold + z * sW;
+  double* Pnew = p.Pnew + z * sW;
+  double* Vc = p.Vc + z * sW;
+  const double* Pq = p.Pin_prev + z * sI;
+  const int j = p.j;
+  const bool have_prev = j > 0, do_sweep = j < p.nin;
+  const int cp = (j - 1) * kNB, rp = p.c0 + cp;            // pivot columns (panel) / rows (matrix) of block j - 1
+  const int cpj = j * kNB, rpj = p.c0 + cpj;               // ... of block j
+  const int nbp = have_prev ? min(kNB, p.nbw - cp) : 0;
+  const int nbj = do_sweep ? min(kNB, p.nbw - cpj) : 0;
+
+  if (have_prev) {
+    for (int e = tid; e < kNB * kNB; e += 256) {
+      const int r = e >> 5, c = e & 31;
+      Vown[r * kPLd + c] = (r0 + r < p.N) ? Vc[(size_t)(r0 + r) * kWide + cp + c] : 0.0;
+      if (do_sweep) Vp[r * kPLd + c] = (r < nbj) ? Vc[(size_t)(rpj + r) * kWide + cp + c] : 0.0;
+    }
+  }
+  if (do_sweep) {
+    // old value of pivot block j (identity padded); the update of block j - 1 is subtracted below
+    for (int e = tid; e < kNB * kNB; e += 256) {
+      const int r = e >> 5, c = e & 31;
+      double v = (r == c) ? 1.0 : 0.0;
+      if (r < nbj && c < nbj)
+        v = have_prev ? Pold[(size_t)(rpj + r) * kWide + cpj + c] : A[(size_t)(rpj + r) * p.ld + p.c0 + cpj + c];
+      Dm[r * kPLd + c] = v;
+    }
+  }
+  __syncthreads();
+
+  // ---- A: the CTA's slice of the panel --------------------------------------------------------------------------------
+  // warp w owns the column tiles ct = w, w + 8, w + 16, w + 24 (8 columns each) for all 4 row tiles. Two column tiles per
+  // round: their V rows (L2) and the old values of the slice (L2) are requested together, ahead of the DMMAs
+#pragma unroll 1
+  for (int tt = 0; tt < 2; ++tt) {
+    double bf[2][8];
+    double2 oldv[2][4];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int ct = warp + 8 * (2 * tt + u);
+      if (have_prev) {
+        const int vrow = p.c0 + 8 * ct + gr;               // panel column c is row c0 + c of the matrix
+        const bool live = 8 * ct + gr < p.nbw && vrow < p.N;
+        const double* vj = Vc + (size_t)(live ? vrow : 0) * kWide + cp + gc;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) bf[u][k] = live ? __ldcg(vj + 4 * k) : 0.0;
+      }
+#pragma unroll
+      for (int rt = 0; rt < 4; ++rt) {
+        const int grow = r0 + 8 * rt + gr, c = 8 * ct + 2 * gc;
+        double2 v = make_double2(0.0, 0.0);
+        if (grow < p.N) {
+          if (have_prev) {
+            v = __ldcg(reinterpret_cast<const double2*>(Pold + (size_t)grow * kWide + c));
+          } else {
+            // gather from the matrix (ld and c0 + c are even only when ld is: two scalar loads)
+            if (c < p.nbw) v.x = A[(size_t)grow * p.ld + p.c0 + c];
+            if (c + 1 < p.nbw) v.y = A[(size_t)grow * p.ld + p.c0 + c + 1];
+          }
+        }
+        oldv[u][rt] = v;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int ct = warp + 8 * (2 * tt + u);
+#pragma unroll
+      for (int rt = 0; rt < 4; ++rt) {
+        double a0 = 0.0, a1 = 0.0;
+        if (have_prev) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) pdmma(a0, a1, Vown[(8 * rt + gr) * kPLd + 4 * k + gc], bf[u][k]);
+        }
+        const int r = 8 * rt + gr, grow = r0 + r;
+        double out2[2];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const int c = 8 * ct + 2 * gc + q;
+          const double ov = q ? oldv[u][rt].y : oldv[u][rt].x;
+          double v = 0.0;
+          if (grow < p.N && c < p.nbw) {
+            if (!have_prev) {
+              v = ov;
+            } else {
+              const bool ip = grow >= rp && grow < rp + nbp, jp = c >= cp && c < cp + nbp;
+              if (!ip && !jp) v = ov - (q ? a1 : a0);
+              else if (jp) v = Pq[(size_t)grow * kNB + (c - cp)];
+              else v = Pq[(size_t)(p.c0 + c) * kNB + (grow - rp)];
+            }
+          }
+          out2[q] = v;
+          if (do_sweep && c >= cpj && c < cpj + kNB) {
+            // R: the CTA's rows of the pivot columns; identity rows for the pivot rows themselves (their P is D^-1)
+            const int cc = c - cpj;
+            double rv = (cc < nbj) ? v : 0.0;
+            if (grow >= rpj && grow < rpj + nbj) rv = (grow - rpj == cc) ? 1.0 : 0.0;
+            Rs[r * kPLd + cc] = rv;
+          }
+        }
+        *reinterpret_cast<double2*>(Pnew + (size_t)grow * kWide + 8 * ct + 2 * gc) = make_double2(out2[0], out2[1]);
+      }
+    }
+  }
+  if (!do_sweep) return;
+
+  // ---- B: pivot block j ------------------------------------------------------------------------------------------------
+  if (have_prev) {
+    // D -= Vp Vp' (the rank-32 update of block j - 1 restricted to the pivot block; every CTA recomputes it)
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      const int tile = warp * 2 + t, ti = tile >> 2, tj = tile & 3;
+      double n0 = 0.0, n1 = 0.0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) pdmma(n0, n1, Vp[(8 * ti + gr) * kPLd + 4 * k + gc], Vp[(8 * tj + gr) * kPLd + 4 * k + gc]);
+      const int r = 8 * ti + gr, c = 8 * tj + 2 * gc;
+      if (r < nbj && c < nbj) Dm[r * kPLd + c] -= n0;
+      if (r < nbj && c + 1 < nbj) Dm[r * kPLd + c + 1] -= n1;
+    }
+  }
+  __syncthreads();
+  double logdet_part = 0.0;
+  int bad = 0;
+  factor32(Dm, Li, scratch, &logdet_part, &bad);   // ends with a barrier; Li = L^-1 (lower triangular)
+  if (r0 == (rpj / kNB) * kNB) {                    // exactly one CTA owns the pivot rows: log det and the PD check
+    if (warp == 7) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) logdet_part += __shfl_xor_sync(0xffffffffu, logdet_part, o);
+      if (lane == 0) atomicAdd(p.logdet + z, logdet_part);
+    }
+    if (bad) *p.info = 1;
+  }
+  // V = R L^-T: V[r][c] = sum_b R[r][b] Linv[c][b]
+#pragma unroll
+  for (int t = 0; t < 2; ++t) {
+    const int tile = warp * 2 + t, ti = tile >> 2, tj = tile & 3;
+    double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) pdmma(c0, c1, Rs[(8 * ti + gr) * kPLd + 4 * k + gc], Li[(8 * tj + gr) * kPLd + 4 * k + gc]);
+    Vs[(8 * ti + gr) * kPLd + 8 * tj + 2 * gc] = c0;
+    Vs[(8 * ti + gr) * kPLd + 8 * tj + 2 * gc + 1] = c1;
+    const int grow = r0 + 8 * ti + gr;
+    if (grow < p.N) *reinterpret_cast<double2*>(Vc + (size_t)grow * kWide + cpj + 8 * tj + 2 * gc) = make_double2(c0, c1);
+  }
+  __syncthreads();
+  // P = V L^-1: P[r][c] = sum_b V[r][b] Linv[b][c]; negated on the pivot rows (-D^-1)
+  double* Pout = p.Pin + z * sI;
+#pragma unroll
+  for (int t = 0; t < 2; ++t) {
+    const int tile = warp * 2 + t, ti = tile >> 2, tj = tile & 3;
+    double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) pdmma(c0, c1, Vs[(8 * ti + gr) * kPLd + 4 * k + gc], Li[(4 * k + gc) * kPLd + 8 * tj + gr]);
+    const int grow = r0 + 8 * ti + gr;
+    const double sgn = (grow >= rpj && grow < rpj + nbj) ? -1.0 : 1.0;
+    if (grow < p.N) *reinterpret_cast<double2*>(Pout + (size_t)grow * kNB + 8 * tj + 2 * gc) = make_double2(sgn * c0, sgn * c1);
+  }
+}
+
 cudaError_t spd_inverse_reserve(DenseWs& ws, int N, int Z) {
   const int ld16 = (N + 15) & ~15;
   if (spd_inverse_slab_ok(N, ld16)) return spd_inverse_slab_reserve(ws, N, Z);
@@ -584,8 +790,9 @@ cudaError_t spd_inverse_reserve(DenseWs& ws, int N, int Z) {
   const size_t rows = (size_t)nblk * kNB;
   cudaError_t e;
   if ((e = ws.Pbuf.ensure(rows * kWide * Z)) != cudaSuccess) return e;
+  if ((e = ws.Pbuf2.ensure(rows * kWide * Z)) != cudaSuccess) return e;
   if ((e = ws.Cold.ensure(rows * kWide * Z)) != cudaSuccess) return e;
-  return ws.red.ensure(rows * kNB * Z);
+  return ws.red.ensure(2 * rows * kNB * Z);
 }
 
 // Pn[r][c] = A[r][c0 + c] for c < nbw (zero beyond, and for the pad rows): the column panel of an outer block
@@ -668,8 +875,9 @@ cudaError_t spd_inverse(cudaStream_t s, double* A, int N, int ld, long long stri
   const int rows = nblk * kNB;
   cudaError_t e;
   if ((e = ws.Pbuf.ensure((size_t)rows * kWide * Z)) != cudaSuccess) return e;
+  if ((e = ws.Pbuf2.ensure((size_t)rows * kWide * Z)) != cudaSuccess) return e;
   if ((e = ws.Cold.ensure((size_t)rows * kWide * Z)) != cudaSuccess) return e;
-  if ((e = ws.red.ensure((size_t)rows * kNB * Z)) != cudaSuccess) return e;
+  if ((e = ws.red.ensure(2 * (size_t)rows * kNB * Z)) != cudaSuccess) return e;
   if ((e = cudaMemsetAsync(logdet, 0, sizeof(double) * Z, s)) != cudaSuccess) return e;
   if (narrow) {
     // first version: one rank-32 update of the whole matrix per 32 pivots (each re-reads and re-writes the matrix)
@@ -695,12 +903,45 @@ cudaError_t spd_inverse(cudaStream_t s, double* A, int N, int ld, long long stri
   double* Pin = ws.red.p;     // [Z][rows][kNB]   P_j of the current inner block
   const long long sW = (long long)rows * kWide, sI = (long long)rows * kNB;
   const int nout = (N + kWide - 1) / kWide;
+  static const bool old_panel = getenv("MCB_OLD_PANEL") != nullptr;
+  const size_t psmem = sizeof(double) * (6 * (size_t)kNB * kPLd + kF32Scratch + 8);
+  if (!old_panel) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      if ((e = cudaFuncSetAttribute(panel_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem)) != cudaSuccess) return e;
+      attr_set = true;
+    }
+  }
   for (int ob = 0; ob < nout; ++ob) {
     const int c0 = ob * kWide;
     const int nbw = (N - c0 < kWide) ? N - c0 : kWide;
+    const int nin = (nbw + kNB - 1) / kNB;
+    if (!old_panel) {
+      // one fused launch per inner block (+ one that applies the last update): the panel ping-pongs between Pn and Pn2,
+      // P_j between the two halves of Pin
+      double* Pn2 = ws.Pbuf2.p;
+      double* cur = Pn;          // written by the launch in flight
+      double* prev = Pn2;
+      for (int j = 0; j <= nin; ++j) {
+        PanelStep ps{};
+        ps.N = N; ps.rows = rows; ps.ld = ld; ps.strideA = stride;
+        ps.c0 = c0; ps.nbw = nbw; ps.j = j; ps.nin = nin;
+        ps.A = A; ps.Pold = prev; ps.Pnew = cur; ps.Vc = Vc;
+        ps.Pin_prev = Pin + (size_t)((j + 1) & 1) * sI * Z;
+        ps.Pin = Pin + (size_t)(j & 1) * sI * Z;
+        ps.logdet = logdet; ps.info = info;
+        panel_step_kernel<<<dim3(nblk, 1, Z), 256, psmem, s>>>(ps);
+        if (launches) ++*launches;
+        std::swap(cur, prev);
+      }
+      // `prev` now is the buffer the last launch wrote: the finished panel P
+      launch_sweep_update(s, N, N, nin * kNB, Vc, kWide, sW, Vc, kWide, sW, A, ld, stride, prev, kWide, sW, c0, c0, nbw, 0,
+                          (ob == nout - 1) ? -1.0 : 1.0, Z, 1);
+      if (launches) ++*launches;
+      continue;
+    }
     const long long nel = (long long)rows * kWide;
     panel_gather_kernel<<<dim3((unsigned)((nel + 255) / 256), 1, Z), 256, 0, s>>>(A, N, ld, stride, c0, nbw, Pn, sW, rows);
-    const int nin = (nbw + kNB - 1) / kNB;
     for (int j = 0; j < nin; ++j) {
       const int cj = j * kNB;
       const int nbj = (nbw - cj < kNB) ? nbw - cj : kNB;

@@ -85,7 +85,7 @@ __device__ long long f32_prof[8];
 #else
 #define F32_T(i)
 #endif
-__device__ void factor32(double* Dm, double* Li, double* scratch, double* logdet_acc, int* bad) {
+static __device__ void factor32(double* Dm, double* Li, double* scratch, double* logdet_acc, int* bad) {
 #ifdef F32_PROFILE
   long long f32_t0 = clock64();
 #endif
