@@ -744,7 +744,7 @@ extern "C" int mcb_eval_indiv(mcb_handle* h, const double* theta, double* f, dou
   }
   H_CUDA(cudaMemcpyAsync(f, h->fi_tmp.p, sizeof(double) * M, cudaMemcpyDeviceToHost, h->st));
   if (g) H_CUDA(cudaMemcpyAsync(g, h->gi_tmp.p, sizeof(double) * 3 * M, cudaMemcpyDeviceToHost, h->st));
-  h->has_cand = false;
+  h->has_cand = false; h->fnew_valid = false; h->fsum_valid = false;   // theta_i_new holds trial points now
   return check_info(h, "logL_clust_multi_GP");
 }
 
@@ -759,11 +759,20 @@ static int eval_indiv_common(mcb_handle* h, const double* theta3, bool want_grad
   H_CUDA(launch_indiv_eval(h->st, h->idata(), h->M, h->nmax, h->iwork(), dth, 0, want_grad, nullptr, nullptr, dsum,
                            h->info.p));
   ++h->launches;
-  info_to_double(h, dsum + 4);
-  MCB_TRY(comm_allreduce_sum(h, dsum, h->nranks > 1 ? 5 : 4));
-  info_from_double(h, dsum + 4);
+  MCB_TRY(comm_allreduce_sum(h, dsum, 4));
   H_CUDA(cudaMemcpyAsync(h->hbuf + 520, dsum, sizeof(double) * 4, cudaMemcpyDeviceToHost, h->st));
-  MCB_TRY(check_info(h, "logL_clust_multi_GP_common_hp_i", true));
+  if (h->nranks > 1) {
+    // A non-positive pivot makes that individual's F_i NaN (log of the pivot), so the all-reduced sum is not finite on
+    // EVERY rank: all ranks take the same branch without exchanging the local flag (which is cleared)
+    H_CUDA(cudaMemsetAsync(h->info.p, 0, sizeof(int), h->st));
+    H_CUDA(cudaStreamSynchronize(h->st));
+    if (!std::isfinite(h->hbuf[520])) {
+      h->err = "logL_clust_multi_GP_common_hp_i: a covariance matrix is not positive definite";
+      return MCB_ENOTPD;
+    }
+  } else {
+    MCB_TRY(check_info(h, "logL_clust_multi_GP_common_hp_i"));
+  }
   memcpy(out4, h->hbuf + 520, sizeof(double) * 4);
   return MCB_OK;
 }
@@ -796,24 +805,34 @@ static int elbo_impl(mcb_handle* h, const double* theta_k, const double* theta_i
     MCB_TRY(eval_mean_groups(h, G, groups.data(), gmap.data(), false, resident, f.data(), nullptr));
     for (int g = 0; g < G; ++g) sum_k += f[g];
   }
-  double* dsum = h->scal.p + 24;
-  H_CUDA(cudaMemsetAsync(dsum, 0, sizeof(double), h->st));
-  if (theta_i_dev == nullptr) {
-    vec_sum(h->st, h->M, h->Fi.p, dsum, &h->launches);
-  } else if (theta_i_dev == h->theta_i_new.p && h->fnew_valid) {
-    // the per-individual optimiser already evaluated F_i at the point it returned
-    vec_sum(h->st, h->M, h->Fnew.p, dsum, &h->launches);
+  double sum_i;
+  if (theta_i_dev == h->theta_i_new.p && h->fsum_valid) {
+    // shared theta_i: the optimiser's objective at the point it returned IS sum_i F_i(theta_i_new), already summed over ranks
+    sum_i = h->fsum_new;
   } else {
-    H_CUDA(launch_indiv_eval(h->st, h->idata(), h->M, h->nmax, h->iwork(), theta_i_dev, 3, 0, nullptr, nullptr, dsum,
-                             h->info.p));
-    ++h->launches;
+    double* dsum = h->scal.p + 24;
+    H_CUDA(cudaMemsetAsync(dsum, 0, sizeof(double), h->st));
+    if (theta_i_dev == nullptr) {
+      vec_sum(h->st, h->M, h->Fi.p, dsum, &h->launches);
+    } else if (theta_i_dev == h->theta_i_new.p && h->fnew_valid) {
+      // the per-individual optimiser already evaluated F_i at the point it returned
+      vec_sum(h->st, h->M, h->Fnew.p, dsum, &h->launches);
+    } else {
+      H_CUDA(launch_indiv_eval(h->st, h->idata(), h->M, h->nmax, h->iwork(), theta_i_dev, 3, 0, nullptr, nullptr, dsum,
+                               h->info.p));
+      ++h->launches;
+    }
+    MCB_TRY(comm_allreduce_sum(h, dsum, 1));
+    H_CUDA(cudaMemcpyAsync(h->hbuf + 600, dsum, sizeof(double), cudaMemcpyDeviceToHost, h->st));
+    if (h->nranks > 1) {
+      // as in eval_indiv_common: a non-positive pivot poisons the all-reduced sum on every rank
+      H_CUDA(cudaMemsetAsync(h->info.p, 0, sizeof(int), h->st));
+      H_CUDA(cudaStreamSynchronize(h->st));
+    } else {
+      MCB_TRY(check_info(h, "logL_monitoring_VEM"));
+    }
+    sum_i = h->hbuf[600];
   }
-  info_to_double(h, dsum + 1);
-  MCB_TRY(comm_allreduce_sum(h, dsum, h->nranks > 1 ? 2 : 1));
-  info_from_double(h, dsum + 1);
-  H_CUDA(cudaMemcpyAsync(h->hbuf + 600, dsum, sizeof(double), cudaMemcpyDeviceToHost, h->st));
-  MCB_TRY(check_info(h, "logL_monitoring_VEM", true));
-  const double sum_i = h->hbuf[600];
   if (!std::isfinite(sum_i)) { h->err = "logL_monitoring_VEM: covariance not positive definite"; return MCB_ENOTPD; }
   out[0] = -sum_k - sum_i;
   double ld = 0.0;
@@ -1160,6 +1179,7 @@ static int m_step_impl(mcb_handle* h, int common_hp_k, int common_hp_i, int* sta
   int nfev_i = 0, nit_i = 0, nfev_k = 0, nit_k = 0;
   int fw = 0;
   h->fnew_valid = false;
+  h->fsum_valid = false;
   // With individual-specific theta_i and a shared theta_k the two optimisations are independent (pen_diag only
   // replaces the third entry of theta_k afterwards, CF.R:666-668): run them concurrently.
   static const bool no_overlap = getenv("MCB_NO_OVERLAP") != nullptr;
@@ -1223,6 +1243,7 @@ static int m_step_impl(mcb_handle* h, int common_hp_k, int common_hp_i, int* sta
         st = lb_advance(opt, out[0], out + 1);
       }
       nfev_i = opt.nfev; nit_i = opt.iter;
+      if (st != LB_NONFINITE && std::isfinite(opt.f)) { h->fsum_new = opt.f; h->fsum_valid = true; }
       std::vector<double> rep(3 * (size_t)M);
       for (int i = 0; i < M; ++i) { rep[3 * i] = opt.x[0]; rep[3 * i + 1] = opt.x[1]; rep[3 * i + 2] = opt.x[2]; }
       H_CUDA(cudaMemcpyAsync(h->theta_i_new.p, rep.data(), sizeof(double) * 3 * M, cudaMemcpyHostToDevice, h->st));

@@ -50,6 +50,8 @@ struct mcb_handle {
   mcb::DevBuf<int> gscr_i;
   mcb::DevBuf<double> Fnew;   // F_i at theta_i_new as left by the per-individual M-step kernel
   bool fnew_valid = false;
+  double fsum_new = 0.0;     // sum over ALL individuals (all ranks) of F_i at theta_i_new as left by the shared-theta_i optimiser
+  bool fsum_valid = false;
   bool nfev_valid = false;   // nfev_i holds the counts of a previous per-individual M-step on this data set
 
   // ---- dense side ----
