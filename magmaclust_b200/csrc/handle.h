@@ -20,6 +20,12 @@ struct mcb_handle {
   // ---- communicator (NCCL, loaded lazily; nranks == 1 means single GPU) ----
   int nranks = 1, rank = 0;
   void* comm = nullptr;
+  // peer-memory mailboxes for the scalar all-reduces of the optimiser loops (comm.cu: tiny_allreduce_kernel)
+  double* mbox = nullptr;                  // this GPU's mailbox
+  double** mbox_peers = nullptr;           // device array [nranks]: every rank's mailbox as seen from this GPU
+  std::vector<void*> mbox_opened;          // pointers obtained with cudaIpcOpenMemHandle (closed in comm_destroy)
+  unsigned mbox_epoch = 0;
+  int* mbox_err = nullptr;                 // device flag: a peer did not show up in time
 
   // ---- training set (local shard) ----
   bool has_data = false;
