@@ -139,3 +139,47 @@ def test_m_step_with_more_than_eight_clusters(session):
     f_g = O.logL_GP_mod_common_hp_k(th_g[:2], ref["mean"], m_k, O.kernel_mu, ref["cov"], th_g[2])
     f_r = O.logL_GP_mod_common_hp_k(th_r[:2], ref["mean"], m_k, O.kernel_mu, ref["cov"], th_r[2])
     assert f_g <= f_r + 1e-5 * abs(f_r)   # the GPU optimum is not worse (it may be slightly better: end points are loose)
+
+
+def test_per_individual_optimiser_outcomes_are_reported(session):
+    """mcb_last_mstep_indiv: optim's counts and convergence code of every per-individual optimisation (CF.R:653-659 keeps only
+    `par`): evaluation counts add up to the M-step's total, every optimisation ends in a documented state, and the returned
+    theta_i is a point where the oracle's objective is not above its value at the start point"""
+    from magmaclust_b200 import magma
+    db, hp, tau, m_k = small_problem(M=16, K=3, n=(8, 20), n_grid=50, seed=41)
+    ref, got = _setup(session, db, hp, tau, m_k)
+    new = magma.m_step_VEM(db, hp, got, magma.kernel_mu, magma.kernel, m_k, True, False, session=session)
+    stats = session.eng.last_mstep_stats()
+    nfev, nit, status = session.eng.last_mstep_indiv()
+    assert nfev.shape == (16,) and np.all(nfev >= 1) and np.all(nit >= 0) and np.all(nit <= 100)
+    assert set(status.tolist()) <= {1, 2, 3, 4}, status          # converged / maxit / abnormal line search / zero gradient
+    assert int(nfev.sum()) == stats["nfev_i_sum"] and int(nfev.max()) == stats["nfev_i_max"]
+    per = O.split_db(db)
+    for i, d in per.items():
+        f_new = O.logL_clust_multi_GP(np.asarray(new["theta_i"][i]), d, ref, O.kernel)
+        f_old = O.logL_clust_multi_GP(np.asarray(hp["theta_i"][i]), d, ref, O.kernel)
+        assert f_new <= f_old + 1e-9 * abs(f_old), i
+
+
+def test_prediction_into_caller_owned_page_locked_buffers(session):
+    """mcb_predict with out = page-locked buffers (mcb_host_alloc) reused across calls, a batch large enough to be cut into
+    chunks whose copies overlap the next chunk: identical to the default path"""
+    from magmaclust_b200 import magma
+    db, hp, tau, m_k = small_problem(M=12, K=2, n=(8, 14), n_grid=60, seed=43, common_hp_i=True)
+    param = magma.e_step_VEM(db, m_k, magma.kernel_mu, magma.kernel, hp, tau, session=session)
+    grid = np.round(np.linspace(0, 10, 60), 3)
+    magma.posterior_mu_k(db, grid, m_k, magma.kernel_mu, magma.kernel, {"hp": hp, "param": param}, session=session)
+    B, nstar, K = 1300, 6, 2                                   # 1300 / 512 -> 2 chunks
+    rng = np.random.default_rng(2)
+    obs = np.sort(np.argsort(rng.random((B, 60)), axis=1)[:, :nstar], axis=1).astype(np.int32)
+    y = rng.standard_normal((B, nstar))
+    off = (np.arange(B + 1) * nstar).astype(np.int32)
+    pidx = np.arange(0, 60, 3, dtype=np.int32)
+    th = np.array([0.7, 0.4, 0.35])
+    e = session.eng
+    t0, m0, v0 = e.predict(off, obs.ravel(), y.ravel(), th, pidx)
+    out = (e.pinned_empty((B, K)), e.pinned_empty((B, K, pidx.shape[0])), e.pinned_empty((B, K, pidx.shape[0])))
+    for _ in range(2):
+        out[1][:] = np.nan
+        t1, m1, v1 = e.predict(off, obs.ravel(), y.ravel(), th, pidx, out=out)
+        assert np.array_equal(t1, t0) and np.array_equal(m1, m0) and np.array_equal(v1, v0)
