@@ -224,6 +224,8 @@ static void drop_graphs(mcb_handle* h) {
   h->eval_graphs.clear();
   if (h->mopt_exec) cudaGraphExecDestroy(h->mopt_exec);
   h->mopt_exec = nullptr;
+  if (h->iopt_exec) cudaGraphExecDestroy(h->iopt_exec);
+  h->iopt_exec = nullptr;
 }
 
 static int alloc_state(mcb_handle* h, int K) {
@@ -1096,6 +1098,125 @@ static int build_mean_opt_graph(mcb_handle* h) {
   return MCB_OK;
 }
 
+// ---- device-driven shared-theta_i optimisation --------------------------------------------------------------------------
+// The optimiser of m_step_VEM's common_hp_i branch (CF.R:645-650: ONE opm() over sum_i F_i) as a WHILE graph, like the theta_k
+// loop above: body = clear the 4 sums, the batched objective + gradient kernel over the local individuals (theta from device
+// memory), the peer-memory all-reduce of the sums when the individuals are sharded over GPUs, one L-BFGS update on one thread.
+// No host round trip per evaluation: at M = 100,000 on 8 GPUs the host turn-around (copy of 4 doubles, stream synchronisation,
+// next launches) was 75 of the 374 us per evaluation.
+// result: [0..2] theta, [3] nfev, [4] iterations, [5] status, [6] objective at theta, [7] evaluations with a non-finite sum
+__global__ void indiv_opt_init_kernel(const double* __restrict__ x0, double* state, double* itheta) {
+  if (threadIdx.x == 0) {
+    Lbfgs* o = reinterpret_cast<Lbfgs*>(state);
+    lb_init(*o, 3, x0);
+    itheta[0] = x0[0]; itheta[1] = x0[1]; itheta[2] = x0[2];
+  }
+}
+
+__global__ void indiv_opt_advance_kernel(double* state, const double* __restrict__ sum4, int* info, double* itheta,
+                                         cudaGraphConditionalHandle handle, double* result) {
+  __shared__ double words[kMoptWords];
+  for (int w = threadIdx.x; w < kMoptWords; w += blockDim.x) words[w] = state[w];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    Lbfgs& o = *reinterpret_cast<Lbfgs*>(words);
+    double f = sum4[0];
+    double g[3] = {sum4[1], sum4[2], sum4[3]};
+    // a trial point where some Psi_i is not positive definite leaves NaN in that F_i, hence in the (all-reduced) sum on every
+    // rank: an infinite objective for the line search (the reference's solve() would fail over to ginv, CF.R:142)
+    if (!isfinite(f)) { f = INFINITY; g[0] = g[1] = g[2] = 0.0; result[7] += 1.0; }
+    *info = 0;
+    const int st = lb_advance(o, f, g);
+    itheta[0] = o.x[0]; itheta[1] = o.x[1]; itheta[2] = o.x[2];
+    result[0] = o.x[0]; result[1] = o.x[1]; result[2] = o.x[2];
+    result[3] = (double)o.nfev; result[4] = (double)o.iter; result[5] = (double)st; result[6] = o.f;
+    cudaGraphSetConditional(handle, st == LB_EVAL ? 1u : 0u);
+  }
+  __syncthreads();
+  for (int w = threadIdx.x; w < kMoptWords; w += blockDim.x) state[w] = words[w];
+}
+
+__global__ void fill_theta_kernel(double* __restrict__ theta, int M, const double* __restrict__ x) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < M) { theta[3 * (size_t)i] = x[0]; theta[3 * (size_t)i + 1] = x[1]; theta[3 * (size_t)i + 2] = x[2]; }
+}
+
+static int build_indiv_opt_graph(mcb_handle* h) {
+  H_CUDA(h->iopt_state.ensure(kMoptWords + 16 + 8));
+  if (!h->st_cap) H_CUDA(cudaStreamCreateWithFlags(&h->st_cap, cudaStreamNonBlocking));
+  double* state = h->iopt_state.p;
+  double* result = state + kMoptWords;
+  double* itheta = result + 16;
+  double* dsum = h->scal.p + 16;
+  const double* x0 = h->scal.p + 32;
+  cudaGraph_t graph = nullptr;
+  const long long before = h->launches;
+  H_CUDA(cudaStreamBeginCapture(h->st, cudaStreamCaptureModeThreadLocal));
+  auto fail = [&](const char* what, cudaError_t ce) {
+    cudaGraph_t g2 = nullptr;
+    cudaStreamEndCapture(h->st, &g2);
+    if (g2) cudaGraphDestroy(g2);
+    h->launches = before;
+    h->err = std::string("theta_i loop graph: ") + what + ": " + cudaGetErrorString(ce);
+    cudaGetLastError();
+    return MCB_ECUDA;
+  };
+  cudaError_t ce;
+  if ((ce = cudaMemsetAsync(result, 0, sizeof(double) * 16, h->st)) != cudaSuccess) return fail("memset", ce);
+  indiv_opt_init_kernel<<<1, 32, 0, h->st>>>(x0, state, itheta);
+  ++h->launches;
+  h->iopt_pre = h->launches - before;
+  cudaStreamCaptureStatus cst;
+  const cudaGraphNode_t* deps = nullptr;
+  size_t ndeps = 0;
+  if ((ce = cudaStreamGetCaptureInfo(h->st, &cst, nullptr, &graph, &deps, &ndeps)) != cudaSuccess) return fail("capture info", ce);
+  cudaGraphConditionalHandle handle;
+  if ((ce = cudaGraphConditionalHandleCreate(&handle, graph, 1, cudaGraphCondAssignDefault)) != cudaSuccess) return fail("handle", ce);
+  cudaGraphNodeParams np = {};
+  np.type = cudaGraphNodeTypeConditional;
+  np.conditional.handle = handle;
+  np.conditional.type = cudaGraphCondTypeWhile;
+  np.conditional.size = 1;
+  cudaGraphNode_t loop;
+  if ((ce = cudaGraphAddNode(&loop, graph, deps, ndeps, &np)) != cudaSuccess) return fail("conditional node", ce);
+  cudaGraph_t body = np.conditional.phGraph_out[0];
+  {
+    const long long b0 = h->launches;
+    if ((ce = cudaStreamBeginCaptureToGraph(h->st_cap, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal)) != cudaSuccess)
+      return fail("body capture", ce);
+    cudaStream_t s = h->st_cap;
+    cudaError_t ie = cudaMemsetAsync(dsum, 0, sizeof(double) * 4, s);
+    if (ie == cudaSuccess)
+      ie = launch_indiv_eval(s, h->idata(), h->M, h->nmax, h->iwork(), itheta, 0, 1, nullptr, nullptr, dsum, h->info.p);
+    ++h->launches;
+    bool ok = comm_allreduce_small_on(h, s, dsum, 4);
+    if (h->nranks > 1) ++h->launches;
+    indiv_opt_advance_kernel<<<1, 32, 0, s>>>(state, dsum, h->info.p, itheta, handle, result);
+    ++h->launches;
+    cudaError_t ee = cudaStreamEndCapture(s, nullptr);
+    h->iopt_body = h->launches - b0;
+    if (ie != cudaSuccess) return fail("evaluation in body", ie);
+    if (!ok) return fail("peer all-reduce in body", cudaErrorNotSupported);
+    if (ee != cudaSuccess) return fail("body end capture", ee);
+  }
+  if ((ce = cudaStreamUpdateCaptureDependencies(h->st, &loop, 1, cudaStreamSetCaptureDependencies)) != cudaSuccess)
+    return fail("dependencies", ce);
+  fill_theta_kernel<<<(h->M + 255) / 256, 256, 0, h->st>>>(h->theta_i_new.p, h->M, result);
+  if ((ce = cudaMemcpyAsync(h->hbuf + 9000, result, sizeof(double) * 8, cudaMemcpyDeviceToHost, h->st)) != cudaSuccess)
+    return fail("result copy", ce);
+  h->launches = before;
+  H_CUDA(cudaStreamEndCapture(h->st, &graph));
+  cudaError_t inst = cudaGraphInstantiate(&h->iopt_exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (inst != cudaSuccess) {
+    h->iopt_exec = nullptr;
+    h->err = std::string("theta_i loop graph: instantiate: ") + cudaGetErrorString(inst);
+    cudaGetLastError();
+    return MCB_ECUDA;
+  }
+  return MCB_OK;
+}
+
 // Runs the whole optimisation; out[0..2] = theta, nfev / iterations returned through the pointers. Enqueue only when
 // !wait (the caller synchronises h->st later and then calls with collect = true).
 static int mean_opt_launch(mcb_handle* h, cudaStream_t stream = nullptr) {
@@ -1230,6 +1351,25 @@ static int m_step_impl(mcb_handle* h, int common_hp_k, int common_hp_i, int* sta
         H_CUDA(cudaStreamSynchronize(h->st));
       }
       memcpy(x0, h->hbuf, sizeof x0);
+      // Device-side loop (WHILE graph) unless switched off, unavailable (several ranks without peer mailboxes) or it failed
+      // to build once; the host loop below is the same state machine with one launch + one round trip per evaluation.
+      static const bool host_loop_i = getenv("MCB_HOST_THETA_I") != nullptr || getenv("MCB_NO_GRAPH") != nullptr;
+      bool done = false;
+      if (!host_loop_i && !h->iopt_failed && (h->nranks == 1 || h->mbox_peers != nullptr)) {
+        if (h->nranks == 1) H_CUDA(cudaMemcpyAsync(h->scal.p + 32, h->theta_i.p, sizeof(double) * 3, cudaMemcpyDeviceToDevice, h->st));
+        if (!h->iopt_exec && build_indiv_opt_graph(h) != MCB_OK) {
+          h->iopt_failed = true;   // (every rank builds the same graph from the same state: all fail or none)
+        } else {
+          H_CUDA(cudaGraphLaunch(h->iopt_exec, h->st));
+          H_CUDA(cudaStreamSynchronize(h->st));
+          const double* r = h->hbuf + 9000;
+          nfev_i = (int)r[3]; nit_i = (int)r[4];
+          h->launches += h->iopt_pre + (long long)nfev_i * h->iopt_body + 1;
+          if ((int)r[5] != LB_NONFINITE && std::isfinite(r[6])) { h->fsum_new = r[6]; h->fsum_valid = true; }
+          done = true;
+        }
+      }
+      if (!done) {
       Lbfgs opt;
       lb_init(opt, 3, x0);
       int st = LB_EVAL;
@@ -1248,6 +1388,7 @@ static int m_step_impl(mcb_handle* h, int common_hp_k, int common_hp_i, int* sta
       for (int i = 0; i < M; ++i) { rep[3 * i] = opt.x[0]; rep[3 * i + 1] = opt.x[1]; rep[3 * i + 2] = opt.x[2]; }
       H_CUDA(cudaMemcpyAsync(h->theta_i_new.p, rep.data(), sizeof(double) * 3 * M, cudaMemcpyHostToDevice, h->st));
       H_CUDA(cudaStreamSynchronize(h->st));
+      }
     } else if (!overlap) {
       H_CUDA(launch_indiv_mstep(h->st, h->idata(), M, h->nmax, h->iwork(), h->theta_i.p, h->theta_i_new.p, 100,
                                 h->nfev_i.p, h->niter_i.p, h->status_i.p, h->mstep_ctl.p, 0, order, h->Fnew.p, &fw));

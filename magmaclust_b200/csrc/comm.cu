@@ -76,10 +76,15 @@ constexpr int kMboxMaxRanks = 32;
 // mailbox layout: vals[2][kMboxMaxRanks][kMboxVals] doubles, then flags[2][kMboxMaxRanks] unsigned
 constexpr size_t kMboxDoubles = 2 * kMboxMaxRanks * kMboxVals + 2 * kMboxMaxRanks;
 
-__global__ void tiny_allreduce_kernel(double* buf, int count, double* const* peers, int rank, int nranks, unsigned epoch,
-                                      int* err) {
+__global__ void tiny_allreduce_kernel(double* buf, int count, double* const* peers, int rank, int nranks,
+                                      unsigned* epoch_ctr, int* err) {
   __shared__ double got[kMboxMaxRanks][kMboxVals];
+  __shared__ unsigned epoch_s;
   const int r = threadIdx.x;
+  // the call counter lives on the device (every rank makes the same sequence of calls, also from inside graph loops)
+  if (r == 0) epoch_s = ++(*epoch_ctr);
+  __syncthreads();
+  const unsigned epoch = epoch_s;
   const int par = epoch & 1;
   if (r < nranks) {
     double* mb = peers[r];
@@ -154,7 +159,7 @@ static int mbox_setup(mcb_handle* h) {
     v = 1.0;
   }
   if (v != 0.0 || cudaMalloc(&h->mbox_peers, sizeof(double*) * R) != cudaSuccess ||
-      cudaMalloc(&h->mbox_err, sizeof(int)) != cudaSuccess) {
+      cudaMalloc(&h->mbox_err, sizeof(int)) != cudaSuccess || cudaMalloc(&h->mbox_epoch_dev, sizeof(unsigned)) != cudaSuccess) {
     for (void* p : h->mbox_opened) cudaIpcCloseMemHandle(p);
     h->mbox_opened.clear();
     if (h->mbox_peers) { cudaFree(h->mbox_peers); h->mbox_peers = nullptr; }
@@ -162,16 +167,23 @@ static int mbox_setup(mcb_handle* h) {
   }
   cudaMemcpy(h->mbox_peers, ptrs.data(), sizeof(double*) * R, cudaMemcpyHostToDevice);
   cudaMemset(h->mbox_err, 0, sizeof(int));
-  h->mbox_epoch = 0;
+  cudaMemset(h->mbox_epoch_dev, 0, sizeof(unsigned));
   return MCB_OK;
+}
+
+// the peer-memory all-reduce on a given stream (a capture stream of a graph body); false when it is not available
+bool comm_allreduce_small_on(mcb_handle* h, cudaStream_t s, double* buf, int count) {
+  if (h->nranks <= 1) return true;
+  if (!h->mbox_peers || count > kMboxVals) return false;
+  tiny_allreduce_kernel<<<1, kMboxMaxRanks, 0, s>>>(buf, count, h->mbox_peers, h->rank, h->nranks, h->mbox_epoch_dev, h->mbox_err);
+  return cudaGetLastError() == cudaSuccess;
 }
 
 int comm_allreduce_sum(mcb_handle* h, double* buf, size_t count) {
   if (h->nranks <= 1 || count == 0) return MCB_OK;
   if (h->mbox_peers && count <= (size_t)kMboxVals) {
-    ++h->mbox_epoch;
-    tiny_allreduce_kernel<<<1, kMboxMaxRanks, 0, h->st>>>(buf, (int)count, h->mbox_peers, h->rank, h->nranks, h->mbox_epoch,
-                                                          h->mbox_err);
+    tiny_allreduce_kernel<<<1, kMboxMaxRanks, 0, h->st>>>(buf, (int)count, h->mbox_peers, h->rank, h->nranks,
+                                                          h->mbox_epoch_dev, h->mbox_err);
     if (cudaGetLastError() != cudaSuccess) { h->err = "tiny_allreduce_kernel: launch failed"; return MCB_ECUDA; }
     return MCB_OK;
   }
@@ -216,6 +228,8 @@ void comm_destroy(mcb_handle* h) {
   h->mbox_opened.clear();
   if (h->mbox_peers) cudaFree(h->mbox_peers);
   if (h->mbox_err) cudaFree(h->mbox_err);
+  if (h->mbox_epoch_dev) cudaFree(h->mbox_epoch_dev);
+  h->mbox_epoch_dev = nullptr;
   if (h->mbox) cudaFree(h->mbox);
   h->mbox_peers = nullptr; h->mbox_err = nullptr; h->mbox = nullptr;
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t)h->comm);

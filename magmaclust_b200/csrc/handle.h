@@ -24,7 +24,7 @@ struct mcb_handle {
   double* mbox = nullptr;                  // this GPU's mailbox
   double** mbox_peers = nullptr;           // device array [nranks]: every rank's mailbox as seen from this GPU
   std::vector<void*> mbox_opened;          // pointers obtained with cudaIpcOpenMemHandle (closed in comm_destroy)
-  unsigned mbox_epoch = 0;
+  unsigned* mbox_epoch_dev = nullptr;      // call counter (device resident: the all-reduce also runs inside graph loops)
   int* mbox_err = nullptr;                 // device flag: a peer did not show up in time
 
   // ---- training set (local shard) ----
@@ -79,6 +79,11 @@ struct mcb_handle {
   int mopt_budget = 0;                    // ws.max_ctas it was captured with
   long long mopt_pre = 0, mopt_body = 0;  // kernels before the loop / per evaluation
   mcb::DevBuf<double> mopt_state;         // the L-BFGS state (Lbfgs struct) + result slots
+  // device-driven shared-theta_i optimisation (common_hp_i): the same kind of WHILE graph around the batched evaluation
+  cudaGraphExec_t iopt_exec = nullptr;
+  bool iopt_failed = false;               // the graph could not be built once: stay on the host loop
+  long long iopt_pre = 0, iopt_body = 0;
+  mcb::DevBuf<double> iopt_state;
   cudaStream_t st_cap = nullptr;          // capture-only stream for conditional-node bodies
   mcb::DenseWs ws;       // training path only: its buffers are baked into the captured graphs (sized by alloc_state, never grown later)
   mcb::DenseWs ws_aux;   // posterior_mu_k on another grid and the stand-alone kern_to_inv / dmvnorm: may grow at any time
@@ -118,6 +123,7 @@ enum Phase { PH_INDIV = 0, PH_DENSE = 1, PH_TAU = 2, PH_MSTEP_I = 3, PH_MSTEP_K 
 
 // NCCL shim (comm.cu): no-ops when the handle is single-rank
 int comm_allreduce_sum(mcb_handle* h, double* buf, size_t count);
+bool comm_allreduce_small_on(mcb_handle* h, cudaStream_t s, double* buf, int count);   // peer-memory version, any stream
 // cluster ownership for large grids: block z lives on rank z % nranks
 int comm_reduce_to_owners(mcb_handle* h, double* buf, size_t count, long long stride, int Z);
 int comm_bcast_from_owners(mcb_handle* h, double* buf, size_t count, long long stride, int Z);
