@@ -270,5 +270,8 @@ extern "C" int mcb_comm_init(mcb_handle* h, int nranks, int rank, const unsigned
   h->comm = c;
   h->nranks = nranks;
   h->rank = rank;
+  // a shared-theta_i loop graph captured while the handle was single-rank has no all-reduce in its body
+  if (h->iopt_exec) { cudaGraphExecDestroy(h->iopt_exec); h->iopt_exec = nullptr; }
+  h->iopt_failed = false;
   return mcb::mbox_setup(h);
 }
