@@ -56,7 +56,7 @@ int main() {
     cudaFree(dA); cudaFree(dB); cudaFree(dC);
   }
   // ---- spd_inverse
-  for (int N : {5, 20, 32, 33, 64, 100, 195, 401, 800, 1000, 1111}) {
+  for (int N : {5, 20, 32, 33, 64, 100, 195, 401, 513, 700, 768, 800, 1000, 1111}) {
     for (int Z : {1, 3}) {
       if (N > 768 && Z == 3 && N != 800) continue;   // the large-grid (multi-launch) path: one batched case is enough
       int ld = (N + 15) & ~15;
