@@ -25,13 +25,35 @@
 // E block reduction -> f, g.   Flops as executed ~ n^3/2 + n^3 + n^3/2 FMAs (reference: n^3 + 4 n^3 + 4 n^3 flops).
 #pragma once
 #include "common.cuh"
+#include "exp_tab.h"
 #include "indiv_eval.cuh"  // dmma884_i, cta_sum_v, tsync, MCB_STAMP
 
 namespace mcb {
 
 // exp() out of line: the evaluation kernels are instruction-fetch bound (ncu: 24 % of the warp samples stall on
 // no_inst at 4 CTAs per SM, I-cache hit rate 73 %), and every inlined exp is ~35 instructions at ~30 call sites
+// and a table-driven one (exp_tab.h: 24 instead of 46 instructions per call; MCB_LIBM_EXP restores libdevice's for A/B runs)
+#ifdef MCB_LIBM_EXP
 __device__ __noinline__ double ev_exp(double x) { return exp(x); }
+#else
+__device__ __noinline__ double ev_exp(double x) { return exp_tab(x, kExpTab); }
+#endif
+// two at a time: half the calls, two independent dependency chains per call (the kernels stall mostly on fixed-latency
+// dependencies: profiles/r02s2_eval2_c3_ncu.txt, "wait")
+#ifdef MCB_LIBM_EXP
+__device__ __noinline__ double2 ev_exp2(double2 x) { return make_double2(exp(x.x), exp(x.y)); }
+#else
+__device__ __noinline__ double2 ev_exp2(double2 x) { return make_double2(exp_tab(x.x, kExpTab), exp_tab(x.y, kExpTab)); }
+#endif
+struct Exp4 { double a, b, c, d; };   // passed and returned in registers
+__device__ __noinline__ Exp4 ev_exp4(Exp4 x) {
+  Exp4 r;
+  r.a = exp_tab(x.a, kExpTab);
+  r.b = exp_tab(x.b, kExpTab);
+  r.c = exp_tab(x.c, kExpTab);
+  r.d = exp_tab(x.d, kExpTab);
+  return r;
+}
 __device__ __noinline__ double ev_log(double x) { return log(x); }
 
 __device__ __forceinline__ double fast_rcp(double d) {
@@ -156,6 +178,25 @@ __device__ void indiv_eval_v2(const EvalSm2<NT>& s, int n, const int (&bI)[E], c
     }
 #pragma unroll
     for (int a = 0; a < 4; ++a) {
+      // the four SE values of this row of the block, two per call (lanes outside the matrix compute exp(th1): harmless)
+      double kr[4];
+#ifndef MCB_EXP_SCALAR
+      // measured on a B200 (gpurun_out/r02s3_exp*.log): four per call is the faster form at n = 50 (theta_i phase of C2
+      // 4.26 -> 4.10 ms with pairs, 4.03 ms with fours), two per call at n = 30 (one evaluation of C3 2.48 -> 2.38 / 2.41 ms)
+      if constexpr (NT >= 7) {
+        const double d0 = tr[a] - tc[0], d1 = tr[a] - tc[1], d2 = tr[a] - tc[2], d3 = tr[a] - tc[3];
+        const Exp4 k4 = ev_exp4(Exp4{th1 - hl * (d0 * d0), th1 - hl * (d1 * d1), th1 - hl * (d2 * d2), th1 - hl * (d3 * d3)});
+        kr[0] = k4.a; kr[1] = k4.b; kr[2] = k4.c; kr[3] = k4.d;
+      } else {
+#pragma unroll
+        for (int b = 0; b < 4; b += 2) {
+          const double d0 = tr[a] - tc[b], d1 = tr[a] - tc[b + 1];
+          const double2 k2 = ev_exp2(make_double2(th1 - hl * (d0 * d0), th1 - hl * (d1 * d1)));
+          kr[b] = k2.x;
+          kr[b + 1] = k2.y;
+        }
+      }
+#endif
 #pragma unroll
       for (int b = 0; b < 4; ++b) {
         double v = 0.0, kv = 0.0;
@@ -166,8 +207,12 @@ __device__ void indiv_eval_v2(const EvalSm2<NT>& s, int n, const int (&bI)[E], c
               v = dg;
               kv = e1;
             } else {
+#ifdef MCB_EXP_SCALAR
               const double d = tr[a] - tc[b];
               kv = ev_exp(th1 - hl * (d * d));
+#else
+              kv = kr[b];
+#endif
               v = kv;
             }
           } else if (r < ntot && c < n) {
@@ -424,6 +469,25 @@ __device__ void indiv_eval_v2(const EvalSm2<NT>& s, int n, const int (&bI)[E], c
         }
         const double wgt = (tj == ti) ? 1.0 : 2.0;
         const double hq[2] = {h.x + h2.x, h.y + h2.y};
+#ifndef MCB_EXP_SCALAR
+        {
+          const int c0 = 8 * tj + 2 * gc;
+          const double d0 = trv - ((c0 < n) ? s.t[c0] : 0.0), d1 = trv - ((c0 + 1 < n) ? s.t[c0 + 1] : 0.0);
+          const double gq[2] = {hl * (d0 * d0), hl * (d1 * d1)};
+          const double2 k2 = ev_exp2(make_double2(th1 - gq[0], th1 - gq[1]));
+          const double kq[2] = {k2.x, k2.y};
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            const int c = c0 + q;
+            if (r < n && c < n) {
+              const double kv = (r == c) ? e1 : kq[q];
+              v13[9] += wgt * hq[q] * kv;
+              v13[10] += wgt * hq[q] * (gq[q] * kv);
+              if (r == c) v13[8] += hq[q];
+            }
+          }
+        }
+#else
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
           const int c = 8 * tj + 2 * gc + q;
@@ -436,6 +500,7 @@ __device__ void indiv_eval_v2(const EvalSm2<NT>& s, int n, const int (&bI)[E], c
             if (r == c) v13[8] += hq[q];
           }
         }
+#endif
       }
     }
   }
