@@ -116,9 +116,33 @@ __device__ __forceinline__ void eval2_load(const EvalSm2<NT>& s, int n, const do
     s.c1[a] = c1g[a];
   }
   tsync<TT>();
-  for (int e = threadIdx.x; e < n * n; e += TT) {
-    const int a = e / n, b = e - a * n;
-    s.S[a * G::LDM + b] = c2g[e];
+  // S: a warp per row, lanes over the columns, RB rows in flight per thread (independent loads issued back to back, no
+  // division). The element-per-thread loop this replaces (e / n, one dependent load per trip) was 12 % of the warp samples
+  // of a batched evaluation at n = 30 (profiles/r02s3_eval2_c3_lines.txt).
+  constexpr int NW = TT / 32;
+  constexpr int CB = (8 * NT + 31) / 32;
+  constexpr int RB = (NT <= 4) ? 8 : 4;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int a0 = warp; a0 < n; a0 += RB * NW) {
+    double v[RB][CB];
+#pragma unroll
+    for (int i = 0; i < RB; ++i) {
+      const int a = a0 + i * NW;
+#pragma unroll
+      for (int j = 0; j < CB; ++j) {
+        const int b = lane + 32 * j;
+        v[i][j] = (a < n && b < n) ? c2g[a * n + b] : 0.0;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < RB; ++i) {
+      const int a = a0 + i * NW;
+#pragma unroll
+      for (int j = 0; j < CB; ++j) {
+        const int b = lane + 32 * j;
+        if (a < n && b < n) s.S[a * G::LDM + b] = v[i][j];
+      }
+    }
   }
   tsync<TT>();
 }
