@@ -1407,12 +1407,15 @@ static int m_step_impl(mcb_handle* h, int common_hp_k, int common_hp_i, int* sta
     H_CUDA(cudaStreamWaitEvent(h->st2, h->ev_fork, 0));
     {
       PhaseScope ps(h, PH_MSTEP_I, h->st2);
-      // SMs left to the theta_k chain: one per CTA of the slab inverse (they must be co-resident), i.e. two column
-      // parts per 32-row slab when that stays below ~a quarter of the GPU; the GEMMs / reductions between two
+      // SMs left to the theta_k chain: one per CTA of the slab inverse (they must be co-resident), i.e. three (else two)
+      // column parts per 32-row slab when that stays below ~a quarter of the GPU; the GEMMs / reductions between two
       // inverses share the same SMs
       const int nblk = (h->N + kNB - 1) / kNB;
       static const int extra = getenv("MCB_RESERVE_EXTRA") ? atoi(getenv("MCB_RESERVE_EXTRA")) : -1;
-      const int reserve = extra >= 0 ? std::min(nblk + extra, 96) : (2 * nblk <= 40 ? 2 * nblk : nblk);
+      // (re-tuned after the theta_i kernel got faster than the theta_k chain, gpurun_out/r02s3_resv*.log: three column
+      // parts = 39 SMs and 8 one-CTA SMs at N = 401, M = 1000: 5.45 -> 5.25 ms per iteration)
+      const int reserve = extra >= 0 ? std::min(nblk + extra, 96)
+                                     : (3 * nblk <= 40 ? 3 * nblk : (2 * nblk <= 40 ? 2 * nblk : nblk));
       H_CUDA(launch_indiv_mstep(h->st2, h->idata(), M, h->nmax, h->iwork(), h->theta_i.p, h->theta_i_new.p, 100,
                                 h->nfev_i.p, h->niter_i.p, h->status_i.p, h->mstep_ctl.p, reserve, order, h->Fnew.p, &fw));
       h->fnew_valid = fw != 0;

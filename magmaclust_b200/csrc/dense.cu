@@ -45,17 +45,17 @@ __global__ void se_build_kernel(double* __restrict__ Kmat, double* __restrict__ 
   const double sg = theta[(size_t)z * theta_stride + 2];
   const double hl = exp(-b) / 2.0;
   const double d = grid[i] - grid[j];
-  const double d2 = d * d;
+  const double g = hl * (d * d);
+  // one exp per element: dK/db = e^a g e^-g = g K off the diagonal (the per-individual kernels use the same form)
   double k, dk1, dk2;
   if (i == j) {
     dk1 = exp(a);
     k = dk1 + sg * sg;
     dk2 = 0.0;
   } else {
-    k = exp(a - hl * d2);
+    k = exp(a - g);
     dk1 = k;
-    const double g = 0.5 * exp(-b) * d2;
-    dk2 = exp(a) * g * exp(-g);
+    dk2 = g * k;
   }
   Kmat[z * stride + (size_t)i * ld + j] = k;
   if (D1) D1[z * stride + (size_t)i * ld + j] = dk1;

@@ -888,7 +888,7 @@ cudaError_t launch_indiv_mstep(cudaStream_t s, const IndivData& dd, int M, int n
     int solo = 0, solo_items = 0;                                                                                      \
     if (order && per_sm > 1 && M >= 2 * sms) {                                                                         \
       /* solo SMs pay off while the optimisations outnumber the CTA slots only a few times (tail-bound regime) */      \
-      solo = solo_sms >= 0 ? solo_sms : ((long long)M < 8LL * per_sm * sms ? (sms - reserve_sms) / 8 : 0);            \
+      solo = solo_sms >= 0 ? solo_sms : ((long long)M < 8LL * per_sm * sms ? (sms - reserve_sms + 7) / 14 : 0);        \
       if (solo > sms - reserve_sms - 1) solo = sms - reserve_sms - 1;                                                  \
       solo_items = solo_mult * solo * solo_ctas;                                                                       \
     }                                                                                                                  \
