@@ -705,6 +705,15 @@ def run_ours(args):
                     "all": kernels, "phase_ms_per_step": {k: v / args.steps for k, v in phase_ms.items()},
                     "note": "theta_i (mstep_indiv) and theta_k (mstep_mean) optimisations run concurrently on two streams; "
                             "the theta_k chain is latency-bound (N sequential pivots per inverse)"}
+        if not common_i:
+            # the persistent theta_i kernel leaves whole SMs to the slab inverse of the theta_k chain (api.cu, m_step_impl:
+            # three / two / one column part per 32-row slab while that stays <= 40 SMs); `peak` above is the whole GPU's
+            nblk = (int(sh["N"]) + 31) // 32
+            reserve = 3 * nblk if 3 * nblk <= 40 else (2 * nblk if 2 * nblk <= 40 else nblk)
+            import torch
+            sms = torch.cuda.get_device_properties(local).multi_processor_count
+            roofline["sm_share"] = {"sms": sms, "left_to_theta_k_chain": reserve, "kernel_sms": sms - reserve,
+                                    "frac_on_its_sms": roofline["frac"] * sms / (sms - reserve)}
 
     # ---- the dominant kernel away from the latency-bound benchmark size (reported beside the roofline, N = 1 only) -----
     # At 1000 individuals per GPU the per-individual M-step is bounded by its longest optimisation (82 sequential
