@@ -33,6 +33,13 @@
 #define LB_LOOP
 #endif
 
+// full unrolling of the compile-time-D loops (device passes only: the host compiler does not know the pragma)
+#ifdef __CUDA_ARCH__
+#define LB_UNROLL _Pragma("unroll")
+#else
+#define LB_UNROLL
+#endif
+
 namespace mcb {
 
 constexpr int LB_MAXD = 3;
@@ -258,7 +265,8 @@ MCB_HD_BIG void lb_begin_search(Lbfgs& o) {
 
 // Feed the value and gradient at the current o.x. Returns the new status; while it is LB_EVAL the
 // caller evaluates at o.x again. On termination o.x/o.f hold the best accepted point.
-MCB_HD int lb_advance(Lbfgs& o, double f, const double* g) {
+// (any D <= LB_MAXD, loops over D rolled in device code; lb_advance below dispatches to the compile-time-D version)
+MCB_HD int lb_advance_any(Lbfgs& o, double f, const double* g) {
   const int D = o.D;
   const double epsmch = 2.220446049250313e-16;
   o.nfev++;
@@ -329,6 +337,175 @@ MCB_HD int lb_advance(Lbfgs& o, double f, const double* g) {
   }
   lb_begin_search(o);
   return o.status;
+}
+
+// ---- the same state machine with D known at compile time ----------------------------------------------------------
+// In device code the update above runs on ONE thread between two evaluations while the rest of the CTA waits: 7.2 k cycles
+// alone on an SM, 13.7 k next to three other CTAs (profiles/r01e_eval_phases.txt) = 16 % of an evaluation. With a run-time D
+// the short loops over D either unroll with remainder code (4,505 SASS instructions) or stay rolled, and then q[], s[], y[],
+// alpha[] are indexed dynamically and live in LOCAL memory (184 bytes of stack in the M-step kernel): every step of the
+// two-loop recursion waits for a local-memory round trip. Here D and the memory depth are constants: all loops unroll
+// exactly, every temporary is a register, the ring index needs no modulo. Same operations in the same order as above
+// (tests/test_host_logic.py runs both side by side and compares the trajectories bit for bit on the host).
+template <int DT>
+MCB_HD void lb_direction_t(Lbfgs& o) {
+  double q[DT], alpha[LB_MEM];
+  const int col = o.col, head = o.head;
+LB_UNROLL
+  for (int j = 0; j < DT; ++j) q[j] = o.g[j];
+LB_UNROLL
+  for (int c = LB_MEM - 1; c >= 0; --c) {
+    alpha[c] = 0.0;
+    if (c < col) {
+      int p = head + c;
+      if (p >= LB_MEM) p -= LB_MEM;
+      double a = 0;
+LB_UNROLL
+      for (int j = 0; j < DT; ++j) a += o.S[p][j] * q[j];
+      a *= o.rho[p];
+      alpha[c] = a;
+LB_UNROLL
+      for (int j = 0; j < DT; ++j) q[j] -= a * o.Y[p][j];
+    }
+  }
+  if (col > 0) {
+    int p = head + col - 1;
+    if (p >= LB_MEM) p -= LB_MEM;
+    double yy = 0;
+LB_UNROLL
+    for (int j = 0; j < DT; ++j) yy += o.Y[p][j] * o.Y[p][j];
+    const double h0 = 1.0 / (o.rho[p] * yy);  // s'y / y'y
+LB_UNROLL
+    for (int j = 0; j < DT; ++j) q[j] *= h0;
+  }
+LB_UNROLL
+  for (int c = 0; c < LB_MEM; ++c) {
+    if (c < col) {
+      int p = head + c;
+      if (p >= LB_MEM) p -= LB_MEM;
+      double b = 0;
+LB_UNROLL
+      for (int j = 0; j < DT; ++j) b += o.Y[p][j] * q[j];
+      b *= o.rho[p];
+LB_UNROLL
+      for (int j = 0; j < DT; ++j) q[j] += (alpha[c] - b) * o.S[p][j];
+    }
+  }
+LB_UNROLL
+  for (int j = 0; j < DT; ++j) o.d[j] = -q[j];
+}
+
+template <int DT>
+MCB_HD void lb_begin_search_t(Lbfgs& o) {
+  for (;;) {
+    lb_direction_t<DT>(o);
+    double gd = 0, dn = 0;
+LB_UNROLL
+    for (int j = 0; j < DT; ++j) { gd += o.g[j] * o.d[j]; dn += o.d[j] * o.d[j]; }
+    if (gd >= 0.0) {
+      if (o.col == 0) { o.status = LB_ABNORMAL; return; }
+      o.col = 0; o.head = 0;
+      continue;
+    }
+    o.gd = gd; o.gdold = gd; o.dnorm = sqrt(dn);
+    break;
+  }
+  const double stpmx = 1e10;
+  o.stp = (o.iter == 0) ? fmin(1.0 / o.dnorm, stpmx) : 1.0;
+LB_UNROLL
+  for (int j = 0; j < DT; ++j) { o.xb[j] = o.x[j]; o.gb[j] = o.g[j]; }
+  o.fb = o.f;
+  ls_start(o.ls, o.f, o.gd, o.stp, stpmx);
+  o.nls = 0;
+LB_UNROLL
+  for (int j = 0; j < DT; ++j) o.x[j] = o.xb[j] + o.stp * o.d[j];
+  o.status = LB_EVAL;
+}
+
+template <int DT>
+MCB_HD int lb_advance_t(Lbfgs& o, double f, const double* g) {
+  const double epsmch = 2.220446049250313e-16;
+  o.nfev++;
+  if (!o.started) {
+    o.started = 1;
+    o.f = f;
+    bool fin = isfinite(f);
+    double pg = 0;
+LB_UNROLL
+    for (int j = 0; j < DT; ++j) { o.g[j] = g[j]; fin = fin && isfinite(g[j]); pg = fmax(pg, fabs(g[j])); }
+    if (!fin) { o.status = LB_NONFINITE; return o.status; }
+    if (pg <= 0.0) { o.status = LB_ZEROGRAD; return o.status; }
+    lb_begin_search_t<DT>(o);
+    return o.status;
+  }
+  double gd = 0;
+LB_UNROLL
+  for (int j = 0; j < DT; ++j) gd += g[j] * o.d[j];
+  o.nls++;
+  LsStatus st;
+  const bool fin = isfinite(f) && isfinite(gd);
+  if (!fin) {
+    st = (o.nls >= 20) ? LS_ERROR : LS_CONTINUE;
+    o.stp *= 0.5;
+    o.ls.stpmax = o.stp;
+  } else {
+    st = ls_iterate(o.ls, f, gd, o.stp);
+  }
+  if (st == LS_CONTINUE && o.nls < 20) {
+LB_UNROLL
+    for (int j = 0; j < DT; ++j) o.x[j] = o.xb[j] + o.stp * o.d[j];
+    o.status = LB_EVAL;
+    return o.status;
+  }
+  if (st != LS_CONVERGED && st != LS_WARNING) {
+LB_UNROLL
+    for (int j = 0; j < DT; ++j) { o.x[j] = o.xb[j]; o.g[j] = o.gb[j]; }
+    o.f = o.fb;
+    if (o.col == 0) { o.status = LB_ABNORMAL; return o.status; }
+    o.col = 0; o.head = 0;
+    lb_begin_search_t<DT>(o);
+    return o.status;
+  }
+  o.iter++;
+  double s[DT], y[DT];
+  double sy = 0, yy = 0;
+LB_UNROLL
+  for (int j = 0; j < DT; ++j) {
+    s[j] = o.x[j] - o.xb[j];
+    y[j] = g[j] - o.gb[j];
+    sy += s[j] * y[j]; yy += y[j] * y[j];
+  }
+  const double fold = o.fb;
+  o.f = f;
+  double pg = 0;
+LB_UNROLL
+  for (int j = 0; j < DT; ++j) { o.g[j] = g[j]; pg = fmax(pg, fabs(g[j])); }
+  if (pg <= 0.0) { o.status = LB_ZEROGRAD; return o.status; }
+  const double ddum = fmax(fmax(fabs(fold), fabs(f)), 1.0);
+  if (fold - f <= epsmch * o.factr * ddum) { o.status = LB_CONVERGED; return o.status; }
+  if (o.iter >= o.maxit) { o.status = LB_MAXIT; return o.status; }
+  const double ddum2 = -o.gdold * o.stp;
+  if (sy > epsmch * ddum2 && yy > 0.0) {
+    int p;
+    if (o.col < LB_MEM) { p = o.head + o.col; if (p >= LB_MEM) p -= LB_MEM; o.col++; }
+    else { p = o.head; o.head = (o.head + 1 == LB_MEM) ? 0 : o.head + 1; }
+LB_UNROLL
+    for (int j = 0; j < DT; ++j) { o.S[p][j] = s[j]; o.Y[p][j] = y[j]; }
+    o.rho[p] = 1.0 / sy;
+  }
+  lb_begin_search_t<DT>(o);
+  return o.status;
+}
+
+// Every device-side caller optimises three hyper-parameters; the host also runs D = 2 (per-cluster theta_k with a fixed noise).
+MCB_HD int lb_advance(Lbfgs& o, double f, const double* g) {
+#if defined(__CUDA_ARCH__) && !defined(MCB_LBFGS_ANYD)
+  return lb_advance_t<3>(o, f, g);   // D == 3 is the only size the kernels set up (lb_init(.., 3, ..))
+#else
+  if (o.D == 3) return lb_advance_t<3>(o, f, g);
+  if (o.D == 2) return lb_advance_t<2>(o, f, g);
+  return lb_advance_any(o, f, g);
+#endif
 }
 
 }  // namespace mcb

@@ -136,9 +136,15 @@ def test_m_step_with_more_than_eight_clusters(session):
         assert np.allclose(new_got["theta_k"][k], new_ref["theta_k"][k], atol=5e-3), k
     th_g = next(iter(new_got["theta_k"].values()))
     th_r = next(iter(new_ref["theta_k"].values()))
-    f_g = O.logL_GP_mod_common_hp_k(th_g[:2], ref["mean"], m_k, O.kernel_mu, ref["cov"], th_g[2])
+    # The third entry is pen_diag = mean_i theta_i[3] (CF.R:666-668), i.e. an OUTPUT of the 27 per-individual optimisations,
+    # whose end points move in the 7th digit from run to run (atomic scatter in the E-step, DESIGN "Run-to-run
+    # reproducibility"): measured over 24 runs |pen_g - pen_r| <= 3e-7, which alone moves this objective by +-1.2e-5
+    # relative (gpurun_out/r02s3_flaky.log). So the (a, b) optimum is compared at ONE value of pen_diag, and pen_diag itself
+    # separately.
+    assert abs(th_g[2] - th_r[2]) < 1e-5
+    f_g = O.logL_GP_mod_common_hp_k(th_g[:2], ref["mean"], m_k, O.kernel_mu, ref["cov"], th_r[2])
     f_r = O.logL_GP_mod_common_hp_k(th_r[:2], ref["mean"], m_k, O.kernel_mu, ref["cov"], th_r[2])
-    assert f_g <= f_r + 1e-5 * abs(f_r)   # the GPU optimum is not worse (it may be slightly better: end points are loose)
+    assert f_g <= f_r + 1e-6 * abs(f_r)   # the GPU optimum is not worse (it may be slightly better: end points are loose)
 
 
 def test_per_individual_optimiser_outcomes_are_reported(session):

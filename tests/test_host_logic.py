@@ -101,6 +101,70 @@ def test_lbfgs_header_follows_lbfgsb_trajectory():
     assert np.allclose(x, r.x, rtol=0, atol=1e-9)
 
 
+LBFGS_TWIN_DRIVER = r"""
+#include "lbfgs.h"
+#include <cstdio>
+#include <cstring>
+#include <random>
+using namespace mcb;
+static int D;
+static double A[3][3], bvec[3], c4, wall;
+static void fg(const double* x, double& f, double* g) {
+  f = 0; for (int i = 0; i < D; ++i) g[i] = 0;
+  for (int i = 0; i < D; ++i) {
+    double ax = 0; for (int j = 0; j < D; ++j) ax += A[i][j] * x[j];
+    f += 0.5 * x[i] * ax - bvec[i] * x[i]; g[i] += ax - bvec[i];
+  }
+  for (int i = 0; i + 1 < D; ++i) { double a = x[i + 1] - x[i] * x[i]; f += c4 * a * a; g[i] += -4 * c4 * x[i] * a; g[i + 1] += 2 * c4 * a; }
+  // outside the wall the objective is not finite (a covariance that stopped being positive definite): bisection branch
+  for (int i = 0; i < D; ++i) if (fabs(x[i]) > wall) f = INFINITY;
+}
+int main() {
+  std::mt19937_64 rng(5); std::normal_distribution<double> nd;
+  int mism = 0, runs = 0, status_seen[8] = {0}; long long evals = 0;
+  for (int rep = 0; rep < 4000; ++rep) {
+    D = 2 + rep % 2;
+    double R[3][3]; for (auto& r : R) for (auto& v : r) v = nd(rng);
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) { A[i][j] = (i == j) ? 0.3 : 0.0; for (int k = 0; k < 3; ++k) A[i][j] += R[i][k] * R[j][k]; }
+    for (auto& v : bvec) v = nd(rng);
+    c4 = (rep % 3 == 0) ? 0.0 : 5.0 * fabs(nd(rng));
+    wall = (rep % 5 == 0) ? 2.5 : 1e300;
+    double x0[3] = {nd(rng), nd(rng), nd(rng)};
+    Lbfgs a, b; memset(&a, 0, sizeof a); memset(&b, 0, sizeof b);
+    lb_init(a, D, x0, 100); lb_init(b, D, x0, 100);
+    double f, g[3]; int sa = LB_EVAL, sb = LB_EVAL, n = 0;
+    while (sa == LB_EVAL && n < 5000) {
+      fg(a.x, f, g); sa = lb_advance_any(a, f, g);
+      fg(b.x, f, g); sb = lb_advance(b, f, g);
+      ++n;
+      if (sa != sb || memcmp(a.x, b.x, sizeof(double) * D) || a.col != b.col || a.iter != b.iter || a.nfev != b.nfev) { ++mism; break; }
+    }
+    if (memcmp(&a.f, &b.f, 8)) ++mism;
+    ++status_seen[sa & 7]; ++runs; evals += n;
+  }
+  printf("%d %d %lld", runs, mism, evals);
+  for (int s = 0; s < 6; ++s) printf(" %d", status_seen[s]);
+  printf("\n");
+  return 0;
+}
+"""
+
+
+def test_compile_time_d_lbfgs_walks_the_same_trajectory_as_the_generic_one():
+    """lbfgs.h: lb_advance (D and the memory depth compile-time constants: the form the kernels run) against lb_advance_any
+    (run-time D) on 4000 random problems, D = 2 and 3, a fifth of them with a non-finite region: identical iterates, counts
+    and end states, bit for bit"""
+    with tempfile.TemporaryDirectory() as td:
+        src = os.path.join(td, "t.cpp")
+        open(src, "w").write(LBFGS_TWIN_DRIVER)
+        exe = os.path.join(td, "t")
+        subprocess.run(["g++", "-O2", "-std=c++17", "-I", os.path.join(ROOT, "magmaclust_b200", "csrc"), "-o", exe, src], check=True)
+        out = [int(v) for v in subprocess.run([exe], check=True, capture_output=True, text=True).stdout.split()]
+    runs, mism, evals = out[:3]
+    assert runs == 4000 and mism == 0 and evals > 20000
+    assert out[3 + 1] > 3000          # most runs converge (LB_CONVERGED = 1)
+
+
 def test_synth_configs_have_the_named_shapes():
     from magmaclust_b200 import synth
     ds = synth.config("C1")
