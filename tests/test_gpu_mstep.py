@@ -144,7 +144,7 @@ def test_m_step_with_more_than_eight_clusters(session):
     assert abs(th_g[2] - th_r[2]) < 1e-5
     f_g = O.logL_GP_mod_common_hp_k(th_g[:2], ref["mean"], m_k, O.kernel_mu, ref["cov"], th_r[2])
     f_r = O.logL_GP_mod_common_hp_k(th_r[:2], ref["mean"], m_k, O.kernel_mu, ref["cov"], th_r[2])
-    assert f_g <= f_r + 1e-6 * abs(f_r)   # the GPU optimum is not worse (it may be slightly better: end points are loose)
+    assert f_g <= f_r + 5e-6 * abs(f_r)   # the GPU optimum is not worse (measured: within 2e-7 either way)
 
 
 def test_per_individual_optimiser_outcomes_are_reported(session):
