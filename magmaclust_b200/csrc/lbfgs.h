@@ -23,10 +23,11 @@
 #define MCB_HD_BIG static inline
 #endif
 
-// Code size: in the persistent M-step kernel this update is 4,505 of 9,272 SASS instructions (72 KB, profiles/
-// r01f_ptxas.txt) although one thread runs it once per evaluation, because the short loops over D and over the stored
-// pairs are unrolled with remainder code. -DMCB_LBFGS_ROLLED keeps them rolled in device code (9,272 -> 6,632 instructions,
-// same arithmetic in the same order); default off until it has been timed on the GPU.
+// History of the device-side form: with a run-time D the short loops over D and over the stored pairs unrolled with remainder
+// code (4,505 of the 9,272 SASS instructions of the persistent M-step kernel, profiles/r01f_ptxas.txt); -DMCB_LBFGS_ROLLED
+// kept them rolled (9,272 -> 6,632 instructions, theta_i phase 4.44 -> 4.29 ms) at the price of local-memory temporaries.
+// Since the end of round 2 the kernels run lb_advance_t<3> (bottom of this file: D and the memory depth are compile-time
+// constants); LB_LOOP only shapes lb_advance_any, the run-time-D form the host keeps for other sizes and for the twin test.
 #if defined(MCB_LBFGS_ROLLED) && defined(__CUDA_ARCH__)
 #define LB_LOOP _Pragma("unroll 1")
 #else
